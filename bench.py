@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: FIR Msamples/s (cf32, 256 taps) on 1/2/4/8 B200.
+
+One "step" = one pass of the /comms/fir_filter hot path over one batch of synthetic
+tone+noise input (per GPU: 2^28 complex-float32 samples = 2 GiB in + 2 GiB out, far larger
+than the 126 MB L2, so nothing is cache-resident between steps).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the reference's CPU path on the host cores
+
+Multi-GPU (N>1): ONE long stream of N*2^28 samples is split into contiguous segments, one per
+rank; before every pass rank r sends the last K-1 samples of its segment to rank r+1
+(NCCL P2P over NVLink) -- the only exchange the path has.  Weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "FIR Msamples/s (cf32, 256 taps)"
+UNIT = "Msamples/s"
+
+WORKLOADS = {
+    # name: (dtype name, taps config, decim, interp, log2 samples per GPU, bytes/input sample (algorithmic))
+    "headline": ("complex_float32", "headline", 1, 1, 28, 16.0),
+    "c1": ("complex_float32", "c1", 1, 1, 28, 16.0),
+    "c1_real": ("complex_float32", "c1_real", 1, 1, 28, 16.0),
+    "c2": ("complex_int16", "c2", 1, 1, 28, 8.0),
+    "c3": ("complex_float32", "c3", 2, 3, 28, 20.0),
+    "c5": ("complex_float32", "c5", 1, 1, 26, 16.0),
+}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def cpu_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_sample(wl_name: str, threads: int, log2_per_thread: int = 21, repeats: int = 1):
+    """Times the FIR oracle port (kind "port": the reference FIR block needs PothosCore and
+    cannot be compiled) on a bounded sample of the workload with `threads` host threads."""
+    import numpy as np
+
+    import oracle
+    from pothoscomms_b200 import workloads as wl
+    dt_name, taps_name, M, L, _, _ = WORKLOADS[wl_name]
+    code = oracle.DTYPE_CODES[dt_name]
+    taps, tt = wl.config_taps(taps_name)
+    n = threads << log2_per_thread
+    x = wl.tone_noise_numpy(code, min(n, 1 << 22), seed=0xC0FFEE01)
+    if x.shape[0] < n:
+        x = np.tile(x, (n // x.shape[0], 1))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, cons, _ = oracle.fir(code, tt == "COMPLEX", taps, M, L, x, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return cons / best / 1e6, cons, best
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores
+    (the oracle port of filter/FIRFilter.cpp:278-302 -- the block itself cannot be compiled
+    without PothosCore), all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = cpu_threads()
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_sample(args.workload, threads, log2_per_thread=18)
+    total_s, total_n = 0.0, 0
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        _, cons, dt = run_cpu_sample(args.workload, threads, log2_per_thread=20)
+        total_s += dt
+        total_n += cons
+    value = total_n / total_s / 1e6
+    dt_name, taps_name, M, L, _, _ = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": total_s / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: /comms/fir_filter {dt_name} 256 COMPLEX taps decim={M} interp={L}",
+                   "sample": f"{threads} threads x 2^20 samples per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{threads} x 2^20 samples per step, {steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2-samples", type=int, default=None, help="override samples per GPU (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pothoscomms_b200 import FirFilter
+    from pothoscomms_b200 import workloads as wl
+    from pothoscomms_b200.handles import dtype_code
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dt_name, taps_name, M, L, log2n, bytes_per_sample = WORKLOADS[args.workload]
+    if args.log2_samples:
+        log2n = args.log2_samples
+    code = dtype_code(dt_name)
+    taps, tt = wl.config_taps(taps_name)
+    fir = FirFilter(code, tt, device=local_rank)
+    fir.set_taps(taps)
+    fir.set_rates(M, L)
+    K = fir.K
+    n_seg = (1 << log2n) // M * M           # new samples per rank and step (multiple of M: SURVEY 8e)
+    nc = 2
+
+    # [K-1 halo | n_seg samples]; rank r's segment is samples [r*n_seg, (r+1)*n_seg) of one stream
+    buf = torch.empty((K - 1 + n_seg, nc), dtype=wl.tone_noise_torch(code, 1, 0, dev).dtype, device=dev)
+    buf[K - 1:] = wl.tone_noise_torch(code, n_seg, 0xC0FFEE01 + rank, dev)
+    buf[: K - 1] = 0   # rank 0: the stream's first K-1 samples are history only (FIRFilter.cpp:281)
+    out_cap = n_seg // M * L
+    out = torch.empty((out_cap, nc), dtype=buf.dtype, device=dev)
+    torch.cuda.synchronize()
+
+    def halo_exchange():
+        if world == 1:
+            return
+        ops = []
+        if rank + 1 < world:
+            ops.append(dist.P2POp(dist.isend, buf[n_seg: n_seg + K - 1], rank + 1))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, buf[: K - 1], rank - 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def step():
+        halo_exchange()
+        _, cons, prod = fir.run(buf, out=out, out_capacity=out_cap)
+        return cons, prod
+
+    for _ in range(args.warmup):
+        cons, prod = step()
+    torch.cuda.synchronize()
+    assert cons == n_seg and prod == out_cap, (cons, prod, n_seg, out_cap)
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        halo_exchange()
+        kev[i][0].record()
+        fir.run(buf, out=out, out_capacity=out_cap)
+        kev[i][1].record()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kernel_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = t.tolist()
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n_seg / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H timed) ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((K - 1 + n_seg, nc), dtype=buf.dtype).pin_memory()
+        h_out = torch.empty((out_cap, nc), dtype=buf.dtype).pin_memory()
+        h_in.copy_(buf)
+        x_np, y_np = h_in.numpy(), h_out.numpy()
+        e2e_steps = max(3, min(args.steps, 5))
+        fir.run_host(x_np, out=y_np, out_capacity=out_cap)   # warm-up (allocates the staging slots)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fir.run_host(x_np, out=y_np, out_capacity=out_cap)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = t.item()
+        # the host path must agree with the resident path
+        assert torch.equal(h_out[:4096], out[:4096].cpu()) if world == 1 else True
+        e2e = {"value": world * n_seg / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * h_in.element_size()),
+               "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()), "steps": e2e_steps}
+        del h_in, h_out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_kind = measured_peaks()
+    algo_bytes = bytes_per_sample * n_seg
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
+                "kernel": "fir_tile_kernel", "kernel_ms": kernel_ms,
+                "note": "FFMA-issue bound at 256 complex taps (2048 flop/sample); see DESIGN.md"}
+    flops = {"c1": 512, "c1_real": 256, "headline": 2048, "c3": 510, "c5": 8192}.get(args.workload)
+    if flops:
+        roofline["fp32_tflops"] = flops * n_seg / (kernel_ms * 1e-3) / 1e12
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = cpu_threads()
+        v, cons_cpu, secs = run_cpu_sample(args.workload, threads, log2_per_thread=21)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{threads} threads x 2^21 samples of the same workload ({secs:.1f} s)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if code in (0, 1) else dt_name, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: /comms/fir_filter {dt_name} {len(taps)} {tt} taps decim={M} interp={L}, "
+                               f"2^{log2n} samples per GPU tone+noise, one stream split in contiguous segments with K-1 halo",
+                   "samples_per_gpu": n_seg, "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per pass)"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the /comms/fir_filter + /comms/fft hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product (``pothoscomms_b200``) never
+does; it fails loudly if its CUDA library is missing instead of falling back to this.
+
+* ``fir(...)``      : C restatement of filter/FIRFilter.cpp:278-302,327-354 (``liboracle.so``).
+                      The FIR block cannot be compiled here (PothosCore absent) => kind "port";
+                      Q-format rounding is PARITY UNPINNED (see qformat.h).
+* ``fft(...)``      : C restatement of fft/kissfft.hh + fft/kiss_fft.c (``liboracle.so``), pinned
+                      bit-for-bit against ``ref_fft``.
+* ``ref_fft(...)``  : the REFERENCE's own kiss_fft sources compiled from /root/reference into
+                      ``oracle/_ref/libkissref.so`` (git-ignored, travels to the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# dtype codes shared with include/b200comms.h
+F32, CF32, F64, CF64, I8, CI8, I16, CI16, I32, CI32, I64, CI64 = range(12)
+DTYPE_CODES = {
+    "float32": F32, "complex_float32": CF32, "float64": F64, "complex_float64": CF64,
+    "int8": I8, "complex_int8": CI8, "int16": I16, "complex_int16": CI16,
+    "int32": I32, "complex_int32": CI32, "int64": I64, "complex_int64": CI64,
+}
+_SCALAR_NP = {0: np.float32, 1: np.float64, 2: np.int8, 3: np.int16, 4: np.int32, 5: np.int64}
+
+
+def scalar_np(dtype_code: int):
+    return _SCALAR_NP[dtype_code >> 1]
+
+
+def is_complex(dtype_code: int) -> bool:
+    return bool(dtype_code & 1)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    lib = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "qformat.h", "Makefile")]
+    stale = force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
+    ref = os.path.join(_HERE, "_ref", "libkissref.so")
+    if stale or (not os.path.exists(ref) and os.path.exists("/root/reference/fft/kiss_fft.c")):
+        subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True, capture_output=True)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(os.path.join(_HERE, "liboracle.so"))
+        sz, vp, i = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
+        _lib.oracle_fir_run.argtypes = [i, i, vp, sz, sz, sz, vp, sz, vp, sz, i, vp, vp]
+        _lib.oracle_fir_run_mt.argtypes = [i, i, i, vp, sz, sz, sz, vp, sz, vp, sz, vp, vp]
+        _lib.oracle_fir_K.argtypes = [sz, sz]
+        _lib.oracle_fir_K.restype = sz
+        _lib.oracle_fir_phase_taps.argtypes = [i, i, vp, sz, sz, vp, vp]
+        _lib.oracle_fft.argtypes = [i, sz, i, vp, vp, sz]
+        _lib.oracle_fft_plan.argtypes = [i, i, vp, vp]
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libkissref.so"))
+
+
+def ref():
+    """The reference's own FFT sources, compiled (oracle/_ref)."""
+    global _ref
+    if _ref is None:
+        build()
+        _ref = ctypes.CDLL(os.path.join(_HERE, "_ref", "libkissref.so"))
+        sz, vp, i = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
+        _ref.ref_fft.argtypes = [i, sz, i, vp, vp, sz]
+        _ref.ref_fft_mt.argtypes = [i, i, sz, i, vp, vp, sz]
+    return _ref
+
+
+def _as_taps(taps, taps_complex: bool) -> np.ndarray:
+    if taps_complex:
+        t = np.ascontiguousarray(np.asarray(taps, dtype=np.complex128))
+        return t.view(np.float64)
+    return np.ascontiguousarray(np.asarray(taps, dtype=np.float64))
+
+
+def to_raw(x: np.ndarray, dtype_code: int) -> np.ndarray:
+    """Interleaved scalar view [n, ncomp] of a numpy array for ``dtype_code``."""
+    sc = scalar_np(dtype_code)
+    if is_complex(dtype_code):
+        if np.iscomplexobj(x):
+            if sc in (np.float32, np.float64):
+                return np.ascontiguousarray(x.astype(np.complex64 if sc == np.float32 else np.complex128)).view(sc).reshape(-1, 2)
+            out = np.empty((x.size, 2), dtype=sc)
+            out[:, 0] = x.real
+            out[:, 1] = x.imag
+            return out
+        x = np.ascontiguousarray(x, dtype=sc)
+        return x.reshape(-1, 2)
+    return np.ascontiguousarray(x, dtype=sc).reshape(-1, 1)
+
+
+def fir_K(ntaps: int, interp: int) -> int:
+    return int(lib().oracle_fir_K(ntaps, interp))
+
+
+def fir(dtype_code: int, taps_complex: bool, taps, decim: int, interp: int, x_raw: np.ndarray,
+        out_capacity: int | None = None, zero_tail: bool = False, threads: int = 1):
+    """One work() call.  ``x_raw`` is [n, ncomp] scalars: K-1 history elements then new data.
+    Returns (out_raw [produced, ncomp], consumed, produced)."""
+    t = _as_taps(taps, taps_complex)
+    ntaps = t.size // (2 if taps_complex else 1)
+    ncomp = 2 if is_complex(dtype_code) else 1
+    x_raw = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code)).reshape(-1, ncomp)
+    n_in = x_raw.shape[0]
+    K = fir_K(ntaps, interp)
+    if out_capacity is None:
+        out_capacity = ((n_in + (K - 1 if zero_tail else 0)) // decim + 1) * interp
+    out = np.zeros((max(out_capacity, 1), ncomp), dtype=x_raw.dtype)
+    cons, prod = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    if threads > 1 and not zero_tail:
+        rc = lib().oracle_fir_run_mt(threads, dtype_code, int(taps_complex), t.ctypes.data, ntaps, decim, interp,
+                                     x_raw.ctypes.data, n_in, out.ctypes.data, out_capacity,
+                                     ctypes.addressof(cons), ctypes.addressof(prod))
+    else:
+        rc = lib().oracle_fir_run(dtype_code, int(taps_complex), t.ctypes.data, ntaps, decim, interp,
+                                  x_raw.ctypes.data, n_in, out.ctypes.data, out_capacity, int(zero_tail),
+                                  ctypes.addressof(cons), ctypes.addressof(prod))
+    if rc != 0:
+        raise ValueError("oracle_fir_run: invalid arguments")
+    return out[: prod.value], cons.value, prod.value
+
+
+def fir_phase_taps(dtype_code: int, taps_complex: bool, taps, interp: int):
+    t = _as_taps(taps, taps_complex)
+    tc = 2 if taps_complex else 1
+    ntaps = t.size // tc
+    K = fir_K(ntaps, interp)
+    out = np.zeros((interp, K, tc), dtype=np.float64)
+    nt = np.zeros(interp, dtype=np.uintp)
+    rc = lib().oracle_fir_phase_taps(dtype_code, int(taps_complex), t.ctypes.data, ntaps, interp,
+                                     out.ctypes.data, nt.ctypes.data)
+    if rc != 0:
+        raise ValueError("oracle_fir_phase_taps: invalid arguments")
+    return out, nt
+
+
+def _fft_call(fn, dtype_code, nbins, inverse, x_raw, *pre):
+    ncomp = 2
+    x_raw = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code)).reshape(-1, ncomp)
+    batch = x_raw.shape[0] // nbins
+    out = np.zeros_like(x_raw[: batch * nbins])
+    rc = fn(*pre, dtype_code, nbins, int(inverse), x_raw.ctypes.data, out.ctypes.data, batch)
+    if rc != 0:
+        raise ValueError("fft oracle: unsupported dtype")
+    return out
+
+
+def fft(dtype_code: int, nbins: int, inverse: bool, x_raw: np.ndarray) -> np.ndarray:
+    """floor(len/nbins) transforms with the restated kiss_fft."""
+    return _fft_call(lib().oracle_fft, dtype_code, nbins, inverse, x_raw)
+
+
+def ref_fft(dtype_code: int, nbins: int, inverse: bool, x_raw: np.ndarray, threads: int = 1) -> np.ndarray:
+    """floor(len/nbins) transforms with the reference's own compiled kiss_fft."""
+    if threads > 1:
+        return _fft_call(ref().ref_fft_mt, dtype_code, nbins, inverse, x_raw, threads)
+    return _fft_call(ref().ref_fft, dtype_code, nbins, inverse, x_raw)
+
+
+def fft_plan(nbins: int, fixed: bool):
+    radix = (ctypes.c_int * 64)()
+    rem = (ctypes.c_int * 64)()
+    n = lib().oracle_fft_plan(nbins, int(fixed), ctypes.addressof(radix), ctypes.addressof(rem))
+    return list(radix[:n]), list(rem[:n])

@@ -1,0 +1,363 @@
+// sm_100a batched FFT kernels for /comms/fft.
+// Replaces FFT<Type>::work() -> FFTAux::transform (fft/FFT.cpp:61-72, fft/FFTAux.h:21-44),
+// i.e. kissfft<T> (fft/kissfft.hh) for cf32/cf64 and the Q15 C kiss_fft (fft/kiss_fft.c built
+// with FIXED_POINT=16) for complex int16.
+//
+// The reference recurses (decimation in time); here every transform is done ITERATIVELY by
+// one CTA (or a fraction of one): a mixed-radix digit-reversal scatter into shared memory,
+// then the radix stages innermost first, each element seeing exactly the reference's
+// sequence of arithmetic -- which is what makes the int16 path bit-exact (per-stage
+// C_FIXDIV 1/radix scaling, Q15 C_MUL with sround, int16 wrap on every add).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <type_traits>
+
+#include "fft.hpp"
+
+namespace b200c {
+
+// ---------------------------------------------------------------- element arithmetic ---
+template <typename T> struct FloatTraits {
+    using E = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+    using Sc = T;
+    static constexpr bool kFixed = false;
+    __device__ static E mk(T r, T i) { E e; e.x = r; e.y = i; return e; }
+    __device__ static E add(E a, E b) { return mk(a.x + b.x, a.y + b.y); }
+    __device__ static E sub(E a, E b) { return mk(a.x - b.x, a.y - b.y); }
+    __device__ static E mul(E a, E b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+    __device__ static E fixdiv(E a, int) { return a; }
+    __device__ static T smul(T a, T b) { return a * b; }
+    __device__ static T half(T a) { return a * (T)0.5; }
+    __device__ static T wrap(T a) { return a; }
+};
+
+struct Q15Traits {   // fft/_kiss_fft_guts.h:44-124 with FIXED_POINT=16
+    using E = short2;
+    using Sc = int;  // int16 values carried in 32-bit registers, wrapped at every assignment
+    static constexpr bool kFixed = true;
+    __device__ static int wrap(int a) { return (int)(short)a; }
+    __device__ static int sround(int x) { return (int)(short)((x + (1 << 14)) >> 15); }
+    __device__ static E mk(int r, int i) { E e; e.x = (short)r; e.y = (short)i; return e; }
+    __device__ static E add(E a, E b) { return mk((int)a.x + b.x, (int)a.y + b.y); }
+    __device__ static E sub(E a, E b) { return mk((int)a.x - b.x, (int)a.y - b.y); }
+    __device__ static E mul(E a, E b)
+    {
+        return mk(sround((int)((unsigned)((int)a.x * b.x) - (unsigned)((int)a.y * b.y))),
+                  sround((int)((unsigned)((int)a.x * b.y) + (unsigned)((int)a.y * b.x))));
+    }
+    __device__ static E fixdiv(E a, int div)
+    {
+        const int f = 32767 / div;
+        return mk(sround((int)a.x * f), sround((int)a.y * f));
+    }
+    __device__ static int smul(int a, int b) { return sround(a * b); }
+    __device__ static int half(int a) { return a >> 1; }
+};
+
+// radix-2/3/4/5 butterflies on F[0], F[m], ... with twiddles tw[q*tws]
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly2(E *F, int m, const E *__restrict__ tw, int tws)
+{
+    E f0 = Tr::fixdiv(F[0], 2), f1 = Tr::fixdiv(F[m], 2);
+    const E t = Tr::mul(f1, tw[tws]);
+    F[m] = Tr::sub(f0, t);
+    F[0] = Tr::add(f0, t);
+}
+
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly4(E *F, int m, const E *__restrict__ tw, int tws, int inverse)
+{
+    E f0 = Tr::fixdiv(F[0], 4), f1 = Tr::fixdiv(F[m], 4), f2 = Tr::fixdiv(F[2 * m], 4), f3 = Tr::fixdiv(F[3 * m], 4);
+    const E s0 = Tr::mul(f1, tw[tws]);
+    const E s1 = Tr::mul(f2, tw[2 * tws]);
+    const E s2 = Tr::mul(f3, tw[3 * tws]);
+    const E s5 = Tr::sub(f0, s1);
+    f0 = Tr::add(f0, s1);
+    const E s3 = Tr::add(s0, s2);
+    const E s4 = Tr::sub(s0, s2);
+    F[2 * m] = Tr::sub(f0, s3);
+    F[0] = Tr::add(f0, s3);
+    // forward: F[m] = s5 + (s4.i, -s4.r), F[3m] = s5 - (s4.i, -s4.r); inverse swaps the two
+    const E rot = Tr::mk(s4.y, Tr::wrap(-s4.x));   // wrap(-x) only matters mod 2^16 below
+    if (inverse) { F[m] = Tr::sub(s5, rot); F[3 * m] = Tr::add(s5, rot); }
+    else { F[m] = Tr::add(s5, rot); F[3 * m] = Tr::sub(s5, rot); }
+}
+
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly3(E *F, int m, const E *__restrict__ tw, int tws, E epi3)
+{
+    E f0 = Tr::fixdiv(F[0], 3), f1 = Tr::fixdiv(F[m], 3), f2 = Tr::fixdiv(F[2 * m], 3);
+    const E s1 = Tr::mul(f1, tw[tws]);
+    const E s2 = Tr::mul(f2, tw[2 * tws]);
+    const E s3 = Tr::add(s1, s2);
+    E s0 = Tr::sub(s1, s2);
+    f1 = Tr::mk(f0.x - Tr::half(s3.x), f0.y - Tr::half(s3.y));
+    s0 = Tr::mk(Tr::smul(s0.x, epi3.y), Tr::smul(s0.y, epi3.y));
+    f0 = Tr::add(f0, s3);
+    f2 = Tr::mk(f1.x + s0.y, f1.y - s0.x);
+    f1 = Tr::mk(f1.x - s0.y, f1.y + s0.x);
+    F[0] = f0; F[m] = f1; F[2 * m] = f2;
+}
+
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly5(E *F, int m, const E *__restrict__ tw, int tws, E ya, E yb)
+{
+    using Sc = typename Tr::Sc;
+    E f0 = Tr::fixdiv(F[0], 5), f1 = Tr::fixdiv(F[m], 5), f2 = Tr::fixdiv(F[2 * m], 5), f3 = Tr::fixdiv(F[3 * m], 5),
+      f4 = Tr::fixdiv(F[4 * m], 5);
+    const E c0 = f0;
+    const E c1 = Tr::mul(f1, tw[tws]);
+    const E c2 = Tr::mul(f2, tw[2 * tws]);
+    const E c3 = Tr::mul(f3, tw[3 * tws]);
+    const E c4 = Tr::mul(f4, tw[4 * tws]);
+    const E c7 = Tr::add(c1, c4), c10 = Tr::sub(c1, c4), c8 = Tr::add(c2, c3), c9 = Tr::sub(c2, c3);
+    if constexpr (Tr::kFixed) {
+        f0 = Tr::mk((Sc)f0.x + ((Sc)c7.x + c8.x), (Sc)f0.y + ((Sc)c7.y + c8.y));
+    } else {
+        f0 = Tr::add(f0, c7);
+        f0 = Tr::add(f0, c8);
+    }
+    const E c5 = Tr::mk((Sc)c0.x + (Tr::smul(c7.x, ya.x) + Tr::smul(c8.x, yb.x)),
+                        (Sc)c0.y + (Tr::smul(c7.y, ya.x) + Tr::smul(c8.y, yb.x)));
+    const E c6 = Tr::mk(Tr::smul(c10.y, ya.y) + Tr::smul(c9.y, yb.y),
+                        -Tr::smul(c10.x, ya.y) - Tr::smul(c9.x, yb.y));
+    F[m] = Tr::sub(c5, c6);
+    F[4 * m] = Tr::add(c5, c6);
+    const E c11 = Tr::mk((Sc)c0.x + (Tr::smul(c7.x, yb.x) + Tr::smul(c8.x, ya.x)),
+                         (Sc)c0.y + (Tr::smul(c7.y, yb.x) + Tr::smul(c8.y, ya.x)));
+    const E c12 = Tr::mk(-Tr::smul(c10.y, yb.y) + Tr::smul(c9.y, ya.y),
+                         Tr::smul(c10.x, yb.y) - Tr::smul(c9.x, ya.y));
+    F[2 * m] = Tr::add(c11, c12);
+    F[3 * m] = Tr::sub(c11, c12);
+    F[0] = f0;
+}
+
+struct FftArgs {
+    const void *in;
+    void *out;
+    const void *tw;
+    const int *scatter;
+    void *scratch;
+    long long batch;
+    int n, inverse, nstages, tpc, has_generic;
+    int radix[24], rem[24];
+};
+
+template <typename Tr, bool SMEM>
+__global__ void __launch_bounds__(256) fft_staged_kernel(const FftArgs a)
+{
+    using E = typename Tr::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, tid = threadIdx.x, nthr = blockDim.x;
+    const E *__restrict__ tw = static_cast<const E *>(a.tw);
+    const long long ngroups = (a.batch + a.tpc - 1) / a.tpc;
+
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long first = grp * a.tpc;
+        const int nt = (int)((a.batch - first) < a.tpc ? (a.batch - first) : a.tpc);
+        const int total = nt * n;
+        const E *in = static_cast<const E *>(a.in) + first * n;
+        E *out = static_cast<E *>(a.out) + first * n;
+        E *F, *scr;
+        if constexpr (SMEM) {
+            F = reinterpret_cast<E *>(smem_raw);
+            scr = F + (size_t)a.tpc * n;
+        } else {
+            F = out;
+            scr = static_cast<E *>(a.scratch) + (size_t)blockIdx.x * a.tpc * n;
+        }
+
+        // kf_work's leaf copy (fft/kissfft.hh:93-98, fft/kiss_fft.c:277-281) as a scatter
+        for (int i = tid; i < total; i += nthr) {
+            const int tb = i / n, ii = i - tb * n;
+            F[tb * n + a.scatter[ii]] = in[i];
+        }
+        __syncthreads();
+
+        for (int s = a.nstages - 1; s >= 0; s--) {
+            const int p = a.radix[s], m = a.rem[s], span = p * m, fstride = n / span;
+            if (p <= 5) {
+                const int per = n / p, nb = nt * per;
+                E e1 = Tr::mk(0, 0), e2 = Tr::mk(0, 0);
+                if (p == 3) e1 = tw[fstride * m];
+                if (p == 5) { e1 = tw[fstride * m]; e2 = tw[2 * fstride * m]; }
+                for (int b = tid; b < nb; b += nthr) {
+                    const int tb = b / per, bb = b - tb * per;
+                    const int g = bb / m, k = bb - g * m;
+                    E *Fb = F + tb * n + g * span + k;
+                    const int tws = k * fstride;
+                    if (p == 4) bfly4<Tr, E>(Fb, m, tw, tws, a.inverse);
+                    else if (p == 2) bfly2<Tr, E>(Fb, m, tw, tws);
+                    else if (p == 3) bfly3<Tr, E>(Fb, m, tw, tws, e1);
+                    else bfly5<Tr, E>(Fb, m, tw, tws, e1, e2);
+                }
+            } else {
+                // kf_bfly_generic (fft/kissfft.hh:263-303, fft/kiss_fft.c:199-235), one output per thread
+                for (int i = tid; i < total; i += nthr) scr[i] = Tr::fixdiv(F[i], p);
+                __syncthreads();
+                for (int i = tid; i < total; i += nthr) {
+                    const int tb = i / n, ii = i - tb * n;
+                    const int kk = ii % span, g0 = i - kk, u = kk % m;
+                    E acc = scr[g0 + u];
+                    int twidx = 0;
+                    for (int q = 1; q < p; q++) {
+                        twidx += fstride * kk;
+                        if (twidx >= n) twidx -= n;
+                        acc = Tr::add(acc, Tr::mul(scr[g0 + u + q * m], tw[twidx]));
+                    }
+                    F[i] = acc;
+                }
+            }
+            __syncthreads();
+        }
+
+        if constexpr (SMEM) {
+            for (int i = tid; i < total; i += nthr) out[i] = F[i];
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------ host: plan ---
+static int make_plan(FftPlan &p)
+{
+    // fft/kissfft.hh:38-55 (float/double) and fft/kiss_fft.c:308-330 (int16)
+    int n = p.n, r = 4, s = 0;
+    const double floor_sqrt = std::floor(std::sqrt((double)p.n));
+    do {
+        while (n % r) {
+            switch (r) { case 4: r = 2; break; case 2: r = 3; break; default: r += 2; break; }
+            if (p.dtype == B200C_CI16) { if (r > floor_sqrt) r = n; }
+            else { if ((long long)r * r > n) r = n; }
+        }
+        n /= r;
+        if (s >= 24) { set_error("FFT: too many radix stages"); return B200C_ERR_UNSUPPORTED; }
+        p.radix[s] = r; p.rem[s] = n; s++;
+    } while (n > 1);
+    p.nstages = s;
+    p.has_generic = false;
+    for (int i = 0; i < s; i++) if (p.radix[i] > 5) p.has_generic = true;
+    return B200C_OK;
+}
+
+int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t smem_budget)
+{
+    if (dtype != B200C_CF32 && dtype != B200C_CF64 && dtype != B200C_CI16) {
+        set_error("FFTFactory(dtype=%d): unsupported type", dtype);
+        return B200C_ERR_UNSUPPORTED;
+    }
+    if (nbins < 1 || nbins > (1u << 22)) { set_error("FFT: numBins %zu out of range [1, 2^22]", nbins); return B200C_ERR_INVALID; }
+    p.dtype = dtype; p.n = (int)nbins; p.inverse = inverse ? 1 : 0;
+    int rc = make_plan(p);
+    if (rc) return rc;
+    const int n = p.n;
+    const size_t esz = dtype_bytes(dtype);
+
+    // scatter[input index] = output slot  (inverse of the leaf-copy permutation)
+    std::vector<int> scatter(n);
+    for (int o = 0; o < n; o++) {
+        int remn = o, idx = 0, fstride = 1;
+        for (int s = 0; s < p.nstages; s++) {
+            const int k = remn / p.rem[s];
+            remn -= k * p.rem[s];
+            idx += k * fstride;
+            fstride *= p.radix[s];
+        }
+        scatter[idx] = o;
+    }
+
+    // twiddles
+    std::vector<uint8_t> tw((size_t)n * esz);
+    if (dtype == B200C_CF32) {
+        // fft/kissfft.hh:21-26: acos((T)-1) resolves to ::acos(double); phinc rounded once to
+        // float, phase i*phinc formed in float, std::exp(std::complex<float>)
+        const float phinc = (float)((inverse ? 2 : -2) * std::acos((double)-1) / n);
+        auto *t = reinterpret_cast<std::complex<float> *>(tw.data());
+        for (int i = 0; i < n; i++) t[i] = std::exp(std::complex<float>(0, i * phinc));
+    } else if (dtype == B200C_CF64) {
+        const double phinc = (inverse ? 2 : -2) * std::acos((double)-1) / n;
+        auto *t = reinterpret_cast<std::complex<double> *>(tw.data());
+        for (int i = 0; i < n; i++) t[i] = std::exp(std::complex<double>(0, i * phinc));
+    } else {
+        // fft/kiss_fft.c:357-363 + fft/_kiss_fft_guts.h:128-129
+        auto *t = reinterpret_cast<int16_t *>(tw.data());
+        for (int i = 0; i < n; i++) {
+            const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+            double phase = -2 * pi * i / n;
+            if (inverse) phase *= -1;
+            t[2 * i] = (int16_t)std::floor(.5 + 32767 * std::cos(phase));
+            t[2 * i + 1] = (int16_t)std::floor(.5 + 32767 * std::sin(phase));
+        }
+    }
+
+    B200C_CUDA_TRY(cudaMalloc(&p.d_tw, tw.size()));
+    B200C_CUDA_TRY(cudaMalloc((void **)&p.d_scatter, sizeof(int) * n));
+    B200C_CUDA_TRY(cudaMemcpy(p.d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice));
+    B200C_CUDA_TRY(cudaMemcpy(p.d_scatter, scatter.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+
+    // execution shape
+    const size_t bufs = p.has_generic ? 2 : 1;
+    p.tpc = std::max(1, 2048 / n);
+    p.smem_bytes = (size_t)p.tpc * n * esz * bufs;
+    p.smem = p.smem_bytes <= smem_budget;
+    if (!p.smem) { p.tpc = 1; p.smem_bytes = 0; }
+    const int work = p.tpc * n / 4;
+    p.threads = std::min(256, std::max(32, (work + 31) / 32 * 32));
+    return B200C_OK;
+}
+
+void fft_plan_destroy(FftPlan &p)
+{
+    if (p.d_tw) cudaFree(p.d_tw);
+    if (p.d_scatter) cudaFree(p.d_scatter);
+    if (p.d_scratch) cudaFree(p.d_scratch);
+    p.d_tw = nullptr; p.d_scatter = nullptr; p.d_scratch = nullptr;
+}
+
+template <typename Tr>
+static int launch_staged(FftPlan &p, const FftArgs &a, int grid, cudaStream_t stream)
+{
+    if (p.smem) {
+        auto kern = fft_staged_kernel<Tr, true>;
+        if (p.smem_bytes > 48 * 1024)
+            B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        kern<<<grid, p.threads, p.smem_bytes, stream>>>(a);
+    } else {
+        fft_staged_kernel<Tr, false><<<grid, p.threads, 0, stream>>>(a);
+    }
+    B200C_CUDA_TRY(cudaGetLastError());
+    return B200C_OK;
+}
+
+int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream)
+{
+    if (batch == 0) return B200C_OK;
+    if (d_in == d_out) { set_error("FFT: in-place transforms are not supported (d_in == d_out)"); return B200C_ERR_INVALID; }
+    FftArgs a;
+    a.in = d_in; a.out = d_out; a.tw = p.d_tw; a.scatter = p.d_scatter; a.scratch = nullptr;
+    a.batch = (long long)batch; a.n = p.n; a.inverse = p.inverse; a.nstages = p.nstages; a.tpc = p.tpc;
+    a.has_generic = p.has_generic ? 1 : 0;
+    for (int i = 0; i < p.nstages; i++) { a.radix[i] = p.radix[i]; a.rem[i] = p.rem[i]; }
+    const long long ngroups = ((long long)batch + p.tpc - 1) / p.tpc;
+    int grid = (int)std::min<long long>(ngroups, (long long)sm_count * 8);
+    if (!p.smem && p.has_generic) {
+        const size_t need = (size_t)grid * p.n * dtype_bytes(p.dtype);
+        if (need > p.scratch_bytes) {
+            B200C_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (p.d_scratch) cudaFree(p.d_scratch);
+            p.d_scratch = nullptr; p.scratch_bytes = 0;
+            B200C_CUDA_TRY(cudaMalloc(&p.d_scratch, need));
+            p.scratch_bytes = need;
+        }
+        a.scratch = p.d_scratch;
+    }
+    switch (p.dtype) {
+    case B200C_CF32: return launch_staged<FloatTraits<float>>(p, a, grid, stream);
+    case B200C_CF64: return launch_staged<FloatTraits<double>>(p, a, grid, stream);
+    default: return launch_staged<Q15Traits>(p, a, grid, stream);
+    }
+}
+
+} // namespace b200c

@@ -1,0 +1,39 @@
+// Host-side plan of one configured /comms/fft block (libb200comms.so).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "common.hpp"
+
+namespace b200c {
+
+// The radix plan and tables a reference FFTAux holds (fft/FFTAux.h:16-48):
+//   float/double: kissfft<T>::_twiddles/_stageRadix/_stageRemainder (fft/kissfft.hh:28-56,306-309)
+//   int16       : kiss_fft_state factors + Q15 twiddles (fft/kiss_fft.c:339-368)
+struct FftPlan {
+    int dtype = B200C_CF32;
+    int n = 0;
+    int inverse = 0;
+    int nstages = 0;
+    int radix[64];
+    int rem[64];          // m of each stage
+    bool has_generic = false;   // any radix outside {2,3,4,5}
+    // device tables
+    void *d_tw = nullptr;       // n twiddles in the element type
+    int *d_scatter = nullptr;   // scatter[i] = output slot o of input index i (inverse of kf_work's leaf copy)
+    // execution shape
+    int tpc = 1;                // transforms per CTA
+    int threads = 256;
+    bool smem = true;           // working buffer in shared memory (else: in d_out + scratch)
+    size_t smem_bytes = 0;
+    void *d_scratch = nullptr;  // generic-radix scratch for the global path
+    size_t scratch_bytes = 0;
+    int fast = 0;               // 0 = generic staged kernel, >0 = specialised kernel id
+};
+
+int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t smem_budget);
+void fft_plan_destroy(FftPlan &p);
+int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream);
+
+} // namespace b200c

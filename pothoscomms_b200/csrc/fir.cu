@@ -1,0 +1,440 @@
+// sm_100a FIR / polyphase-resampler kernels for /comms/fir_filter.
+// Replaces the scalar loop nest of filter/FIRFilter.cpp:286-302 (see fir.hpp for the
+// polyphase algebra).  Design:
+//   * one CTA = one tile of QT = 32*R*nrb output blocks; persistent grid-stride over tiles
+//   * the tile's input (+ history halo) is staged ONCE in shared memory, de-interleaved into
+//     the M decimation residues and already converted to the accumulator type
+//   * each thread owns R consecutive blocks of one output slot and runs a register
+//     sliding window over the staged samples: per tap step 1 shared load feeds R (complex)
+//     MACs; taps are warp-broadcast shared loads.  R is odd so lane strides of R elements
+//     are bank-conflict free without padding
+//   * results are transposed through shared memory so global stores are fully coalesced
+// Integer variants accumulate in wrapping 32/64-bit arithmetic exactly like the reference's
+// QType (filter/FIRFilter.cpp:377-382) and apply fromQ's arithmetic right shift on store.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "fir.hpp"
+
+namespace b200c {
+
+// ------------------------------------------------------------------------ type traits ---
+template <int DT> struct Dt;
+template <> struct Dt<0> { using S = float; using A = float;
+    __device__ static A ld(S s) { return s; } __device__ static S st(A a) { return a; } };
+template <> struct Dt<1> { using S = double; using A = double;
+    __device__ static A ld(S s) { return s; } __device__ static S st(A a) { return a; } };
+template <> struct Dt<2> { using S = int8_t; using A = uint32_t;   // QType int16: math mod 2^16, fromQ >> 8
+    __device__ static A ld(S s) { return (A)(int32_t)s; }
+    __device__ static S st(A a) { return (S)(((int32_t)(int16_t)(uint16_t)a) >> 8); } };
+template <> struct Dt<3> { using S = int16_t; using A = uint32_t;  // QType int32, fromQ >> 16
+    __device__ static A ld(S s) { return (A)(int32_t)s; }
+    __device__ static S st(A a) { return (S)(((int32_t)a) >> 16); } };
+template <> struct Dt<4> { using S = int32_t; using A = unsigned long long; // QType int64, fromQ >> 32
+    __device__ static A ld(S s) { return (A)(long long)s; }
+    __device__ static S st(A a) { return (S)(((long long)a) >> 32); } };
+template <> struct Dt<5> { using S = long long; using A = unsigned long long; // QType int64, fromQ >> 32
+    __device__ static A ld(S s) { return (A)s; }
+    __device__ static S st(A a) { return (S)(((long long)a) >> 32); } };
+
+template <typename T, int N> struct alignas(sizeof(T) * N) Vec { T v[N]; };
+
+// acc += tap * x for the three (data, taps) shapes of filter/FIRFilter.cpp:373-376
+template <typename A, int NC, int TC>
+__device__ __forceinline__ void mac(Vec<A, NC> &acc, const Vec<A, TC> &t, const Vec<A, NC> &x)
+{
+    if constexpr (NC == 1) {
+        acc.v[0] += t.v[0] * x.v[0];
+    } else if constexpr (TC == 1) {
+        acc.v[0] += t.v[0] * x.v[0];
+        acc.v[1] += t.v[0] * x.v[1];
+    } else {
+        acc.v[0] += t.v[0] * x.v[0];
+        acc.v[0] -= t.v[1] * x.v[1];
+        acc.v[1] += t.v[0] * x.v[1];
+        acc.v[1] += t.v[1] * x.v[0];
+    }
+}
+
+struct FirArgs {
+    const void *in;      // element 0 = first history sample; x[0] = in[K-1]
+    void *out;
+    long long n_in;      // valid elements of `in`; reads past it are zeros (burst zero tail)
+    long long nblocks;   // N / M
+    const void *taps;    // [nsub][S]
+    const int *off;      // [nsub]
+    int M, L, K, S, nsub, lo, W, QT, nrb;
+    long long ntiles;
+};
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+template <int DT, int NC, int TC, int R>
+__global__ void __launch_bounds__(kThreads) fir_tile_kernel(const FirArgs a)
+{
+    using Tr = Dt<DT>;
+    using S = typename Tr::S;
+    using A = typename Tr::A;
+    using XE = Vec<A, NC>;
+    using TE = Vec<A, TC>;
+    using IE = Vec<S, NC>;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: taps [nsub*S] | xs [M*W] | outs [QT*L] | off [nsub]   (sections 16 B aligned)
+    size_t o = 0;
+    TE *taps_s = reinterpret_cast<TE *>(smem_raw + o);
+    o += (((size_t)a.nsub * a.S * sizeof(TE)) + 15) & ~(size_t)15;
+    XE *xs = reinterpret_cast<XE *>(smem_raw + o);
+    o += (((size_t)a.M * a.W * sizeof(XE)) + 15) & ~(size_t)15;
+    IE *outs = reinterpret_cast<IE *>(smem_raw + o);
+    o += (((size_t)a.QT * a.L * sizeof(IE)) + 15) & ~(size_t)15;
+    int *off_s = reinterpret_cast<int *>(smem_raw + o);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const TE *gt = static_cast<const TE *>(a.taps);
+        for (int i = tid; i < a.nsub * a.S; i += kThreads) taps_s[i] = gt[i];
+        for (int i = tid; i < a.nsub; i += kThreads) off_s[i] = a.off[i];
+    }
+
+    const IE *in = static_cast<const IE *>(a.in);
+    IE *out = static_cast<IE *>(a.out);
+    const int M = a.M, L = a.L, W = a.W, S_ = a.S;
+    const int nchunks = L * a.nrb;
+
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const long long Q0 = tile * a.QT;
+        // ---- stage the input tile: x_e[i] = x[(Q0 + lo + i)*M + e], x[n] = in[K-1+n] ----
+        {
+            const long long gbase = (long long)(a.K - 1) + (Q0 + a.lo) * M;
+            const int total = W * M;
+            if (M == 1) {
+#pragma unroll 4
+                for (int c = tid; c < total; c += kThreads) {
+                    const long long g = gbase + c;
+                    XE v;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) v.v[k] = A(0);
+                    if (g >= 0 && g < a.n_in) {
+                        const IE s = in[g];
+#pragma unroll
+                        for (int k = 0; k < NC; k++) v.v[k] = Tr::ld(s.v[k]);
+                    }
+                    xs[c] = v;
+                }
+            } else {
+#pragma unroll 4
+                for (int c = tid; c < total; c += kThreads) {
+                    const long long g = gbase + c;
+                    XE v;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) v.v[k] = A(0);
+                    if (g >= 0 && g < a.n_in) {
+                        const IE s = in[g];
+#pragma unroll
+                        for (int k = 0; k < NC; k++) v.v[k] = Tr::ld(s.v[k]);
+                    }
+                    const int i = c / M, e = c - i * M;
+                    xs[e * W + i] = v;
+                }
+            }
+        }
+        __syncthreads(); // xs ready; also orders the previous tile's outs reads before new writes
+
+        // ---- compute: chunk = (output slot p, run block rb); lane owns R consecutive q ----
+        for (int c = warp; c < nchunks; c += kWarps) {
+            const int p = c % L, rb = c / L;
+            const int q_local = (rb * 32 + lane) * R;
+            XE acc[R];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int k = 0; k < NC; k++) acc[r].v[k] = A(0);
+
+            for (int e = 0; e < M; e++) {
+                const int sub = p * M + e;
+                const TE *g = taps_s + sub * S_;
+                const XE *xp = xs + e * W + q_local + (off_s[sub] - a.lo);
+                XE w[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) w[r] = xp[r];
+                xp += R;
+                for (int t0 = 0; t0 < S_; t0 += R) {
+#pragma unroll
+                    for (int u = 0; u < R; u++) {
+                        const TE tp = g[t0 + u];
+#pragma unroll
+                        for (int r = 0; r < R; r++) mac<A, NC, TC>(acc[r], tp, w[(u + r) % R]);
+                        w[u] = xp[t0 + u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                IE v;
+#pragma unroll
+                for (int k = 0; k < NC; k++) v.v[k] = Tr::st(acc[r].v[k]);
+                outs[(q_local + r) * L + p] = v;
+            }
+        }
+        __syncthreads(); // outs complete, xs free for the next tile
+
+        // ---- coalesced store of the tile's (contiguous) outputs ----
+        {
+            const long long qleft = a.nblocks - Q0;
+            const int nq = qleft < a.QT ? (int)qleft : a.QT;
+            const int total = nq * L;
+            IE *dst = out + Q0 * L;
+            for (int i = tid; i < total; i += kThreads) dst[i] = outs[i];
+        }
+    }
+}
+
+// Fallback for rate pairs whose staged tile cannot fit shared memory (huge M or L): one
+// output per thread straight from global memory, reference order of operations.
+template <int DT, int NC, int TC>
+__global__ void __launch_bounds__(kThreads) fir_generic_kernel(const FirArgs a)
+{
+    using Tr = Dt<DT>;
+    using S = typename Tr::S;
+    using A = typename Tr::A;
+    using XE = Vec<A, NC>;
+    using TE = Vec<A, TC>;
+    using IE = Vec<S, NC>;
+    const IE *in = static_cast<const IE *>(a.in);
+    IE *out = static_cast<IE *>(a.out);
+    const TE *taps = static_cast<const TE *>(a.taps);
+    const long long total = a.nblocks * a.L;
+    for (long long m = blockIdx.x * (long long)kThreads + threadIdx.x; m < total; m += (long long)gridDim.x * kThreads) {
+        const long long q = m / a.L;
+        const int p = (int)(m - q * a.L);
+        XE acc;
+#pragma unroll
+        for (int k = 0; k < NC; k++) acc.v[k] = A(0);
+        for (int e = 0; e < a.M; e++) {
+            const int sub = p * a.M + e;
+            const TE *g = taps + (size_t)sub * a.S;
+            const long long i0 = q + a.off[sub];
+            for (int t = 0; t < a.S; t++) {
+                const long long gi = (long long)(a.K - 1) + (i0 + t) * a.M + e;
+                XE x;
+#pragma unroll
+                for (int k = 0; k < NC; k++) x.v[k] = A(0);
+                if (gi >= 0 && gi < a.n_in) {
+                    const IE s = in[gi];
+#pragma unroll
+                    for (int k = 0; k < NC; k++) x.v[k] = Tr::ld(s.v[k]);
+                }
+                mac<A, NC, TC>(acc, g[t], x);
+            }
+        }
+        IE v;
+#pragma unroll
+        for (int k = 0; k < NC; k++) v.v[k] = Tr::st(acc.v[k]);
+        out[m] = v;
+    }
+}
+
+// ------------------------------------------------------------------- host: the table ---
+static inline long long floordiv(long long a, long long b)
+{
+    long long q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
+    return q;
+}
+
+// floatToQ, PothosCore Pothos/Util/QFormat.hpp (external; call site filter/FIRFilter.cpp:348):
+// integer Q -> trunc(ldexp(x, 4*sizeof(Q scalar))) narrowed to the Q scalar; float Q -> cast.
+static void store_tap(uint8_t *dst, int dtype, double v)
+{
+    const int cls = dtype >> 1;
+    if (cls == 0) { float f = (float)v; std::memcpy(dst, &f, 4); return; }
+    if (cls == 1) { std::memcpy(dst, &v, 8); return; }
+    const int qb = (int)qtaps_scalar_bytes(dtype);
+    const long long q = (long long)std::ldexp(v, 4 * qb);
+    if (qb == 2) { const int32_t s = (int32_t)(int16_t)q; std::memcpy(dst, &s, 4); }       // int8 data: int16 taps
+    else if (qb == 4) { const int32_t s = (int32_t)q; std::memcpy(dst, &s, 4); }           // int16 data: int32 taps
+    else { std::memcpy(dst, &q, 8); }                                                       // int32/int64 data: int64 taps
+}
+
+size_t fir_smem_bytes(const FirTable &t, int nrb)
+{
+    const size_t asz = acc_scalar_bytes(t.dtype);
+    const size_t nc = dtype_is_complex(t.dtype) ? 2 : 1;
+    const size_t QT = (size_t)32 * t.R * nrb;
+    const size_t W = QT + (size_t)(t.hi - t.lo) + t.S + t.R;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    return al((size_t)t.nsub * t.S * t.tap_elem_bytes) + al(t.M * W * asz * nc) + al(QT * t.L * dtype_bytes(t.dtype)) +
+           al((size_t)t.nsub * sizeof(int));
+}
+
+int fir_build_table(FirTable &t, int dtype, int taps_kind, const double *taps, size_t ntaps, size_t M, size_t L,
+                    size_t smem_budget)
+{
+    if (ntaps == 0) { set_error("FIRFilter::setTaps(): taps cannot be empty"); return B200C_ERR_INVALID; }
+    if (M == 0) { set_error("FIRFilter::setDecimation(): decimation cannot be 0"); return B200C_ERR_INVALID; }
+    if (L == 0) { set_error("FIRFilter::setInterpolation(): interpolation cannot be 0"); return B200C_ERR_INVALID; }
+    if (M > (1u << 20) || L > (1u << 20) || M * L > (1u << 24)) {
+        set_error("FIRFilter: decimation*interpolation too large for the device path"); return B200C_ERR_UNSUPPORTED;
+    }
+    const size_t tc = taps_kind == B200C_TAPS_COMPLEX ? 2 : 1;
+    t.dtype = dtype; t.taps_kind = taps_kind; t.M = M; t.L = L; t.ntaps = ntaps;
+    t.K = ntaps / L + ((ntaps % L) == 0 ? 0 : 1);  // filter/FIRFilter.cpp:335
+    t.nsub = (int)(L * M);
+    t.tap_elem_bytes = acc_scalar_bytes(dtype) * tc;
+
+    // per (p, e): first tap index k0, stride M, count, and the x_e offset of s = 0
+    struct Sub { size_t j; long long k0, a0, cnt; };
+    std::vector<Sub> subs(t.nsub);
+    long long smax = 1;
+    for (size_t p = 0; p < L; p++) {
+        const size_t i = (p + 1) * M - 1, j = i % L;
+        const long long d = (long long)(i / L);
+        // taps in phase j: indices j + k*L < ntaps  (filter/FIRFilter.cpp:344-349)
+        const long long ntj = j < ntaps ? (long long)((ntaps - j + L - 1) / L) : 0;
+        for (size_t e = 0; e < M; e++) {
+            Sub s;
+            s.j = j;
+            long long r = (d - (long long)e) % (long long)M;
+            if (r < 0) r += (long long)M;
+            s.k0 = r;
+            s.a0 = (d - (long long)e - s.k0) / (long long)M;
+            s.cnt = ntj > s.k0 ? (ntj - s.k0 + (long long)M - 1) / (long long)M : 0;
+            smax = std::max(smax, s.cnt);
+            subs[p * M + e] = s;
+        }
+    }
+
+    // register block: odd R in {9,7,5}, least zero padding wins (ties -> larger R); the 64-bit
+    // accumulator types keep R = 5 to bound register pressure
+    const bool wide = acc_scalar_bytes(dtype) == 8;
+    int bestR = 5;
+    if (!wide) {
+        long long best_pad = -1;
+        for (int R : {9, 7, 5}) {
+            const long long padded = (smax + R - 1) / R * R;
+            // cost model: padded MAC steps, small bonus for wider blocks (fewer tap loads)
+            const long long cost = padded * 64 + (R == 9 ? 0 : R == 7 ? 16 : 48);
+            if (best_pad < 0 || cost < best_pad) { best_pad = cost; bestR = R; }
+        }
+    }
+    t.R = bestR;
+    t.S = (int)((smax + t.R - 1) / t.R * t.R);
+
+    t.off.assign(t.nsub, 0);
+    t.taps.assign((size_t)t.nsub * t.S * t.tap_elem_bytes, 0);
+    const size_t asz = acc_scalar_bytes(dtype);
+    long long lo = 0, hi = 0;
+    bool first = true;
+    for (int sub = 0; sub < t.nsub; sub++) {
+        const Sub &s = subs[sub];
+        const long long off = s.a0 - (t.S - 1);
+        t.off[sub] = (int)off;
+        if (first) { lo = hi = off; first = false; }
+        lo = std::min(lo, off); hi = std::max(hi, off);
+        for (int tt = 0; tt < t.S; tt++) {
+            const long long sidx = (long long)t.S - 1 - tt;   // forward order: t <-> s = S-1-t
+            if (sidx >= s.cnt) continue;
+            const size_t k = (size_t)(s.k0 + (long long)M * sidx);
+            const size_t ti = s.j + k * L;                    // index into the user's taps
+            uint8_t *dst = t.taps.data() + ((size_t)sub * t.S + tt) * t.tap_elem_bytes;
+            for (size_t c = 0; c < tc; c++) store_tap(dst + c * asz, dtype, taps[ti * tc + c]);
+        }
+    }
+    t.lo = (int)lo; t.hi = (int)hi;
+
+    // tile size: largest nrb in {8,4,2,1} that fits the shared-memory budget
+    t.smem_path = false;
+    for (int nrb : {8, 4, 2, 1}) {
+        if (fir_smem_bytes(t, nrb) <= smem_budget) { t.nrb = nrb; t.smem_path = true; break; }
+    }
+    (void)floordiv;
+    return B200C_OK;
+}
+
+// ------------------------------------------------------------------ host: the launch ---
+template <int DT, int NC, int TC, int R>
+static int launch_tile(const FirArgs &a, size_t smem, int grid, cudaStream_t stream)
+{
+    auto kern = fir_tile_kernel<DT, NC, TC, R>;
+    static thread_local size_t configured[16] = {0};
+    int dev = 0;
+    B200C_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 16 && configured[dev] < smem) {
+        B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        configured[dev] = 200 * 1024;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(a);
+    B200C_CUDA_TRY(cudaGetLastError());
+    return B200C_OK;
+}
+
+template <int DT, int NC, int TC>
+static int launch_shape(const FirTable &t, const FirArgs &a, size_t smem, int grid, cudaStream_t stream)
+{
+    if (!t.smem_path) {
+        fir_generic_kernel<DT, NC, TC><<<grid, kThreads, 0, stream>>>(a);
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
+    if constexpr (DT == 0 || DT == 3) { // float32 and int16 families: tuned register blocks
+        switch (t.R) {
+        case 9: return launch_tile<DT, NC, TC, 9>(a, smem, grid, stream);
+        case 7: return launch_tile<DT, NC, TC, 7>(a, smem, grid, stream);
+        default: return launch_tile<DT, NC, TC, 5>(a, smem, grid, stream);
+        }
+    } else {
+        return launch_tile<DT, NC, TC, 5>(a, smem, grid, stream);
+    }
+}
+
+template <int DT>
+static int launch_dt(const FirTable &t, const FirArgs &a, size_t smem, int grid, cudaStream_t stream)
+{
+    const bool cx = dtype_is_complex(t.dtype), tcx = t.taps_kind == B200C_TAPS_COMPLEX;
+    if (!cx) return launch_shape<DT, 1, 1>(t, a, smem, grid, stream);
+    if (!tcx) return launch_shape<DT, 2, 1>(t, a, smem, grid, stream);
+    return launch_shape<DT, 2, 2>(t, a, smem, grid, stream);
+}
+
+int fir_launch(const FirTable &t, const FirDeviceState &ds, const void *d_in, size_t in_elems, void *d_out,
+               size_t nblocks, int sm_count, cudaStream_t stream)
+{
+    if (nblocks == 0) return B200C_OK;
+    FirArgs a;
+    a.in = d_in; a.out = d_out;
+    a.n_in = (long long)in_elems; a.nblocks = (long long)nblocks;
+    a.taps = ds.d_taps; a.off = ds.d_off;
+    a.M = (int)t.M; a.L = (int)t.L; a.K = (int)t.K; a.S = t.S; a.nsub = t.nsub; a.lo = t.lo;
+
+    size_t smem = 0;
+    int grid;
+    if (t.smem_path) {
+        // shrink the tile for short inputs so every SM gets work
+        int nrb = t.nrb;
+        while (nrb > 1 && (nblocks + (size_t)32 * t.R * nrb - 1) / ((size_t)32 * t.R * nrb) < (size_t)4 * sm_count) nrb /= 2;
+        a.nrb = nrb;
+        a.QT = 32 * t.R * nrb;
+        a.W = a.QT + (t.hi - t.lo) + t.S + t.R;
+        a.ntiles = (long long)((nblocks + a.QT - 1) / a.QT);
+        smem = fir_smem_bytes(t, nrb);
+        const long long cap = (long long)sm_count * 8;
+        grid = (int)std::min<long long>(a.ntiles, cap);
+    } else {
+        a.nrb = 0; a.QT = 0; a.W = 0; a.ntiles = 0;
+        const long long want = (long long)((nblocks * t.L + kThreads - 1) / kThreads);
+        grid = (int)std::min<long long>(want, (long long)sm_count * 16);
+    }
+    switch (t.dtype >> 1) {
+    case 0: return launch_dt<0>(t, a, smem, grid, stream);
+    case 1: return launch_dt<1>(t, a, smem, grid, stream);
+    case 2: return launch_dt<2>(t, a, smem, grid, stream);
+    case 3: return launch_dt<3>(t, a, smem, grid, stream);
+    case 4: return launch_dt<4>(t, a, smem, grid, stream);
+    default: return launch_dt<5>(t, a, smem, grid, stream);
+    }
+}
+
+} // namespace b200c

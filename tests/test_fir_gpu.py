@@ -1,0 +1,293 @@
+"""GPU parity: /comms/fir_filter CUDA path (through the C-ABI) vs the CPU oracle.
+
+Bit-exact for every integer type (the reference's Q-format shift and wrap); within 1e-5 of
+the output RMS for float32/complex float32 (BASELINE.json north_star), tighter for float64.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FLOAT_TOL = 1e-5   # of output RMS, float32 paths (north_star)
+DOUBLE_TOL = 1e-13
+
+
+def _rand_input(oracle, code, n, rng, full_scale=False):
+    nc = 2 if code & 1 else 1
+    sc = oracle.scalar_np(code)
+    if np.issubdtype(sc, np.integer):
+        info = np.iinfo(sc)
+        lim = info.max if full_scale else info.max // 2
+        lim = min(lim, 2 ** 31 - 1)
+        return rng.integers(-lim - 1, lim + 1, size=(n, nc)).astype(sc)
+    return rng.standard_normal((n, nc)).astype(sc)
+
+
+def _run_gpu(code, taps_type, taps, M, L, x, zero_tail=False, out_capacity=None):
+    import torch
+    from pothoscomms_b200 import FirFilter
+    f = FirFilter(code, taps_type)
+    f.set_taps(taps)
+    f.set_rates(M, L)
+    d = torch.from_numpy(x).cuda()
+    y, cons, prod = f.run(d, zero_tail=zero_tail, out_capacity=out_capacity)
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), cons, prod, f
+
+
+def _compare(oracle, code, y_gpu, y_ref, what=""):
+    assert y_gpu.shape == y_ref.shape, what
+    sc = oracle.scalar_np(code)
+    if np.issubdtype(sc, np.integer):
+        assert np.array_equal(y_gpu, y_ref), f"{what}: integer path must be bit-exact"
+    else:
+        ref = y_ref.astype(np.float64)
+        rms = np.sqrt(np.mean(ref ** 2)) if ref.size else 1.0
+        err = np.sqrt(np.mean((y_gpu.astype(np.float64) - ref) ** 2)) if ref.size else 0.0
+        tol = FLOAT_TOL if sc == np.float32 else DOUBLE_TOL
+        assert err <= tol * max(rms, 1e-30), f"{what}: rel rms err {err / max(rms, 1e-30):.3e} > {tol}"
+        mx = np.max(np.abs(y_gpu.astype(np.float64) - ref)) if ref.size else 0.0
+        assert mx <= 50 * tol * max(rms, 1e-30), f"{what}: max err {mx}"
+
+
+ALL_TYPES = ["F32", "CF32", "F64", "CF64", "I8", "CI8", "I16", "CI16", "I32", "CI32", "I64", "CI64"]
+
+
+@pytest.mark.parametrize("dt", ALL_TYPES)
+@pytest.mark.parametrize("taps_type", ["REAL", "COMPLEX"])
+def test_all_18_factory_rows(oracle, cuda_device, dt, taps_type):
+    """Every row of FIRFilterFactory (filter/FIRFilter.cpp:373-382), streaming L=M=1."""
+    code = getattr(oracle, dt)
+    if taps_type == "COMPLEX" and not (code & 1):
+        from pothoscomms_b200 import FirFilter, InvalidArgumentError
+        with pytest.raises(InvalidArgumentError):   # filter/FIRFilter.cpp:383
+            FirFilter(code, "COMPLEX")
+        return
+    rng = np.random.default_rng(code * 2 + (taps_type == "COMPLEX"))
+    ntaps = 37
+    taps = rng.standard_normal(ntaps) * 0.2
+    if taps_type == "COMPLEX":
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.2
+    x = _rand_input(oracle, code, 5000, rng)
+    y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, 1, 1, x)
+    y, cons, prod, _ = _run_gpu(code, taps_type, taps, 1, 1, x)
+    assert (cons, prod) == (c_ref, p_ref)
+    _compare(oracle, code, y, y_ref, f"{dt}/{taps_type}")
+
+
+RATES = [(1, 1), (2, 1), (3, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3), (5, 4), (4, 6), (7, 3), (16, 1), (1, 16)]
+
+
+@pytest.mark.parametrize("M,L", RATES)
+@pytest.mark.parametrize("dt,taps_type", [("CF32", "COMPLEX"), ("CF32", "REAL"), ("F32", "REAL"), ("CI16", "COMPLEX"),
+                                          ("CI16", "REAL"), ("I16", "REAL")])
+def test_polyphase_rates(oracle, cuda_device, dt, taps_type, M, L):
+    """decim x interp grid of filter/TestFIRFilter.cpp:68-70 (1..3 x 1..3) and beyond; 101 taps as :40."""
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(1000 + M * 31 + L)
+    ntaps = 101
+    taps = rng.standard_normal(ntaps) * 0.1
+    if taps_type == "COMPLEX":
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.1
+    x = _rand_input(oracle, code, 4096 + 200, rng)
+    y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x)
+    y, cons, prod, _ = _run_gpu(code, taps_type, taps, M, L, x)
+    assert (cons, prod) == (c_ref, p_ref)
+    _compare(oracle, code, y, y_ref, f"{dt}/{taps_type} M={M} L={L}")
+
+
+@pytest.mark.parametrize("ntaps", [1, 2, 3, 8, 9, 10, 63, 64, 65, 128, 255, 256, 257, 1024])
+def test_tap_counts(oracle, cuda_device, ntaps):
+    rng = np.random.default_rng(ntaps)
+    taps = (rng.standard_normal(ntaps) + 1j * rng.standard_normal(ntaps)) / np.sqrt(ntaps)
+    for code, tt in ((oracle.CF32, "COMPLEX"), (oracle.CI16, "COMPLEX")):
+        x = _rand_input(oracle, code, ntaps + 3000, rng)
+        y_ref, c_ref, p_ref = oracle.fir(code, True, taps, 1, 1, x)
+        y, cons, prod, _ = _run_gpu(code, tt, taps, 1, 1, x)
+        assert (cons, prod) == (c_ref, p_ref)
+        _compare(oracle, code, y, y_ref, f"ntaps={ntaps} code={code}")
+
+
+def test_baseline_configs_small(oracle, cuda_device):
+    """The BASELINE.json configs at sizes the oracle finishes in seconds (same taps, tone+noise)."""
+    from pothoscomms_b200 import workloads as wl
+    cases = [("c1", oracle.CF32, 1, 1, 1 << 18), ("c1_real", oracle.CF32, 1, 1, 1 << 18),
+             ("headline", oracle.CF32, 1, 1, 1 << 17), ("c2", oracle.CI16, 1, 1, 1 << 18),
+             ("c3", oracle.CF32, 2, 3, 1 << 18), ("c5", oracle.CF32, 1, 1, 1 << 15)]
+    for name, code, M, L, n in cases:
+        taps, tt = wl.config_taps(name)
+        x = wl.tone_noise_numpy(code, n, seed=0xC0FFEE00 + len(name))
+        y_ref, c_ref, p_ref = oracle.fir(code, tt == "COMPLEX", taps, M, L, x, threads=8)
+        y, cons, prod, _ = _run_gpu(code, tt, taps, M, L, x)
+        assert (cons, prod) == (c_ref, p_ref), name
+        _compare(oracle, code, y, y_ref, name)
+
+
+def test_int16_wrapping_accumulator(oracle, cuda_device):
+    """Deliberately overflowing int32 accumulator must wrap exactly like the reference's QType."""
+    rng = np.random.default_rng(77)
+    taps = (rng.standard_normal(128) + 1j * rng.standard_normal(128)) * 1.9
+    x = _rand_input(oracle, oracle.CI16, 20000, rng, full_scale=True)
+    y_ref, _, _ = oracle.fir(oracle.CI16, True, taps, 1, 1, x)
+    y, _, _, _ = _run_gpu(oracle.CI16, "COMPLEX", taps, 1, 1, x)
+    assert np.array_equal(y, y_ref)
+
+
+def test_default_taps_passthrough(oracle, cuda_device):
+    import torch
+    from pothoscomms_b200 import FirFilter
+    for dt in ("complex_float32", "complex_int16", "float32", "int16", "complex_float64", "complex_int8"):
+        f = FirFilter(dt, "REAL")
+        assert f.info() == (1, 1, 1, 1)
+        code = f.dtype
+        x = _rand_input(oracle, code, 1000, np.random.default_rng(3))
+        y, cons, prod = f.run(torch.from_numpy(x).cuda())
+        assert cons == prod == 1000
+        assert np.array_equal(y.cpu().numpy(), x)
+
+
+def test_setter_errors_and_state(oracle, cuda_device):
+    from pothoscomms_b200 import FirFilter, InvalidArgumentError
+    f = FirFilter("complex_float32", "COMPLEX")
+    with pytest.raises(InvalidArgumentError, match="taps cannot be empty"):       # FIRFilter.cpp:140
+        f.set_taps([])
+    with pytest.raises(InvalidArgumentError, match="decimation cannot be 0"):     # FIRFilter.cpp:153
+        f.set_rates(0, 1)
+    with pytest.raises(InvalidArgumentError, match="interpolation cannot be 0"):  # FIRFilter.cpp:165
+        f.set_rates(1, 0)
+    # a failed setter leaves the previous configuration intact
+    assert f.info() == (1, 1, 1, 1)
+    f.set_taps(np.ones(101, dtype=complex))
+    f.set_rates(2, 3)
+    assert f.info() == (34, 2 + 34 - 1, 2, 3)    # K = ceil(101/3), _inputRequire = M + K - 1
+
+
+def test_output_capacity_limits_N(oracle, cuda_device):
+    rng = np.random.default_rng(5)
+    taps = rng.standard_normal(33)
+    x = _rand_input(oracle, oracle.CF32, 3000, rng)
+    for cap in (0, 1, 2, 3, 10, 100, 1001):
+        y_ref, c_ref, p_ref = oracle.fir(oracle.CF32, False, taps, 2, 3, x, out_capacity=cap)
+        y, cons, prod, _ = _run_gpu(oracle.CF32, "REAL", taps, 2, 3, x, out_capacity=cap)
+        assert (cons, prod) == (c_ref, p_ref), cap
+        _compare(oracle, oracle.CF32, y, y_ref, f"cap={cap}")
+
+
+def test_insufficient_input(oracle, cuda_device):
+    y, cons, prod, f = _run_gpu(oracle.CF32, "REAL", np.ones(64), 1, 1, np.ones((63, 2), dtype=np.float32))
+    assert (cons, prod) == (0, 0) and f.input_require == 64
+
+
+@pytest.mark.parametrize("M,L", [(1, 1), (2, 3), (3, 2)])
+def test_burst_zero_tail(oracle, cuda_device, M, L):
+    """Burst flush (filter/FIRFilter.cpp:265-272): K-1 virtual zeros, never materialised on the device."""
+    rng = np.random.default_rng(8)
+    taps = rng.standard_normal(101) + 1j * rng.standard_normal(101)
+    for code in (oracle.CF32, oracle.CI16):
+        x = _rand_input(oracle, code, 1024, rng)
+        y_ref, c_ref, p_ref = oracle.fir(code, True, taps * 0.1, M, L, x, zero_tail=True)
+        y, cons, prod, _ = _run_gpu(code, "COMPLEX", taps * 0.1, M, L, x, zero_tail=True)
+        assert (cons, prod) == (c_ref, p_ref)
+        _compare(oracle, code, y, y_ref, f"zero tail code={code}")
+    if (M, L) == (1, 1):
+        assert prod == 1024   # filter/TestFIRDesigner.cpp:183
+
+
+def test_streaming_in_pieces_equals_one_shot(oracle, cuda_device):
+    """work() is stateless in the history: feeding consecutive windows that each start K-1
+    elements before the new data reproduces the single-call result (FIRFilter.cpp:304-307)."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    rng = np.random.default_rng(21)
+    taps = rng.standard_normal(255)
+    code = oracle.CF32
+    x = _rand_input(oracle, code, 50000, rng)
+    f = FirFilter(code, "REAL")
+    f.set_taps(taps)
+    f.set_rates(2, 3)
+    d = torch.from_numpy(x).cuda()
+    whole, cons_all, _ = f.run(d)
+    pos, outs = 0, []
+    for piece in (1000, 37, 4096, 2, 10000, 12345, 50000):
+        avail = min(piece, x.shape[0] - pos)
+        y, cons, prod = f.run(d[pos: pos + avail].contiguous())
+        outs.append(y.clone())
+        pos += cons           # K-1 (+ remainder) elements stay in the "input buffer"
+    got = torch.cat(outs)
+    assert pos == cons_all
+    assert torch.equal(got, whole[: got.shape[0]]) and got.shape[0] == whole.shape[0]
+
+
+def test_host_buffer_entry_point(oracle, cuda_device):
+    """b200c_fir_run_host: chunked H2D -> kernel -> D2H gives the same stream."""
+    rng = np.random.default_rng(13)
+    from pothoscomms_b200 import FirFilter
+    for code, tt, M, L, n in ((oracle.CF32, "COMPLEX", 1, 1, 9_000_000), (oracle.CI16, "COMPLEX", 3, 2, 3_000_000)):
+        taps = (rng.standard_normal(64) + 1j * rng.standard_normal(64)) * 0.05
+        x = _rand_input(oracle, code, n, rng)
+        f = FirFilter(code, tt)
+        f.set_taps(taps)
+        f.set_rates(M, L)
+        y_host, cons, prod = f.run_host(x)
+        import torch
+        y_dev, c2, p2 = f.run(torch.from_numpy(x).cuda())
+        assert (cons, prod) == (c2, p2)
+        assert np.array_equal(y_host, y_dev.cpu().numpy())
+        # spot-check against the oracle on a window
+        w0 = 1_234_567 // M * M
+        seg = x[w0: w0 + 20000]
+        y_ref, _, p_ref = oracle.fir(code, True, taps, M, L, seg)
+        got = y_host[w0 // M * L: w0 // M * L + p_ref]
+        _compare(oracle, code, got, y_ref, "host path window")
+
+
+def test_fir_regression_fixtures(oracle, cuda_device):
+    for fn in sorted(os.listdir(GOLDEN)):
+        if not (fn.startswith("fir_") and fn.endswith(".npz")):
+            continue
+        g = np.load(os.path.join(GOLDEN, fn))
+        code, tcx = int(g["dtype"]), bool(g["taps_complex"])
+        y, cons, prod, _ = _run_gpu(code, "COMPLEX" if tcx else "REAL", g["taps"], int(g["M"]), int(g["L"]), g["x"])
+        assert cons == int(g["consumed"]) and prod == int(g["produced"]), fn
+        _compare(oracle, code, y, g["y"], fn)
+
+
+def test_large_rates_use_generic_kernel(oracle, cuda_device):
+    rng = np.random.default_rng(99)
+    taps = rng.standard_normal(4000) * 0.05
+    for code in (oracle.CF32, oracle.I16):
+        x = _rand_input(oracle, code, 60000, rng)
+        for M, L in ((1000, 1), (1, 300), (250, 7)):
+            y_ref, c_ref, p_ref = oracle.fir(code, False, taps, M, L, x)
+            y, cons, prod, _ = _run_gpu(code, "REAL", taps, M, L, x)
+            assert (cons, prod) == (c_ref, p_ref)
+            _compare(oracle, code, y, y_ref, f"M={M} L={L}")
+
+
+def test_full_size_linearity_and_sampled_windows(oracle, cuda_device):
+    """2^26-sample stream (too long for the oracle end to end): sampled windows vs the oracle,
+    plus linearity FIR(a*x1 + x2) == a*FIR(x1) + FIR(x2) within tolerance."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    from pothoscomms_b200 import workloads as wl
+    n = 1 << 26
+    taps, tt = wl.config_taps("headline")
+    f = FirFilter(oracle.CF32, tt)
+    f.set_taps(taps)
+    x1 = wl.tone_noise_torch(oracle.CF32, n, 0xC0FFEE01, cuda_device)
+    y1, cons, prod = f.run(x1)
+    assert cons == n - 255 and prod == n - 255
+    for w0 in (0, 12_345_678, n - 40_000):
+        seg = x1[w0: w0 + 40_000].cpu().numpy()
+        y_ref, _, p_ref = oracle.fir(oracle.CF32, True, taps, 1, 1, seg, threads=8)
+        _compare(oracle, oracle.CF32, y1[w0: w0 + p_ref].cpu().numpy(), y_ref, f"window {w0}")
+    x2 = wl.tone_noise_torch(oracle.CF32, n, 0xC0FFEE02, cuda_device)
+    y2, _, _ = f.run(x2)
+    y12, _, _ = f.run(x1 * 0.5 + x2)
+    lin = y1 * 0.5 + y2
+    err = torch.sqrt(torch.mean((y12 - lin).double() ** 2)).item()
+    rms = torch.sqrt(torch.mean(lin.double() ** 2)).item()
+    assert err <= 2e-6 * rms + 1e-7
