@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -89,10 +89,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.05)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.ok:
             self.join(timeout=2)
         s = sorted(self.samples)
@@ -173,19 +173,98 @@ def reference_arm(args):
     return 0
 
 
+def bench_fft(args):
+    """Auxiliary workload (BASELINE config 4): /comms/fft 4096-point forward then inverse over
+    2^28 samples.  One step = two passes (2 launches); value counts samples per pass."""
+    import numpy as np
+    import torch
+
+    import oracle
+    from pothoscomms_b200 import Fft
+    from pothoscomms_b200 import workloads as wl
+    from pothoscomms_b200.handles import dtype_code
+    args.warmup = max(args.warmup, 3)
+    dt_name = "complex_int16" if args.workload == "c4_i16" else "complex_float32"
+    code = dtype_code(dt_name)
+    n, log2n = 4096, args.log2_samples or 28
+    total = 1 << log2n
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    x = wl.tone_noise_torch(code, total, 0xC0FFEE04, dev)
+    X = torch.empty_like(x)
+    y = torch.empty_like(x)
+    fwd, inv = Fft(code, n, False), Fft(code, n, True)
+    for _ in range(args.warmup):
+        fwd.run(x, out=X); inv.run(X, out=y)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(0))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fwd.run(x, out=X); inv.run(X, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    value = 2 * total / (ms * 1e-3) / 1e6
+    esz = x.element_size() * 2
+    peaks, peak_kind = measured_peaks()
+    achieved = 2 * esz * total * 2 / (ms * 1e-3) / 1e9    # (read + write) x two passes
+    e2e = None
+    if not args.no_e2e:
+        h_in, h_out = x.cpu().pin_memory(), torch.empty(x.shape, dtype=x.dtype).pin_memory()
+        fwd.run_host(h_in.numpy(), out=h_out.numpy())
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fwd.run_host(h_in.numpy(), out=h_out.numpy())
+        e2e_s = (time.perf_counter() - t0) / 3
+        e2e = {"value": total / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * h_in.element_size()),
+               "d2h_bytes_per_step": int(h_out.numel() * h_out.element_size()), "note": "forward pass only"}
+    cpu = None
+    if not args.no_cpu:
+        threads = cpu_threads()
+        nb = threads * 512
+        xs = x[: nb * n].cpu().numpy()
+        t0 = time.perf_counter()
+        if oracle.have_ref():
+            oracle.ref_fft(code, n, False, xs, threads=threads)
+            kind = "reference"
+        else:
+            oracle.fft(code, n, False, xs)
+            kind, threads = "port", 1
+        secs = time.perf_counter() - t0
+        cpu = {"value": nb * n / secs / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{nb} transforms of 4096 (kiss_fft from the reference sources), {secs:.2f} s"}
+    line = {
+        "metric": f"FFT Msamples/s per pass ({dt_name}, 4096-point, forward+inverse)", "value": value, "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if code == 1 else "i16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: /comms/fft {dt_name} 4096-point batched forward then inverse over 2^{log2n} samples",
+                   "l2_policy": "inputs larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "kernel": "fft"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4", "c4_i16"])
     ap.add_argument("--log2-samples", type=int, default=None, help="override samples per GPU (debug)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload in ("c4", "c4_i16"):
+        return bench_fft(args)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np

@@ -1,0 +1,273 @@
+// Test harness for the block layer: a single-block stand-in for what a Pothos::Topology with
+// /blocks/feeder_source -> block -> /blocks/collector_sink does in the reference's tests
+// (filter/TestFIRFilter.cpp:19-53, fft/TestFFT.cpp:33-46), plus an extern "C" surface so that
+// pytest can drive it through ctypes.  NOT part of the product data path: it only feeds host
+// data into the block's device buffer managers, runs work() until it stops making progress
+// (honouring reserves, labels and propagateLabels like the framework's post-work step) and
+// drains produced elements back to the host.
+#include <Pothos/Framework.hpp>
+
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "DeviceBuffers.hpp"
+
+namespace Pothos {
+
+class Harness {
+public:
+    Harness(Block *blk, int device, size_t inBytes, size_t outBytes) : _blk(blk), _device(device)
+    {
+        _inMgr = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(blk->getInputBufferManager("0", b200c_blocks::kHbmDomain));
+        _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
+        if (!_inMgr || !_outMgr) throw Exception("Harness()", "block does not provide device buffer managers");
+        BufferManagerArgs ia;
+        ia.bufferSize = inBytes; ia.numBuffers = 1;
+        _inMgr->init(ia);
+        BufferManagerArgs oa;
+        oa.bufferSize = outBytes; oa.numBuffers = 2;
+        _outMgr->init(oa);
+    }
+
+    void activate()
+    {
+        _blk->_active = true;
+        _blk->activate();
+    }
+
+    void postLabel(const Label &l) { _inLabels.push_back(l); }   // absolute input element index
+
+    // host -> HBM ring; returns the number of elements accepted (ring may be full)
+    size_t feed(const void *host, size_t elems)
+    {
+        InputPort *in = _blk->input(0);
+        const size_t esz = in->dtype().size();
+        const size_t room = _inMgr->front().length / esz;
+        const size_t n = std::min(room, elems);
+        if (n == 0) return 0;
+        b200c_blocks::throwOnError(b200c_copy_h2d(_inMgr->front().as<void *>(), host, n * esz, _device, nullptr), "Harness::feed()");
+        _inMgr->pop(n * esz);
+        _totalFed += n;
+        return n;
+    }
+
+    void run()
+    {
+        InputPort *in = _blk->input(0);
+        OutputPort *out = _blk->output(0);
+        const size_t isz = in->dtype().size(), osz = out->dtype().size();
+        for (int guard = 0; guard < 1000000; guard++) {
+            const BufferChunk rd = _inMgr->readable();
+            in->_addr = rd.address;
+            in->_bytes = rd.length / isz * isz;
+            in->_labels.clear();
+            for (const auto &l : _inLabels) {
+                if (l.index >= _totalConsumed && l.index - _totalConsumed < in->elements()) {
+                    Label r = l;
+                    r.index = l.index - _totalConsumed;
+                    in->_labels.push_back(r);
+                }
+            }
+            if (_outMgr->empty()) break;
+            out->_addr = _outMgr->front().address;
+            out->_bytes = _outMgr->front().length / osz * osz;
+            in->_pendingConsume = 0;
+            out->_pendingProduce = 0;
+            out->_posted.clear();
+            // the scheduler does not call work() until the reserve is met
+            if (in->elements() < std::max<size_t>(in->_reserve, 1)) break;
+
+            _blk->work();
+            _workCalls++;
+
+            const size_t c = in->_pendingConsume, p = out->_pendingProduce;
+            if (c > in->elements() || p > out->elements()) throw Exception("Harness::run()", "block over-consumed or over-produced");
+            if (c) {
+                // post-work: labels inside the consumed region are propagated, then dropped
+                std::vector<Label> consumed, keep;
+                for (const auto &l : in->_labels) if (l.index < c) consumed.push_back(l);
+                in->_labels = consumed;
+                _blk->propagateLabels(in);
+                for (const auto &l : _inLabels) if (!(l.index >= _totalConsumed && l.index - _totalConsumed < c)) keep.push_back(l);
+                _inLabels.swap(keep);
+                _inMgr->push(c * isz);
+                _totalConsumed += c;
+                in->_totalConsumed = _totalConsumed;
+            }
+            for (auto &l : out->_posted) {
+                l.index += _totalProduced;   // posted indices are relative to this call's first output
+                _outLabels.push_back(l);
+            }
+            out->_posted.clear();
+            if (p) {
+                const size_t at = _collected.size();
+                _collected.resize(at + p * osz);
+                b200c_blocks::throwOnError(b200c_copy_d2h(_collected.data() + at, out->buffer().as<const void *>(), p * osz, _device, nullptr), "Harness::run()");
+                b200c_blocks::throwOnError(b200c_stream_sync(_device, nullptr), "Harness::run()");
+                _outMgr->pop(p * osz);
+                _outMgr->push(p * osz);   // the "collector" is done with the slab
+                _totalProduced += p;
+            }
+            if (c == 0 && p == 0) break;
+        }
+    }
+
+    size_t collect(void *host, size_t maxElems)
+    {
+        const size_t osz = _blk->output(0)->dtype().size();
+        const size_t n = std::min(maxElems, _collected.size() / osz);
+        std::memcpy(host, _collected.data(), n * osz);
+        _collected.erase(_collected.begin(), _collected.begin() + n * osz);
+        return n;
+    }
+
+    Block *block() { return _blk.get(); }
+    const std::vector<Label> &outLabels() const { return _outLabels; }
+    size_t pendingOutput() const { return _collected.size() / _blk->output(0)->dtype().size(); }
+    size_t reserve() const { return _blk->_inputs.at(0)._reserve; }
+    unsigned long long totalConsumed() const { return _totalConsumed; }
+    unsigned long long workCalls() const { return _workCalls; }
+    std::string inputDomain() const { return _inMgr->domain(); }
+
+private:
+    std::unique_ptr<Block> _blk;
+    int _device;
+    std::shared_ptr<b200c_blocks::DeviceCircularBufferManager> _inMgr;
+    BufferManager::Sptr _outMgr;
+    std::vector<Label> _inLabels, _outLabels;
+    std::vector<char> _collected;
+    unsigned long long _totalFed = 0, _totalConsumed = 0, _totalProduced = 0, _workCalls = 0;
+};
+
+} // namespace Pothos
+
+// ------------------------------------------------------------------ extern "C" test surface ---
+static thread_local std::string g_blkErr;
+
+template <typename F> static int guarded(F &&f)
+{
+    try { f(); return 0; }
+    catch (const Pothos::InvalidArgumentException &e) { g_blkErr = e.what(); return -1; }
+    catch (const Pothos::Exception &e) { g_blkErr = e.what(); return -2; }
+    catch (const std::exception &e) { g_blkErr = e.what(); return -3; }
+}
+
+using Pothos::Harness;
+using Pothos::Object;
+
+extern "C" {
+
+const char *b200c_blk_last_error(void) { return g_blkErr.c_str(); }
+
+int b200c_blk_registry_has(const char *path) { return Pothos::BlockRegistry::doesBlockExist(path) ? 1 : 0; }
+
+// factory: /comms/fir_filter(dtype, tapsType) when taps_type != NULL, else /comms/fft(dtype, numBins, inverse)
+void *b200c_blk_make(const char *path, const char *dtype, const char *taps_type, size_t num_bins, int inverse, size_t in_bytes,
+                     size_t out_bytes, int *status)
+{
+    Harness *h = nullptr;
+    const int rc = guarded([&] {
+        Pothos::Block *blk = taps_type ? Pothos::BlockRegistry::make(path, Pothos::DType(dtype), std::string(taps_type))
+                                       : Pothos::BlockRegistry::make(path, Pothos::DType(dtype), num_bins, inverse != 0);
+        const char *env = std::getenv("B200C_DEVICE");
+        h = new Harness(blk, env ? std::atoi(env) : 0, in_bytes, out_bytes);
+    });
+    if (status) *status = rc;
+    return h;
+}
+
+void b200c_blk_destroy(void *h) { delete static_cast<Harness *>(h); }
+
+int b200c_blk_call_taps(void *h, const char *name, const double *taps, size_t n, int is_complex)
+{
+    return guarded([&] {
+        if (is_complex) {
+            const auto *c = reinterpret_cast<const std::complex<double> *>(taps);
+            static_cast<Harness *>(h)->block()->call(name, std::vector<std::complex<double>>(c, c + n));
+        } else {
+            static_cast<Harness *>(h)->block()->call(name, std::vector<double>(taps, taps + n));
+        }
+    });
+}
+int b200c_blk_call_size(void *h, const char *name, size_t v) { return guarded([&] { static_cast<Harness *>(h)->block()->call(name, v); }); }
+int b200c_blk_call_bool(void *h, const char *name, int v) { return guarded([&] { static_cast<Harness *>(h)->block()->call(name, v != 0); }); }
+int b200c_blk_call_string(void *h, const char *name, const char *v) { return guarded([&] { static_cast<Harness *>(h)->block()->call(name, std::string(v)); }); }
+
+int b200c_blk_get_size(void *h, const char *name, size_t *out)
+{
+    return guarded([&] { *out = static_cast<Harness *>(h)->block()->call(name).convert<size_t>(); });
+}
+int b200c_blk_get_bool(void *h, const char *name, int *out)
+{
+    return guarded([&] { *out = static_cast<Harness *>(h)->block()->call(name).convert<bool>() ? 1 : 0; });
+}
+int b200c_blk_get_string(void *h, const char *name, char *buf, size_t cap)
+{
+    return guarded([&] {
+        const std::string s = static_cast<Harness *>(h)->block()->call(name).convert<std::string>();
+        std::snprintf(buf, cap, "%s", s.c_str());
+    });
+}
+// getTaps(): writes up to cap doubles (interleaved when complex); *n = tap count
+int b200c_blk_get_taps(void *h, double *buf, size_t cap, size_t *n, int *is_complex)
+{
+    return guarded([&] {
+        const Object o = static_cast<Harness *>(h)->block()->call("getTaps");
+        if (o.type() == typeid(std::vector<double>)) {
+            const auto &v = o.extract<std::vector<double>>();
+            *n = v.size(); *is_complex = 0;
+            for (size_t i = 0; i < v.size() && i < cap; i++) buf[i] = v[i];
+        } else {
+            const auto &v = o.extract<std::vector<std::complex<double>>>();
+            *n = v.size(); *is_complex = 1;
+            for (size_t i = 0; i < v.size() && 2 * i + 1 < cap; i++) { buf[2 * i] = v[i].real(); buf[2 * i + 1] = v[i].imag(); }
+        }
+    });
+}
+int b200c_blk_has_call(void *h, const char *name) { return static_cast<Harness *>(h)->block()->hasCall(name) ? 1 : 0; }
+
+int b200c_blk_activate(void *h) { return guarded([&] { static_cast<Harness *>(h)->activate(); }); }
+
+// kind: 0 = no payload, 1 = size_t payload, 2 = double payload
+int b200c_blk_post_label(void *h, const char *id, int kind, size_t sval, double dval, unsigned long long index, size_t width)
+{
+    return guarded([&] {
+        Pothos::Label l;
+        l.id = id; l.index = index; l.width = width;
+        if (kind == 1) l.data = Object(sval);
+        if (kind == 2) l.data = Object(dval);
+        static_cast<Harness *>(h)->postLabel(l);
+    });
+}
+
+long long b200c_blk_feed(void *h, const void *host, size_t elems)
+{
+    long long n = -1;
+    const int rc = guarded([&] { n = (long long)static_cast<Harness *>(h)->feed(host, elems); });
+    return rc ? rc : n;
+}
+int b200c_blk_run(void *h) { return guarded([&] { static_cast<Harness *>(h)->run(); }); }
+long long b200c_blk_pending(void *h) { return (long long)static_cast<Harness *>(h)->pendingOutput(); }
+long long b200c_blk_collect(void *h, void *host, size_t max_elems) { return (long long)static_cast<Harness *>(h)->collect(host, max_elems); }
+size_t b200c_blk_reserve(void *h) { return static_cast<Harness *>(h)->reserve(); }
+unsigned long long b200c_blk_total_consumed(void *h) { return static_cast<Harness *>(h)->totalConsumed(); }
+unsigned long long b200c_blk_work_calls(void *h) { return static_cast<Harness *>(h)->workCalls(); }
+int b200c_blk_input_domain(void *h, char *buf, size_t cap) { std::snprintf(buf, cap, "%s", static_cast<Harness *>(h)->inputDomain().c_str()); return 0; }
+
+long long b200c_blk_num_out_labels(void *h) { return (long long)static_cast<Harness *>(h)->outLabels().size(); }
+int b200c_blk_out_label(void *h, size_t i, char *id, size_t idcap, unsigned long long *index, size_t *width, int *kind, double *value)
+{
+    return guarded([&] {
+        const Pothos::Label &l = static_cast<Harness *>(h)->outLabels().at(i);
+        std::snprintf(id, idcap, "%s", l.id.c_str());
+        *index = l.index; *width = l.width; *kind = 0; *value = 0;
+        if (l.data) {
+            if (l.data.type() == typeid(double)) { *kind = 2; *value = l.data.convert<double>(); }
+            else if (l.data.canConvert(typeid(size_t))) { *kind = 1; *value = (double)l.data.convert<size_t>(); }
+        }
+    });
+}
+
+} // extern "C"

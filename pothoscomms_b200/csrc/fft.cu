@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) fft_staged_kernel(const FftArgs a)
 
         for (int s = a.nstages - 1; s >= 0; s--) {
             const int p = a.radix[s], m = a.rem[s], span = p * m, fstride = n / span;
-            if (p <= 5) {
+            if (p >= 2 && p <= 5) {
                 const int per = n / p, nb = nt * per;
                 E e1 = Tr::mk(0, 0), e2 = Tr::mk(0, 0);
                 if (p == 3) e1 = tw[fstride * m];
@@ -220,6 +220,143 @@ __global__ void __launch_bounds__(256) fft_staged_kernel(const FftArgs a)
     }
 }
 
+// ------------------------------------------------------------- fast path: N = 4096 ---
+// kiss_fft plans 4096 as six radix-4 stages (remainders m = 1024,256,64,16,4,1, executed
+// innermost first).  Here one 256-thread CTA does one transform in THREE register-resident
+// passes of two fused radix-4 stages each (16 points per thread), with two shared-memory
+// exchanges instead of six -- every element still sees kiss_fft's exact sequence of
+// operations (twiddle products, C_FIXDIV, wraps), so the Q15 variant stays bit-exact.
+//
+// Slot o = 256*A + 16*B + C (A,B,C in [0,16)), input index i = digit-reversed o:
+//   pass 1: thread t = i mod 256 loads in[t + 256*j] (coalesced), does stages m=1 and m=4,
+//           i.e. all C for its (A,B), and writes slots 256A+16B+C
+//   pass 2: thread (A,C) does stages m=16, m=64 over B
+//   pass 3: thread (B,C) does stages m=256, m=1024 over A and stores out[256*A + 16B+C] (coalesced)
+// Shared-memory index of slot o is o + (o >> 8): with that one-element pad per 256 every
+// one of the six access patterns is bank-conflict free.
+// Twiddles are pre-gathered on the host from the reference-order table into per-pass tables
+// laid out in consumption order (tw1: uniform; tw2[j][C]; tw3[j][16B+C]) so loads coalesce.
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly4_reg(E &f0, E &f1, E &f2, E &f3, const E t1, const E t2, const E t3, const int inverse)
+{
+    f0 = Tr::fixdiv(f0, 4); f1 = Tr::fixdiv(f1, 4); f2 = Tr::fixdiv(f2, 4); f3 = Tr::fixdiv(f3, 4);
+    const E s0 = Tr::mul(f1, t1);
+    const E s1 = Tr::mul(f2, t2);
+    const E s2 = Tr::mul(f3, t3);
+    const E s5 = Tr::sub(f0, s1);
+    f0 = Tr::add(f0, s1);
+    const E s3 = Tr::add(s0, s2);
+    const E s4 = Tr::sub(s0, s2);
+    f2 = Tr::sub(f0, s3);
+    f0 = Tr::add(f0, s3);
+    const E rot = Tr::mk(s4.y, Tr::wrap(-s4.x));
+    if (inverse) { f1 = Tr::sub(s5, rot); f3 = Tr::add(s5, rot); }
+    else { f1 = Tr::add(s5, rot); f3 = Tr::sub(s5, rot); }
+}
+
+// same butterfly when all three twiddles are tw[0] = 1: floats skip the (exact) products,
+// Q15 must still do them (tw[0] = 32767/32768)
+template <typename Tr, typename E>
+__device__ __forceinline__ void bfly4_unit(E &f0, E &f1, E &f2, E &f3, const E one, const int inverse)
+{
+    if constexpr (Tr::kFixed) {
+        bfly4_reg<Tr, E>(f0, f1, f2, f3, one, one, one, inverse);
+    } else {
+        const E s5 = Tr::sub(f0, f2);
+        f0 = Tr::add(f0, f2);
+        const E s3 = Tr::add(f1, f3);
+        const E s4 = Tr::sub(f1, f3);
+        f2 = Tr::sub(f0, s3);
+        f0 = Tr::add(f0, s3);
+        const E rot = Tr::mk(s4.y, -s4.x);
+        if (inverse) { f1 = Tr::sub(s5, rot); f3 = Tr::add(s5, rot); }
+        else { f1 = Tr::add(s5, rot); f3 = Tr::sub(s5, rot); }
+    }
+}
+
+struct Fft4096Args {
+    const void *in;
+    void *out;
+    const void *tw1;   // [16]      tw[256*k*q], entry k*4+q (q=0 unused -> tw[0])
+    const void *tw2;   // [15][16]  j<3: tw[64*C*(j+1)]; j=3+3*bm+(q-1): tw[(16*bm+C)*16*q]
+    const void *tw3;   // [15][256] j<3: tw[4*kk*(j+1)]; j=3+3*am+(q-1): tw[(256*am+kk)*q]
+    long long batch;
+    int inverse;
+};
+
+constexpr int kFftPad(int o) { return o + (o >> 8); }
+
+template <typename Tr>
+__global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
+{
+    using E = typename Tr::E;
+    __shared__ E F[4096 + 16];
+    const int t = threadIdx.x;
+    const E *__restrict__ tw1 = static_cast<const E *>(a.tw1);
+    const E *__restrict__ tw2 = static_cast<const E *>(a.tw2);
+    const E *__restrict__ tw3 = static_cast<const E *>(a.tw3);
+    const int inverse = a.inverse;
+
+    // pass-1 slot base: t = k0 + 4k1 + 16k2 + 64k3  ->  A = 4k0 + k1, B = 4k2 + k3
+    const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
+    const int base1 = 257 * A1 + 16 * B1;
+    // pass 2: thread = 16*A + C ; pass 3: thread = 16*B + C = kk
+    const int A2 = t >> 4, C2 = t & 15;
+    const int base2 = 257 * A2 + C2;
+
+    for (long long xf = blockIdx.x; xf < a.batch; xf += gridDim.x) {
+        const E *in = static_cast<const E *>(a.in) + xf * 4096;
+        E *out = static_cast<E *>(a.out) + xf * 4096;
+        E v[16];
+        // ---- pass 1: stages m=1 (over k5) and m=4 (over k4); v[4*k4 + k5] = in[t + 256*(k4 + 4*k5)]
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = in[t + 256 * j];
+        {
+            const E one = tw1[0];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) bfly4_unit<Tr, E>(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3], one, inverse);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k == 0) bfly4_unit<Tr, E>(v[0], v[4], v[8], v[12], one, inverse);
+                else bfly4_reg<Tr, E>(v[k], v[4 + k], v[8 + k], v[12 + k], tw1[4 * k + 1], tw1[4 * k + 2], tw1[4 * k + 3], inverse);
+            }
+        }
+        __syncthreads();   // previous transform's pass-3 reads are done
+#pragma unroll
+        for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
+        __syncthreads();
+        // ---- pass 2: stages m=16 (k = C, q = B mod 4) and m=64 (k = 16*(B mod 4) + C, q = B div 4)
+#pragma unroll
+        for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
+        {
+            const E t1 = tw2[0 * 16 + C2], t2 = tw2[1 * 16 + C2], t3 = tw2[2 * 16 + C2];
+#pragma unroll
+            for (int bd = 0; bd < 4; bd++) bfly4_reg<Tr, E>(v[4 * bd], v[4 * bd + 1], v[4 * bd + 2], v[4 * bd + 3], t1, t2, t3, inverse);
+#pragma unroll
+            for (int bm = 0; bm < 4; bm++)
+                bfly4_reg<Tr, E>(v[bm], v[4 + bm], v[8 + bm], v[12 + bm], tw2[(3 + 3 * bm) * 16 + C2], tw2[(4 + 3 * bm) * 16 + C2],
+                                 tw2[(5 + 3 * bm) * 16 + C2], inverse);
+        }
+#pragma unroll
+        for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
+        __syncthreads();
+        // ---- pass 3: stages m=256 (k = kk, q = A mod 4) and m=1024 (k = 256*(A mod 4) + kk, q = A div 4)
+#pragma unroll
+        for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
+        {
+            const E t1 = tw3[0 * 256 + t], t2 = tw3[1 * 256 + t], t3 = tw3[2 * 256 + t];
+#pragma unroll
+            for (int ad = 0; ad < 4; ad++) bfly4_reg<Tr, E>(v[4 * ad], v[4 * ad + 1], v[4 * ad + 2], v[4 * ad + 3], t1, t2, t3, inverse);
+#pragma unroll
+            for (int am = 0; am < 4; am++)
+                bfly4_reg<Tr, E>(v[am], v[4 + am], v[8 + am], v[12 + am], tw3[(3 + 3 * am) * 256 + t], tw3[(4 + 3 * am) * 256 + t],
+                                 tw3[(5 + 3 * am) * 256 + t], inverse);
+        }
+#pragma unroll
+        for (int A = 0; A < 16; A++) out[256 * A + t] = v[A];
+    }
+}
+
 // ------------------------------------------------------------------------ host: plan ---
 static int make_plan(FftPlan &p)
 {
@@ -238,7 +375,7 @@ static int make_plan(FftPlan &p)
     } while (n > 1);
     p.nstages = s;
     p.has_generic = false;
-    for (int i = 0; i < s; i++) if (p.radix[i] > 5) p.has_generic = true;
+    for (int i = 0; i < s; i++) if (p.radix[i] > 5 || p.radix[i] < 2) p.has_generic = true;   // n = 1 plans a radix-1 stage
     return B200C_OK;
 }
 
@@ -297,6 +434,32 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
     B200C_CUDA_TRY(cudaMemcpy(p.d_tw, tw.data(), tw.size(), cudaMemcpyHostToDevice));
     B200C_CUDA_TRY(cudaMemcpy(p.d_scatter, scatter.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
 
+    // fast path tables: gathered from the reference-order twiddle table (exact same values)
+    p.fast = 0;
+    if (n == 4096 && (dtype == B200C_CF32 || dtype == B200C_CI16)) {
+        auto at = [&](int idx) { return tw.data() + (size_t)(idx % n) * esz; };
+        std::vector<uint8_t> t1(16 * esz), t2(15 * 16 * esz), t3(15 * 256 * esz);
+        for (int k = 0; k < 4; k++)
+            for (int q = 0; q < 4; q++) std::memcpy(&t1[(k * 4 + q) * esz], at(q == 0 ? 0 : 256 * k * q), esz);
+        for (int C = 0; C < 16; C++) {
+            for (int q = 1; q < 4; q++) std::memcpy(&t2[((q - 1) * 16 + C) * esz], at(64 * C * q), esz);
+            for (int bm = 0; bm < 4; bm++)
+                for (int q = 1; q < 4; q++) std::memcpy(&t2[((3 + 3 * bm + q - 1) * 16 + C) * esz], at((16 * bm + C) * 16 * q), esz);
+        }
+        for (int kk = 0; kk < 256; kk++) {
+            for (int q = 1; q < 4; q++) std::memcpy(&t3[((q - 1) * 256 + kk) * esz], at(4 * kk * q), esz);
+            for (int am = 0; am < 4; am++)
+                for (int q = 1; q < 4; q++) std::memcpy(&t3[((3 + 3 * am + q - 1) * 256 + kk) * esz], at((256 * am + kk) * q), esz);
+        }
+        B200C_CUDA_TRY(cudaMalloc(&p.d_fast[0], t1.size()));
+        B200C_CUDA_TRY(cudaMalloc(&p.d_fast[1], t2.size()));
+        B200C_CUDA_TRY(cudaMalloc(&p.d_fast[2], t3.size()));
+        B200C_CUDA_TRY(cudaMemcpy(p.d_fast[0], t1.data(), t1.size(), cudaMemcpyHostToDevice));
+        B200C_CUDA_TRY(cudaMemcpy(p.d_fast[1], t2.data(), t2.size(), cudaMemcpyHostToDevice));
+        B200C_CUDA_TRY(cudaMemcpy(p.d_fast[2], t3.data(), t3.size(), cudaMemcpyHostToDevice));
+        p.fast = 4096;
+    }
+
     // execution shape
     const size_t bufs = p.has_generic ? 2 : 1;
     p.tpc = std::max(1, 2048 / n);
@@ -313,6 +476,7 @@ void fft_plan_destroy(FftPlan &p)
     if (p.d_tw) cudaFree(p.d_tw);
     if (p.d_scatter) cudaFree(p.d_scatter);
     if (p.d_scratch) cudaFree(p.d_scratch);
+    for (auto &f : p.d_fast) { if (f) cudaFree(f); f = nullptr; }
     p.d_tw = nullptr; p.d_scatter = nullptr; p.d_scratch = nullptr;
 }
 
@@ -335,6 +499,16 @@ int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_c
 {
     if (batch == 0) return B200C_OK;
     if (d_in == d_out) { set_error("FFT: in-place transforms are not supported (d_in == d_out)"); return B200C_ERR_INVALID; }
+    if (p.fast == 4096 && !p.force_staged) {
+        Fft4096Args f;
+        f.in = d_in; f.out = d_out; f.tw1 = p.d_fast[0]; f.tw2 = p.d_fast[1]; f.tw3 = p.d_fast[2];
+        f.batch = (long long)batch; f.inverse = p.inverse;
+        const int grid = (int)std::min<long long>((long long)batch, (long long)sm_count * 12);
+        if (p.dtype == B200C_CF32) fft4096_kernel<FloatTraits<float>><<<grid, 256, 0, stream>>>(f);
+        else fft4096_kernel<Q15Traits><<<grid, 256, 0, stream>>>(f);
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
     FftArgs a;
     a.in = d_in; a.out = d_out; a.tw = p.d_tw; a.scatter = p.d_scatter; a.scratch = nullptr;
     a.batch = (long long)batch; a.n = p.n; a.inverse = p.inverse; a.nstages = p.nstages; a.tpc = p.tpc;

@@ -29,7 +29,9 @@ struct FftPlan {
     size_t smem_bytes = 0;
     void *d_scratch = nullptr;  // generic-radix scratch for the global path
     size_t scratch_bytes = 0;
-    int fast = 0;               // 0 = generic staged kernel, >0 = specialised kernel id
+    int fast = 0;               // 0 = generic staged kernel, 4096 = three-pass register kernel
+    void *d_fast[3] = {nullptr, nullptr, nullptr};   // per-pass twiddle tables of the fast kernel
+    bool force_staged = false;  // tests: run the generic staged kernel even when a fast path exists
 };
 
 int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t smem_budget);
