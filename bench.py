@@ -305,17 +305,10 @@ def main():
     out = torch.empty((out_cap, nc), dtype=buf.dtype, device=dev)
     torch.cuda.synchronize()
 
+    from pothoscomms_b200 import sharding
+
     def halo_exchange():
-        if world == 1:
-            return
-        ops = []
-        if rank + 1 < world:
-            ops.append(dist.P2POp(dist.isend, buf[n_seg: n_seg + K - 1], rank + 1))
-        if rank > 0:
-            ops.append(dist.P2POp(dist.irecv, buf[: K - 1], rank - 1))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        sharding.exchange_halo(buf, K, rank, world)
 
     def step():
         halo_exchange()
@@ -390,7 +383,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
+            t = json.load(f).get(args.workload)
+            traffic = t["bytes_per_sample"] * n_seg if t else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -1,0 +1,44 @@
+"""Multi-GPU partitioning of the FIR path, host-side logic only.
+
+One long stream is cut into contiguous per-rank segments whose starts are multiples of the
+decimation M (the reference's decimation counter restarts at M on every work() call,
+filter/FIRFilter.cpp:283,291-292, so any M-aligned cut reproduces the single-stream output).
+The only cross-rank dependency is the K-1 samples of left history (:281,298): rank r sends the
+last K-1 samples of its segment to rank r+1 -- one NCCL P2P over NVLink per pass (gloo in the
+CPU tests).  Independent channels / FFT batches need no exchange at all: `channel_range`.
+"""
+from __future__ import annotations
+
+
+def segment_bounds(total_new: int, world: int, decim: int):
+    """[(start, stop)] over the `total_new` consumable samples (history excluded), every start a
+    multiple of `decim`, lengths as even as possible."""
+    blocks = total_new // decim
+    bounds = []
+    for r in range(world):
+        b0, b1 = blocks * r // world, blocks * (r + 1) // world
+        bounds.append((b0 * decim, b1 * decim))
+    return bounds
+
+
+def channel_range(num_channels: int, world: int, rank: int):
+    """Contiguous block of channels (or FFT batches) owned by `rank`: zero exchange."""
+    return num_channels * rank // world, num_channels * (rank + 1) // world
+
+
+def exchange_halo(buf, K: int, rank: int, world: int):
+    """`buf` is [K-1 halo | segment] on every rank.  Sends this rank's last K-1 samples to
+    rank+1 and receives rank-1's into buf[:K-1]; rank 0 keeps its own halo (the stream's true
+    first K-1 samples, history only).  One grouped P2P; works with nccl (GPU) and gloo (CPU)."""
+    import torch.distributed as dist
+    if world == 1 or K <= 1:
+        return
+    ops = []
+    n = buf.shape[0]
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, buf[n - (K - 1):], rank + 1))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, buf[: K - 1], rank - 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
