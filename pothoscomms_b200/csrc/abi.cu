@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,6 +48,9 @@ static int dev_info(int device, DevInfo &di)
 }
 
 constexpr int kHostSlots = 3;
+// automatic switch to the overlap-save kernel (cf32, L = M = 1): direct FFMA cost grows with K,
+// the fused FFT kernel's does not; below this many taps the direct kernel is near the HBM roof
+constexpr size_t kFirOsAutoMinTaps = 24;
 
 struct HostPipe {   // staging for the *_run_host entry points
     cudaStream_t streams[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -98,6 +102,8 @@ struct b200c_fir {
     FirTable table;
     FirDeviceState ds;
     HostPipe pipe;
+    FirOsPlan os;               // fused overlap-save path (cf32, L = M = 1, long taps)
+    bool use_os = false;
 };
 
 struct b200c_fft {
@@ -144,6 +150,20 @@ static int fir_refresh(b200c_fir *h)
     B200C_CUDA_TRY(cudaMemcpy(h->ds.d_taps, t.taps.data(), tb, cudaMemcpyHostToDevice));
     B200C_CUDA_TRY(cudaMemcpy(h->ds.d_off, t.off.data(), ob, cudaMemcpyHostToDevice));
     h->table = std::move(t);
+    // Long-tap complex float32 streams (no resampling) take the fused overlap-save kernel: one
+    // pass over HBM whatever K is.  B200C_FIR_ALGO=direct|fft overrides the automatic choice
+    // (fft: whenever applicable; direct: never).
+    h->use_os = false;
+    if (h->dtype == B200C_CF32 && h->M == 1 && h->L == 1 && h->ntaps >= 2 && h->ntaps <= kFirOsMaxTaps) {
+        const char *algo = std::getenv("B200C_FIR_ALGO");
+        const bool force_direct = algo && std::strcmp(algo, "direct") == 0, force_fft = algo && std::strcmp(algo, "fft") == 0;
+        if (!force_direct && (force_fft || h->ntaps >= kFirOsAutoMinTaps)) {
+            rc = fir_os_set_taps(h->os, h->taps.data(), h->ntaps, h->taps_kind == B200C_TAPS_COMPLEX,
+                                 std::min<size_t>(h->di.smem_optin, 200 * 1024));
+            if (rc) return rc;
+            h->use_os = h->os.ready;
+        }
+    }
     return B200C_OK;
 }
 
@@ -209,6 +229,7 @@ int b200c_fir_destroy(b200c_fir *h)
         DeviceGuard g(h->device);
         if (h->ds.d_taps) cudaFree(h->ds.d_taps);
         if (h->ds.d_off) cudaFree(h->ds.d_off);
+        fir_os_destroy(h->os);
         h->pipe.release();
     }
     delete h;
@@ -271,6 +292,7 @@ int b200c_fir_run(b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, 
     if (!d_in || !d_out) { set_error("b200c_fir_run: null device buffer"); return B200C_ERR_INVALID; }
     DeviceGuard g(h->device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", h->device); return B200C_ERR_CUDA; }
+    if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, c, h->di.sm_count, (cudaStream_t)stream);
     return fir_launch(h->table, h->ds, d_in, in_elems, d_out, c / h->M, h->di.sm_count, (cudaStream_t)stream);
 }
 
@@ -291,6 +313,9 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
     const size_t nblocks = c / M;
     // chunks of ~32 MiB of input, a whole number of blocks each
     size_t cb = std::max<size_t>(1, (32u << 20) / (esz * M));
+    // overlap-save: chunk on a whole number of FFT hops so chunked and one-shot runs use the very
+    // same block partition (bit-identical outputs)
+    if (h->use_os) cb = std::max<size_t>(1, cb / h->os.hop()) * h->os.hop();
     cb = std::min(cb, nblocks);
     const size_t in_chunk_elems = cb * M + K - 1, out_chunk_elems = cb * L;
     int rc = h->pipe.ensure(in_chunk_elems * esz, out_chunk_elems * esz);
@@ -305,7 +330,8 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
         const size_t have = in_elems > first ? std::min(want, in_elems - first) : 0;   // beyond: zero tail
         cudaStream_t s = h->pipe.streams[slot];
         if (have) B200C_CUDA_TRY(cudaMemcpyAsync(h->pipe.d_in[slot], src + first * esz, have * esz, cudaMemcpyHostToDevice, s));
-        rc = fir_launch(h->table, h->ds, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, h->di.sm_count, s);
+        rc = h->use_os ? fir_os_launch(h->os, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, h->di.sm_count, s)
+                       : fir_launch(h->table, h->ds, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, h->di.sm_count, s);
         if (rc) return rc;
         B200C_CUDA_TRY(cudaMemcpyAsync(dst + b0 * L * esz, h->pipe.d_out[slot], nb * L * esz, cudaMemcpyDeviceToHost, s));
     }

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -236,13 +237,24 @@ __global__ void __launch_bounds__(256) fft_staged_kernel(const FftArgs a)
 // one of the six access patterns is bank-conflict free.
 // Twiddles are pre-gathered on the host from the reference-order table into per-pass tables
 // laid out in consumption order (tw1: uniform; tw2[j][C]; tw3[j][16B+C]) so loads coalesce.
-template <typename Tr, typename E>
+// CONJ = multiply by the conjugate twiddle: lets the float overlap-save FIR run its inverse
+// transform from the FORWARD tables (kissfft's inverse twiddles are exactly the conjugates for
+// floats; NOT so for the Q15 table, whose floor(.5 + x) rounding is asymmetric -- the Q15 FFT
+// therefore always carries its own per-direction tables).
+template <typename Tr, bool CONJ, typename E>
+__device__ __forceinline__ E twmul(const E f, const E t)
+{
+    if constexpr (CONJ) return Tr::mk(f.x * t.x + f.y * t.y, f.y * t.x - f.x * t.y);
+    else return Tr::mul(f, t);
+}
+
+template <typename Tr, bool CONJ, typename E>
 __device__ __forceinline__ void bfly4_reg(E &f0, E &f1, E &f2, E &f3, const E t1, const E t2, const E t3, const int inverse)
 {
     f0 = Tr::fixdiv(f0, 4); f1 = Tr::fixdiv(f1, 4); f2 = Tr::fixdiv(f2, 4); f3 = Tr::fixdiv(f3, 4);
-    const E s0 = Tr::mul(f1, t1);
-    const E s1 = Tr::mul(f2, t2);
-    const E s2 = Tr::mul(f3, t3);
+    const E s0 = twmul<Tr, CONJ, E>(f1, t1);
+    const E s1 = twmul<Tr, CONJ, E>(f2, t2);
+    const E s2 = twmul<Tr, CONJ, E>(f3, t3);
     const E s5 = Tr::sub(f0, s1);
     f0 = Tr::add(f0, s1);
     const E s3 = Tr::add(s0, s2);
@@ -260,7 +272,7 @@ template <typename Tr, typename E>
 __device__ __forceinline__ void bfly4_unit(E &f0, E &f1, E &f2, E &f3, const E one, const int inverse)
 {
     if constexpr (Tr::kFixed) {
-        bfly4_reg<Tr, E>(f0, f1, f2, f3, one, one, one, inverse);
+        bfly4_reg<Tr, false, E>(f0, f1, f2, f3, one, one, one, inverse);
     } else {
         const E s5 = Tr::sub(f0, f2);
         f0 = Tr::add(f0, f2);
@@ -284,7 +296,61 @@ struct Fft4096Args {
     int inverse;
 };
 
-constexpr int kFftPad(int o) { return o + (o >> 8); }
+// The three passes on one transform.  In: v[4*k4 + k5] = x[t + 256*(k4 + 4*k5)] (thread t of
+// 256).  Out: v[A] = X[256*A + t].  F is the CTA's 4096+16 element exchange buffer.
+template <typename Tr, bool CONJ, typename E>
+__device__ __forceinline__ void fft4096_core(E (&v)[16], E *F, const E *__restrict__ tw1, const E *__restrict__ tw2,
+                                             const E *__restrict__ tw3, const int t, const int inverse)
+{
+    // pass-1 slot base: t = k0 + 4k1 + 16k2 + 64k3  ->  A = 4k0 + k1, B = 4k2 + k3
+    const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
+    const int base1 = 257 * A1 + 16 * B1;
+    // pass 2: thread = 16*A + C ; pass 3: thread = 16*B + C = kk
+    const int C2 = t & 15;
+    const int base2 = 257 * (t >> 4) + C2;
+    // ---- pass 1: stages m=1 (over k5) and m=4 (over k4)
+    {
+        const E one = tw1[0];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) bfly4_unit<Tr, E>(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3], one, inverse);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k == 0) bfly4_unit<Tr, E>(v[0], v[4], v[8], v[12], one, inverse);
+            else bfly4_reg<Tr, CONJ, E>(v[k], v[4 + k], v[8 + k], v[12 + k], tw1[4 * k + 1], tw1[4 * k + 2], tw1[4 * k + 3], inverse);
+        }
+    }
+    __syncthreads();   // earlier readers of F are done
+#pragma unroll
+    for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
+    __syncthreads();
+    // ---- pass 2: stages m=16 (k = C, q = B mod 4) and m=64 (k = 16*(B mod 4) + C, q = B div 4)
+#pragma unroll
+    for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
+    {
+        const E t1 = tw2[0 * 16 + C2], t2 = tw2[1 * 16 + C2], t3 = tw2[2 * 16 + C2];
+#pragma unroll
+        for (int bd = 0; bd < 4; bd++) bfly4_reg<Tr, CONJ, E>(v[4 * bd], v[4 * bd + 1], v[4 * bd + 2], v[4 * bd + 3], t1, t2, t3, inverse);
+#pragma unroll
+        for (int bm = 0; bm < 4; bm++)
+            bfly4_reg<Tr, CONJ, E>(v[bm], v[4 + bm], v[8 + bm], v[12 + bm], tw2[(3 + 3 * bm) * 16 + C2], tw2[(4 + 3 * bm) * 16 + C2],
+                                   tw2[(5 + 3 * bm) * 16 + C2], inverse);
+    }
+#pragma unroll
+    for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
+    __syncthreads();
+    // ---- pass 3: stages m=256 (k = kk, q = A mod 4) and m=1024 (k = 256*(A mod 4) + kk, q = A div 4)
+#pragma unroll
+    for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
+    {
+        const E t1 = tw3[0 * 256 + t], t2 = tw3[1 * 256 + t], t3 = tw3[2 * 256 + t];
+#pragma unroll
+        for (int ad = 0; ad < 4; ad++) bfly4_reg<Tr, CONJ, E>(v[4 * ad], v[4 * ad + 1], v[4 * ad + 2], v[4 * ad + 3], t1, t2, t3, inverse);
+#pragma unroll
+        for (int am = 0; am < 4; am++)
+            bfly4_reg<Tr, CONJ, E>(v[am], v[4 + am], v[8 + am], v[12 + am], tw3[(3 + 3 * am) * 256 + t], tw3[(4 + 3 * am) * 256 + t],
+                                   tw3[(5 + 3 * am) * 256 + t], inverse);
+    }
+}
 
 template <typename Tr>
 __global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
@@ -295,65 +361,72 @@ __global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
     const E *__restrict__ tw1 = static_cast<const E *>(a.tw1);
     const E *__restrict__ tw2 = static_cast<const E *>(a.tw2);
     const E *__restrict__ tw3 = static_cast<const E *>(a.tw3);
-    const int inverse = a.inverse;
-
-    // pass-1 slot base: t = k0 + 4k1 + 16k2 + 64k3  ->  A = 4k0 + k1, B = 4k2 + k3
-    const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
-    const int base1 = 257 * A1 + 16 * B1;
-    // pass 2: thread = 16*A + C ; pass 3: thread = 16*B + C = kk
-    const int A2 = t >> 4, C2 = t & 15;
-    const int base2 = 257 * A2 + C2;
-
     for (long long xf = blockIdx.x; xf < a.batch; xf += gridDim.x) {
         const E *in = static_cast<const E *>(a.in) + xf * 4096;
         E *out = static_cast<E *>(a.out) + xf * 4096;
         E v[16];
-        // ---- pass 1: stages m=1 (over k5) and m=4 (over k4); v[4*k4 + k5] = in[t + 256*(k4 + 4*k5)]
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = in[t + 256 * j];
-        {
-            const E one = tw1[0];
-#pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) bfly4_unit<Tr, E>(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3], one, inverse);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k == 0) bfly4_unit<Tr, E>(v[0], v[4], v[8], v[12], one, inverse);
-                else bfly4_reg<Tr, E>(v[k], v[4 + k], v[8 + k], v[12 + k], tw1[4 * k + 1], tw1[4 * k + 2], tw1[4 * k + 3], inverse);
-            }
-        }
-        __syncthreads();   // previous transform's pass-3 reads are done
-#pragma unroll
-        for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
-        __syncthreads();
-        // ---- pass 2: stages m=16 (k = C, q = B mod 4) and m=64 (k = 16*(B mod 4) + C, q = B div 4)
-#pragma unroll
-        for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
-        {
-            const E t1 = tw2[0 * 16 + C2], t2 = tw2[1 * 16 + C2], t3 = tw2[2 * 16 + C2];
-#pragma unroll
-            for (int bd = 0; bd < 4; bd++) bfly4_reg<Tr, E>(v[4 * bd], v[4 * bd + 1], v[4 * bd + 2], v[4 * bd + 3], t1, t2, t3, inverse);
-#pragma unroll
-            for (int bm = 0; bm < 4; bm++)
-                bfly4_reg<Tr, E>(v[bm], v[4 + bm], v[8 + bm], v[12 + bm], tw2[(3 + 3 * bm) * 16 + C2], tw2[(4 + 3 * bm) * 16 + C2],
-                                 tw2[(5 + 3 * bm) * 16 + C2], inverse);
-        }
-#pragma unroll
-        for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
-        __syncthreads();
-        // ---- pass 3: stages m=256 (k = kk, q = A mod 4) and m=1024 (k = 256*(A mod 4) + kk, q = A div 4)
-#pragma unroll
-        for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
-        {
-            const E t1 = tw3[0 * 256 + t], t2 = tw3[1 * 256 + t], t3 = tw3[2 * 256 + t];
-#pragma unroll
-            for (int ad = 0; ad < 4; ad++) bfly4_reg<Tr, E>(v[4 * ad], v[4 * ad + 1], v[4 * ad + 2], v[4 * ad + 3], t1, t2, t3, inverse);
-#pragma unroll
-            for (int am = 0; am < 4; am++)
-                bfly4_reg<Tr, E>(v[am], v[4 + am], v[8 + am], v[12 + am], tw3[(3 + 3 * am) * 256 + t], tw3[(4 + 3 * am) * 256 + t],
-                                 tw3[(5 + 3 * am) * 256 + t], inverse);
-        }
+        for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = in[t + 256 * j];   // coalesced, digit-reversed by register index
+        fft4096_core<Tr, false, E>(v, F, tw1, tw2, tw3, t, a.inverse);
 #pragma unroll
         for (int A = 0; A < 16; A++) out[256 * A + t] = v[A];
+    }
+}
+
+// ------------------------------------------- fused overlap-save FIR on the same FFT core ---
+// cf32 FIR with L = M = 1 and 2 <= K <= 2049 taps as fast convolution: each CTA takes 4096
+// consecutive input samples (K-1 of them history), transforms them (forward core), multiplies
+// by the taps' spectrum Hf (computed once on the host in double, pre-scaled by 1/4096),
+// transforms back (inverse core on the same tables, conjugate twiddles) and stores the
+// 4096-(K-1) alias-free outputs -- ONE pass over HBM: 8 B in + 8 B out per sample regardless
+// of K, instead of 8K flop/sample on the FMA pipe.
+// After the forward core thread t holds X[256*A + t], which is exactly the register layout the
+// inverse core's first pass wants (x[t + 256*j]) -- no exchange between the two transforms.
+struct FirOsArgs {
+    const void *in;     // element 0 = first history sample
+    void *out;
+    const void *hf;     // [4096] spectrum of the taps / 4096, natural order
+    const void *tw1, *tw2, *tw3;   // forward tables of the 4096 plan
+    long long n_in;     // valid input elements (beyond: zeros -> burst zero tail)
+    long long n_out;    // outputs to produce
+    int K;              // taps
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) fir_os4096_kernel(const FirOsArgs a)
+{
+    using Tr = FloatTraits<float>;
+    using E = float2;
+    __shared__ E F[4096 + 16];
+    const int t = threadIdx.x;
+    const E *__restrict__ tw1 = static_cast<const E *>(a.tw1);
+    const E *__restrict__ tw2 = static_cast<const E *>(a.tw2);
+    const E *__restrict__ tw3 = static_cast<const E *>(a.tw3);
+    const E *__restrict__ hf = static_cast<const E *>(a.hf);
+    const E *__restrict__ in = static_cast<const E *>(a.in);
+    E *__restrict__ out = static_cast<E *>(a.out);
+    const int hop = 4096 - (a.K - 1);
+    const long long nblk = (a.n_out + hop - 1) / hop;
+    for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const long long base = b * hop;
+        E v[16], w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const long long g = base + t + 256 * j;
+            v[4 * (j & 3) + (j >> 2)] = g < a.n_in ? in[g] : make_float2(0.f, 0.f);
+        }
+        fft4096_core<Tr, false, E>(v, F, tw1, tw2, tw3, t, 0);
+        // pointwise product with the tap spectrum, handed over in inverse-pass-1 register order
+#pragma unroll
+        for (int A = 0; A < 16; A++) w[4 * (A & 3) + (A >> 2)] = Tr::mul(v[A], hf[256 * A + t]);
+        fft4096_core<Tr, true, E>(w, F, tw1, tw2, tw3, t, 1);
+        // circular result c[i], i = 256*A + t; alias-free part i >= K-1 is y[base + i - (K-1)]
+#pragma unroll
+        for (int A = 0; A < 16; A++) {
+            const int i = 256 * A + t;
+            const long long o = base + i - (a.K - 1);
+            if (i >= a.K - 1 && o < a.n_out) out[o] = w[A];
+        }
     }
 }
 
@@ -532,6 +605,66 @@ int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_c
     case B200C_CF64: return launch_staged<FloatTraits<double>>(p, a, grid, stream);
     default: return launch_staged<Q15Traits>(p, a, grid, stream);
     }
+}
+
+// ------------------------------------------------------------- host: overlap-save FIR ---
+int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t smem_budget)
+{
+    p.ready = false;
+    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
+    if (!p.have_fwd) {
+        int rc = fft_plan_create(p.fwd, B200C_CF32, 4096, 0, smem_budget);
+        if (rc) { fft_plan_destroy(p.fwd); return rc; }
+        p.have_fwd = true;
+    }
+    // Hf[f] = (1/4096) * sum_k h[k] exp(-2*pi*i*f*k/4096), accumulated in double
+    const int N = 4096;
+    std::vector<double> cs(N), sn(N);
+    for (int i = 0; i < N; i++) {
+        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
+        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
+    }
+    std::vector<float> hf(2 * N);
+    for (int f = 0; f < N; f++) {
+        double re = 0, im = 0;
+        for (size_t k = 0; k < ntaps; k++) {
+            const double hr = complex_taps ? taps[2 * k] : taps[k], hi = complex_taps ? taps[2 * k + 1] : 0.0;
+            const int idx = (int)(((long long)f * (long long)k) & (N - 1));
+            re += hr * cs[idx] - hi * sn[idx];
+            im += hr * sn[idx] + hi * cs[idx];
+        }
+        hf[2 * f] = (float)(re / N);
+        hf[2 * f + 1] = (float)(im / N);
+    }
+    if (!p.d_hf) B200C_CUDA_TRY(cudaMalloc(&p.d_hf, sizeof(float) * 2 * N));
+    B200C_CUDA_TRY(cudaMemcpy(p.d_hf, hf.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
+    p.K = (int)ntaps;
+    p.ready = true;
+    return B200C_OK;
+}
+
+void fir_os_destroy(FirOsPlan &p)
+{
+    if (p.have_fwd) fft_plan_destroy(p.fwd);
+    if (p.d_hf) cudaFree(p.d_hf);
+    p.d_hf = nullptr; p.have_fwd = false; p.ready = false;
+}
+
+int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                  cudaStream_t stream)
+{
+    if (n_out == 0) return B200C_OK;
+    FirOsArgs a;
+    a.in = d_in; a.out = d_out; a.hf = p.d_hf;
+    a.tw1 = p.fwd.d_fast[0]; a.tw2 = p.fwd.d_fast[1]; a.tw3 = p.fwd.d_fast[2];
+    a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
+    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * 12);
+    static const int variant = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 3; }();
+    if (variant == 2) fir_os4096_kernel<2><<<grid, 256, 0, stream>>>(a);
+    else fir_os4096_kernel<3><<<grid, 256, 0, stream>>>(a);
+    B200C_CUDA_TRY(cudaGetLastError());
+    return B200C_OK;
 }
 
 } // namespace b200c

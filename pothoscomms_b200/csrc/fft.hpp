@@ -38,4 +38,19 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
 void fft_plan_destroy(FftPlan &p);
 int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream);
 
+// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps) on the 4096-point FFT core.
+struct FirOsPlan {
+    FftPlan fwd;              // forward 4096 cf32 plan (its fast-path tables are reused for the inverse)
+    bool have_fwd = false;
+    void *d_hf = nullptr;     // [4096] float2: spectrum of the taps / 4096
+    int K = 0;
+    bool ready = false;
+    int hop() const { return 4096 - (K - 1); }
+};
+constexpr size_t kFirOsMaxTaps = 2049;
+int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t smem_budget);
+void fir_os_destroy(FirOsPlan &p);
+int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                  cudaStream_t stream);
+
 } // namespace b200c

@@ -38,7 +38,9 @@ def _run_gpu(code, taps_type, taps, M, L, x, zero_tail=False, out_capacity=None)
     return y.cpu().numpy(), cons, prod, f
 
 
-def _compare(oracle, code, y_gpu, y_ref, what=""):
+def _compare(oracle, code, y_gpu, y_ref, what="", rms_hint=None):
+    """rms_hint: the stream's expected output RMS, used as the denominator when the compared
+    window is too short (< 256 values) for its own RMS to be a meaningful statistic."""
     assert y_gpu.shape == y_ref.shape, what
     sc = oracle.scalar_np(code)
     if np.issubdtype(sc, np.integer):
@@ -46,6 +48,8 @@ def _compare(oracle, code, y_gpu, y_ref, what=""):
     else:
         ref = y_ref.astype(np.float64)
         rms = np.sqrt(np.mean(ref ** 2)) if ref.size else 1.0
+        if rms_hint is not None and ref.size < 256:
+            rms = max(rms, rms_hint)
         err = np.sqrt(np.mean((y_gpu.astype(np.float64) - ref) ** 2)) if ref.size else 0.0
         tol = FLOAT_TOL if sc == np.float32 else DOUBLE_TOL
         assert err <= tol * max(rms, 1e-30), f"{what}: rel rms err {err / max(rms, 1e-30):.3e} > {tol}"
@@ -291,3 +295,78 @@ def test_full_size_linearity_and_sampled_windows(oracle, cuda_device):
     err = torch.sqrt(torch.mean((y12 - lin).double() ** 2)).item()
     rms = torch.sqrt(torch.mean(lin.double() ** 2)).item()
     assert err <= 2e-6 * rms + 1e-7
+
+
+def _with_algo(algo):
+    import contextlib
+    import os
+
+    @contextlib.contextmanager
+    def cm():
+        old = os.environ.get("B200C_FIR_ALGO")
+        os.environ["B200C_FIR_ALGO"] = algo
+        try:
+            yield
+        finally:
+            if old is None:
+                os.environ.pop("B200C_FIR_ALGO", None)
+            else:
+                os.environ["B200C_FIR_ALGO"] = old
+    return cm()
+
+
+@pytest.mark.parametrize("ntaps", [2, 3, 24, 64, 255, 256, 1024, 2048, 2049])
+@pytest.mark.parametrize("taps_type", ["REAL", "COMPLEX"])
+def test_overlap_save_path_matches_oracle_and_direct(oracle, cuda_device, ntaps, taps_type):
+    """The fused FFT (overlap-save) kernel that long-tap cf32 streams take must agree with the
+    oracle within the float tolerance, for ragged lengths, tiny inputs and the burst zero tail,
+    and with the direct FFMA kernel it replaces."""
+    rng = np.random.default_rng(ntaps * 3 + (taps_type == "COMPLEX"))
+    taps = rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    if taps_type == "COMPLEX":
+        taps = taps + 1j * rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    hop = 4096 - (ntaps - 1)
+    rms_hint = float(np.sqrt(np.sum(np.abs(taps) ** 2)))   # unit-variance components in => this per component out
+    for n_new, zero_tail in ((1, False), (hop - 1, False), (hop, False), (hop + 1, False), (3 * hop + 17, False),
+                             (50000, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, oracle.CF32, ntaps - 1 + n_new, rng)
+        y_ref, c_ref, p_ref = oracle.fir(oracle.CF32, taps_type == "COMPLEX", taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("fft"):
+            y_os, cons, prod, _ = _run_gpu(oracle.CF32, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, oracle.CF32, y_os, y_ref, f"overlap-save K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
+        with _with_algo("direct"):
+            y_d, cons_d, prod_d, _ = _run_gpu(oracle.CF32, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+        assert (cons_d, prod_d) == (c_ref, p_ref)
+        _compare(oracle, oracle.CF32, y_d, y_ref, f"direct K={ntaps} n={n_new}", rms_hint)
+
+
+def test_overlap_save_limits_fall_back_to_direct(oracle, cuda_device):
+    """More than 2049 taps, resampling, real data and integer types never take the FFT path."""
+    rng = np.random.default_rng(4)
+    with _with_algo("fft"):
+        taps = rng.standard_normal(2050) / 45.0
+        x = _rand_input(oracle, oracle.CF32, 2049 + 5000, rng)
+        y_ref, c_ref, p_ref = oracle.fir(oracle.CF32, False, taps, 1, 1, x)
+        y, cons, prod, _ = _run_gpu(oracle.CF32, "REAL", taps, 1, 1, x)
+        assert (cons, prod) == (c_ref, p_ref)
+        _compare(oracle, oracle.CF32, y, y_ref, "2050 taps")
+        # int16 stays bit-exact (never FFT)
+        xi = _rand_input(oracle, oracle.CI16, 5000, rng)
+        t2 = rng.standard_normal(64) * 0.1
+        yi_ref, _, _ = oracle.fir(oracle.CI16, False, t2, 1, 1, xi)
+        yi, _, _, _ = _run_gpu(oracle.CI16, "REAL", t2, 1, 1, xi)
+        assert np.array_equal(yi, yi_ref)
+
+
+def test_overlap_save_strong_attenuation_stays_in_tolerance(oracle, cuda_device):
+    """Tone in the pass band + noise through a 60 dB stop-band filter: the FFT path's error is
+    measured against the OUTPUT rms (north_star tolerance), the case where fast convolution is
+    least comfortable."""
+    from pothoscomms_b200 import workloads as wl
+    taps, tt = wl.config_taps("headline")
+    x = wl.tone_noise_numpy(oracle.CF32, 1 << 17, seed=99)
+    y_ref, _, _ = oracle.fir(oracle.CF32, True, taps, 1, 1, x, threads=8)
+    with _with_algo("fft"):
+        y, _, _, _ = _run_gpu(oracle.CF32, tt, taps, 1, 1, x)
+    _compare(oracle, oracle.CF32, y, y_ref, "headline via overlap-save")
