@@ -39,6 +39,13 @@ WORKLOADS = {
     "c2": ("complex_int16", "c2", 1, 1, 28, 8.0),
     "c3": ("complex_float32", "c3", 2, 3, 28, 20.0),
     "c5": ("complex_float32", "c5", 1, 1, 26, 16.0),
+    # short-tap streams: the HBM-bound side of the path (north_star's ">= 70 % of HBM roofline
+    # for short-tap FIR and resampling")
+    "short": ("complex_float32", "short", 1, 1, 28, 16.0),
+    "short_cx": ("complex_float32", "short_cx", 1, 1, 28, 16.0),
+    "resamp_short": ("complex_float32", "resamp_short", 2, 3, 28, 20.0),
+    "real64": ("float32", "real64", 1, 1, 29, 8.0),
+    "real64_i16": ("int16", "real64", 1, 1, 29, 4.0),
 }
 
 
@@ -295,7 +302,7 @@ def main():
     fir.set_rates(M, L)
     K = fir.K
     n_seg = (1 << log2n) // M * M           # new samples per rank and step (multiple of M: SURVEY 8e)
-    nc = 2
+    nc = 2 if code & 1 else 1
 
     # [K-1 halo | n_seg samples]; rank r's segment is samples [r*n_seg, (r+1)*n_seg) of one stream
     buf = torch.empty((K - 1 + n_seg, nc), dtype=wl.tone_noise_torch(code, 1, 0, dev).dtype, device=dev)

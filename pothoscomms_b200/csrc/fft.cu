@@ -392,40 +392,152 @@ struct FirOsArgs {
     int K;              // taps
 };
 
+// Packed complex arithmetic: sm_100a has two-lane fp32 instructions (FADD2/FMUL2/FFMA2, PTX
+// *.f32x2) whose operands take a half swap, a per-half negate and a scalar broadcast for free,
+// so on interleaved (re, im) register pairs a complex add is ONE instruction and a complex
+// multiply TWO (FMUL2 + FFMA2).  A packed instruction occupies the FMA pipe for two cycles but
+// only one issue slot (tools/probe_issue.cu) -- and this kernel is issue/L1 bound, not FMA bound.
+typedef unsigned long long c2;   // (re, im) in one aligned 64-bit register pair
+__device__ __forceinline__ c2 pk(float a, float b) { c2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(c2 p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ c2 fma2(c2 a, c2 b, c2 c) { c2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ c2 mul2(c2 a, c2 b) { c2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ c2 add2(c2 a, c2 b) { c2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ c2 sub2(c2 a, c2 b) { c2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// Cache policy: the per-CTA working set that must stay in L1 is the tables (tap spectrum 32 KB,
+// pass-3 twiddles 30 KB); the sample stream is touched once.  ncu showed ~40 % of the table
+// loads missing L1 (evicted by the stream) and the dependent FMULs stalling on L2 latency, so
+// stream accesses bypass L1 (ld/st.global.cg) and only the tables live there.
+__device__ __forceinline__ c2 ld_stream(const c2 *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_stream(c2 *p, c2 v) { __stcg(p, v); }
+__device__ __forceinline__ c2 ld_keep(const c2 *p) { return *p; }
+// f * w  (CONJ: f * conj(w))
+template <bool CONJ> __device__ __forceinline__ c2 cmul_p(c2 f, c2 w)
+{
+    float fx, fy, wx, wy;
+    upk(f, fx, fy); upk(w, wx, wy);
+    return fma2(f, pk(wx, wx), mul2(CONJ ? pk(fy, -fx) : pk(-fy, fx), pk(wy, wy)));
+}
+// forward: -i*s = (s.y, -s.x); inverse: +i*s
+template <bool INV> __device__ __forceinline__ c2 rot_p(c2 s) { float x, y; upk(s, x, y); return INV ? pk(-y, x) : pk(y, -x); }
+
+template <bool CONJ, bool INV>
+__device__ __forceinline__ void bfly4_p(c2 &f0, c2 &f1, c2 &f2, c2 &f3, const c2 t1, const c2 t2, const c2 t3)
+{
+    const c2 s0 = cmul_p<CONJ>(f1, t1), s1 = cmul_p<CONJ>(f2, t2), s2 = cmul_p<CONJ>(f3, t3);
+    const c2 s5 = sub2(f0, s1);
+    f0 = add2(f0, s1);
+    const c2 s3 = add2(s0, s2), s4 = sub2(s0, s2);
+    f2 = sub2(f0, s3);
+    f0 = add2(f0, s3);
+    const c2 r = rot_p<INV>(s4);
+    f1 = add2(s5, r);
+    f3 = sub2(s5, r);
+}
+template <bool INV>
+__device__ __forceinline__ void bfly4_unit_p(c2 &f0, c2 &f1, c2 &f2, c2 &f3)
+{
+    const c2 s5 = sub2(f0, f2);
+    f0 = add2(f0, f2);
+    const c2 s3 = add2(f1, f3), s4 = sub2(f1, f3);
+    f2 = sub2(f0, s3);
+    f0 = add2(f0, s3);
+    const c2 r = rot_p<INV>(s4);
+    f1 = add2(s5, r);
+    f3 = sub2(s5, r);
+}
+
+// fft4096_core on packed registers (same slots, same tables, same exchange layout).
+template <bool CONJ, bool INV>
+__device__ __forceinline__ void fft4096_core_p(c2 (&v)[16], c2 *F, const c2 *__restrict__ tw1, const c2 *__restrict__ tw2,
+                                               const c2 *__restrict__ tw3, const int t)
+{
+    const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
+    const int base1 = 257 * A1 + 16 * B1;
+    const int C2 = t & 15;
+    const int base2 = 257 * (t >> 4) + C2;
+#pragma unroll
+    for (int k4 = 0; k4 < 4; k4++) bfly4_unit_p<INV>(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+    bfly4_unit_p<INV>(v[0], v[4], v[8], v[12]);
+#pragma unroll
+    for (int k = 1; k < 4; k++) bfly4_p<CONJ, INV>(v[k], v[4 + k], v[8 + k], v[12 + k], ld_keep(tw1 + 4 * k + 1), ld_keep(tw1 + 4 * k + 2), ld_keep(tw1 + 4 * k + 3));
+    __syncthreads();   // earlier readers of F are done
+#pragma unroll
+    for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
+    {
+        const c2 t1 = ld_keep(tw2 + 0 * 16 + C2), t2 = ld_keep(tw2 + 1 * 16 + C2), t3 = ld_keep(tw2 + 2 * 16 + C2);
+#pragma unroll
+        for (int bd = 0; bd < 4; bd++) bfly4_p<CONJ, INV>(v[4 * bd], v[4 * bd + 1], v[4 * bd + 2], v[4 * bd + 3], t1, t2, t3);
+#pragma unroll
+        for (int bm = 0; bm < 4; bm++)
+            bfly4_p<CONJ, INV>(v[bm], v[4 + bm], v[8 + bm], v[12 + bm], ld_keep(tw2 + (3 + 3 * bm) * 16 + C2),
+                               ld_keep(tw2 + (4 + 3 * bm) * 16 + C2), ld_keep(tw2 + (5 + 3 * bm) * 16 + C2));
+    }
+#pragma unroll
+    for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
+    __syncthreads();
+#pragma unroll
+    for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
+    {
+        const c2 t1 = ld_keep(tw3 + 0 * 256 + t), t2 = ld_keep(tw3 + 1 * 256 + t), t3 = ld_keep(tw3 + 2 * 256 + t);
+#pragma unroll
+        for (int ad = 0; ad < 4; ad++) bfly4_p<CONJ, INV>(v[4 * ad], v[4 * ad + 1], v[4 * ad + 2], v[4 * ad + 3], t1, t2, t3);
+#pragma unroll
+        for (int am = 0; am < 4; am++)
+            bfly4_p<CONJ, INV>(v[am], v[4 + am], v[8 + am], v[12 + am], ld_keep(tw3 + (3 + 3 * am) * 256 + t),
+                               ld_keep(tw3 + (4 + 3 * am) * 256 + t), ld_keep(tw3 + (5 + 3 * am) * 256 + t));
+    }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) fir_os4096_kernel(const FirOsArgs a)
 {
-    using Tr = FloatTraits<float>;
-    using E = float2;
-    __shared__ E F[4096 + 16];
+    __shared__ c2 F[4096 + 16];
     const int t = threadIdx.x;
-    const E *__restrict__ tw1 = static_cast<const E *>(a.tw1);
-    const E *__restrict__ tw2 = static_cast<const E *>(a.tw2);
-    const E *__restrict__ tw3 = static_cast<const E *>(a.tw3);
-    const E *__restrict__ hf = static_cast<const E *>(a.hf);
-    const E *__restrict__ in = static_cast<const E *>(a.in);
-    E *__restrict__ out = static_cast<E *>(a.out);
-    const int hop = 4096 - (a.K - 1);
+    const c2 *__restrict__ tw1 = static_cast<const c2 *>(a.tw1);
+    const c2 *__restrict__ tw2 = static_cast<const c2 *>(a.tw2);
+    const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
+    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    c2 *__restrict__ out = static_cast<c2 *>(a.out);
+    const int Km1 = a.K - 1;
+    const int hop = 4096 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
     for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
         const long long base = b * hop;
-        E v[16], w[16];
+        c2 v[16], w[16];
+        if (base + 4096 <= a.n_in) {   // interior block: no bounds checks
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const long long g = base + t + 256 * j;
-            v[4 * (j & 3) + (j >> 2)] = g < a.n_in ? in[g] : make_float2(0.f, 0.f);
+            for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = ld_stream(in + base + t + 256 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const long long g = base + t + 256 * j;
+                v[4 * (j & 3) + (j >> 2)] = g < a.n_in ? ld_stream(in + g) : 0ull;
+            }
         }
-        fft4096_core<Tr, false, E>(v, F, tw1, tw2, tw3, t, 0);
+        fft4096_core_p<false, false>(v, F, tw1, tw2, tw3, t);
         // pointwise product with the tap spectrum, handed over in inverse-pass-1 register order
 #pragma unroll
-        for (int A = 0; A < 16; A++) w[4 * (A & 3) + (A >> 2)] = Tr::mul(v[A], hf[256 * A + t]);
-        fft4096_core<Tr, true, E>(w, F, tw1, tw2, tw3, t, 1);
+        for (int A = 0; A < 16; A++) w[4 * (A & 3) + (A >> 2)] = cmul_p<false>(v[A], ld_keep(hf + 256 * A + t));
+        fft4096_core_p<true, true>(w, F, tw1, tw2, tw3, t);
         // circular result c[i], i = 256*A + t; alias-free part i >= K-1 is y[base + i - (K-1)]
+        c2 *o = out + (base - Km1);
+        if (base + hop <= a.n_out) {
 #pragma unroll
-        for (int A = 0; A < 16; A++) {
-            const int i = 256 * A + t;
-            const long long o = base + i - (a.K - 1);
-            if (i >= a.K - 1 && o < a.n_out) out[o] = w[A];
+            for (int A = 0; A < 16; A++) {
+                const int i = 256 * A + t;
+                if (i >= Km1) st_stream(o + i, w[A]);
+            }
+        } else {
+#pragma unroll
+            for (int A = 0; A < 16; A++) {
+                const int i = 256 * A + t;
+                if (i >= Km1 && base + i - Km1 < a.n_out) st_stream(o + i, w[A]);
+            }
         }
     }
 }

@@ -61,6 +61,16 @@ def config_taps(name: str):
         return root_raised_cosine(255, 3.0, 0.5), "REAL"
     if name == "c5":
         return complex_bandpass(1024, F0 / FS, 0.02), "COMPLEX"
+    # short-tap streams (north_star: "the short-tap path stays on FFMA and is reported as an
+    # HBM-bound stream"): not BASELINE configs, bench-only
+    if name == "short":      # 16 real taps
+        return sinc_lowpass(16, 0.1), "REAL"
+    if name == "short_cx":   # 16 complex taps
+        return complex_bandpass(16, F0 / FS, 0.1), "COMPLEX"
+    if name == "resamp_short":   # L=3, M=2, 48-tap RRC (16 taps per phase)
+        return root_raised_cosine(48, 3.0, 0.5), "REAL"
+    if name == "real64":     # real data, 64 real taps
+        return sinc_lowpass(64, 0.1), "REAL"
     raise KeyError(name)
 
 
