@@ -373,175 +373,6 @@ __global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
     }
 }
 
-// ------------------------------------------- fused overlap-save FIR on the same FFT core ---
-// cf32 FIR with L = M = 1 and 2 <= K <= 2049 taps as fast convolution: each CTA takes 4096
-// consecutive input samples (K-1 of them history), transforms them (forward core), multiplies
-// by the taps' spectrum Hf (computed once on the host in double, pre-scaled by 1/4096),
-// transforms back (inverse core on the same tables, conjugate twiddles) and stores the
-// 4096-(K-1) alias-free outputs -- ONE pass over HBM: 8 B in + 8 B out per sample regardless
-// of K, instead of 8K flop/sample on the FMA pipe.
-// After the forward core thread t holds X[256*A + t], which is exactly the register layout the
-// inverse core's first pass wants (x[t + 256*j]) -- no exchange between the two transforms.
-struct FirOsArgs {
-    const void *in;     // element 0 = first history sample
-    void *out;
-    const void *hf;     // [4096] spectrum of the taps / 4096, natural order
-    const void *tw1, *tw2, *tw3;   // forward tables of the 4096 plan
-    long long n_in;     // valid input elements (beyond: zeros -> burst zero tail)
-    long long n_out;    // outputs to produce
-    int K;              // taps
-};
-
-// Packed complex arithmetic: sm_100a has two-lane fp32 instructions (FADD2/FMUL2/FFMA2, PTX
-// *.f32x2) whose operands take a half swap, a per-half negate and a scalar broadcast for free,
-// so on interleaved (re, im) register pairs a complex add is ONE instruction and a complex
-// multiply TWO (FMUL2 + FFMA2).  A packed instruction occupies the FMA pipe for two cycles but
-// only one issue slot (tools/probe_issue.cu) -- and this kernel is issue/L1 bound, not FMA bound.
-typedef unsigned long long c2;   // (re, im) in one aligned 64-bit register pair
-__device__ __forceinline__ c2 pk(float a, float b) { c2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk(c2 p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
-__device__ __forceinline__ c2 fma2(c2 a, c2 b, c2 c) { c2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ c2 mul2(c2 a, c2 b) { c2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ c2 add2(c2 a, c2 b) { c2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ c2 sub2(c2 a, c2 b) { c2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// Cache policy: the per-CTA working set that must stay in L1 is the tables (tap spectrum 32 KB,
-// pass-3 twiddles 30 KB); the sample stream is touched once.  ncu showed ~40 % of the table
-// loads missing L1 (evicted by the stream) and the dependent FMULs stalling on L2 latency, so
-// stream accesses bypass L1 (ld/st.global.cg) and only the tables live there.
-__device__ __forceinline__ c2 ld_stream(const c2 *p) { return __ldcg(p); }
-__device__ __forceinline__ void st_stream(c2 *p, c2 v) { __stcg(p, v); }
-__device__ __forceinline__ c2 ld_keep(const c2 *p) { return *p; }
-// f * w  (CONJ: f * conj(w))
-template <bool CONJ> __device__ __forceinline__ c2 cmul_p(c2 f, c2 w)
-{
-    float fx, fy, wx, wy;
-    upk(f, fx, fy); upk(w, wx, wy);
-    return fma2(f, pk(wx, wx), mul2(CONJ ? pk(fy, -fx) : pk(-fy, fx), pk(wy, wy)));
-}
-// forward: -i*s = (s.y, -s.x); inverse: +i*s
-template <bool INV> __device__ __forceinline__ c2 rot_p(c2 s) { float x, y; upk(s, x, y); return INV ? pk(-y, x) : pk(y, -x); }
-
-template <bool CONJ, bool INV>
-__device__ __forceinline__ void bfly4_p(c2 &f0, c2 &f1, c2 &f2, c2 &f3, const c2 t1, const c2 t2, const c2 t3)
-{
-    const c2 s0 = cmul_p<CONJ>(f1, t1), s1 = cmul_p<CONJ>(f2, t2), s2 = cmul_p<CONJ>(f3, t3);
-    const c2 s5 = sub2(f0, s1);
-    f0 = add2(f0, s1);
-    const c2 s3 = add2(s0, s2), s4 = sub2(s0, s2);
-    f2 = sub2(f0, s3);
-    f0 = add2(f0, s3);
-    const c2 r = rot_p<INV>(s4);
-    f1 = add2(s5, r);
-    f3 = sub2(s5, r);
-}
-template <bool INV>
-__device__ __forceinline__ void bfly4_unit_p(c2 &f0, c2 &f1, c2 &f2, c2 &f3)
-{
-    const c2 s5 = sub2(f0, f2);
-    f0 = add2(f0, f2);
-    const c2 s3 = add2(f1, f3), s4 = sub2(f1, f3);
-    f2 = sub2(f0, s3);
-    f0 = add2(f0, s3);
-    const c2 r = rot_p<INV>(s4);
-    f1 = add2(s5, r);
-    f3 = sub2(s5, r);
-}
-
-// fft4096_core on packed registers (same slots, same tables, same exchange layout).
-template <bool CONJ, bool INV>
-__device__ __forceinline__ void fft4096_core_p(c2 (&v)[16], c2 *F, const c2 *__restrict__ tw1, const c2 *__restrict__ tw2,
-                                               const c2 *__restrict__ tw3, const int t)
-{
-    const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
-    const int base1 = 257 * A1 + 16 * B1;
-    const int C2 = t & 15;
-    const int base2 = 257 * (t >> 4) + C2;
-#pragma unroll
-    for (int k4 = 0; k4 < 4; k4++) bfly4_unit_p<INV>(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-    bfly4_unit_p<INV>(v[0], v[4], v[8], v[12]);
-#pragma unroll
-    for (int k = 1; k < 4; k++) bfly4_p<CONJ, INV>(v[k], v[4 + k], v[8 + k], v[12 + k], ld_keep(tw1 + 4 * k + 1), ld_keep(tw1 + 4 * k + 2), ld_keep(tw1 + 4 * k + 3));
-    __syncthreads();   // earlier readers of F are done
-#pragma unroll
-    for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
-    __syncthreads();
-#pragma unroll
-    for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
-    {
-        const c2 t1 = ld_keep(tw2 + 0 * 16 + C2), t2 = ld_keep(tw2 + 1 * 16 + C2), t3 = ld_keep(tw2 + 2 * 16 + C2);
-#pragma unroll
-        for (int bd = 0; bd < 4; bd++) bfly4_p<CONJ, INV>(v[4 * bd], v[4 * bd + 1], v[4 * bd + 2], v[4 * bd + 3], t1, t2, t3);
-#pragma unroll
-        for (int bm = 0; bm < 4; bm++)
-            bfly4_p<CONJ, INV>(v[bm], v[4 + bm], v[8 + bm], v[12 + bm], ld_keep(tw2 + (3 + 3 * bm) * 16 + C2),
-                               ld_keep(tw2 + (4 + 3 * bm) * 16 + C2), ld_keep(tw2 + (5 + 3 * bm) * 16 + C2));
-    }
-#pragma unroll
-    for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
-    __syncthreads();
-#pragma unroll
-    for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
-    {
-        const c2 t1 = ld_keep(tw3 + 0 * 256 + t), t2 = ld_keep(tw3 + 1 * 256 + t), t3 = ld_keep(tw3 + 2 * 256 + t);
-#pragma unroll
-        for (int ad = 0; ad < 4; ad++) bfly4_p<CONJ, INV>(v[4 * ad], v[4 * ad + 1], v[4 * ad + 2], v[4 * ad + 3], t1, t2, t3);
-#pragma unroll
-        for (int am = 0; am < 4; am++)
-            bfly4_p<CONJ, INV>(v[am], v[4 + am], v[8 + am], v[12 + am], ld_keep(tw3 + (3 + 3 * am) * 256 + t),
-                               ld_keep(tw3 + (4 + 3 * am) * 256 + t), ld_keep(tw3 + (5 + 3 * am) * 256 + t));
-    }
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) fir_os4096_kernel(const FirOsArgs a)
-{
-    __shared__ c2 F[4096 + 16];
-    const int t = threadIdx.x;
-    const c2 *__restrict__ tw1 = static_cast<const c2 *>(a.tw1);
-    const c2 *__restrict__ tw2 = static_cast<const c2 *>(a.tw2);
-    const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
-    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
-    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
-    c2 *__restrict__ out = static_cast<c2 *>(a.out);
-    const int Km1 = a.K - 1;
-    const int hop = 4096 - Km1;
-    const long long nblk = (a.n_out + hop - 1) / hop;
-    for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-        const long long base = b * hop;
-        c2 v[16], w[16];
-        if (base + 4096 <= a.n_in) {   // interior block: no bounds checks
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = ld_stream(in + base + t + 256 * j);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const long long g = base + t + 256 * j;
-                v[4 * (j & 3) + (j >> 2)] = g < a.n_in ? ld_stream(in + g) : 0ull;
-            }
-        }
-        fft4096_core_p<false, false>(v, F, tw1, tw2, tw3, t);
-        // pointwise product with the tap spectrum, handed over in inverse-pass-1 register order
-#pragma unroll
-        for (int A = 0; A < 16; A++) w[4 * (A & 3) + (A >> 2)] = cmul_p<false>(v[A], ld_keep(hf + 256 * A + t));
-        fft4096_core_p<true, true>(w, F, tw1, tw2, tw3, t);
-        // circular result c[i], i = 256*A + t; alias-free part i >= K-1 is y[base + i - (K-1)]
-        c2 *o = out + (base - Km1);
-        if (base + hop <= a.n_out) {
-#pragma unroll
-            for (int A = 0; A < 16; A++) {
-                const int i = 256 * A + t;
-                if (i >= Km1) st_stream(o + i, w[A]);
-            }
-        } else {
-#pragma unroll
-            for (int A = 0; A < 16; A++) {
-                const int i = 256 * A + t;
-                if (i >= Km1 && base + i - Km1 < a.n_out) st_stream(o + i, w[A]);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------ host: plan ---
 static int make_plan(FftPlan &p)
 {
@@ -717,66 +548,6 @@ int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_c
     case B200C_CF64: return launch_staged<FloatTraits<double>>(p, a, grid, stream);
     default: return launch_staged<Q15Traits>(p, a, grid, stream);
     }
-}
-
-// ------------------------------------------------------------- host: overlap-save FIR ---
-int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t smem_budget)
-{
-    p.ready = false;
-    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
-    if (!p.have_fwd) {
-        int rc = fft_plan_create(p.fwd, B200C_CF32, 4096, 0, smem_budget);
-        if (rc) { fft_plan_destroy(p.fwd); return rc; }
-        p.have_fwd = true;
-    }
-    // Hf[f] = (1/4096) * sum_k h[k] exp(-2*pi*i*f*k/4096), accumulated in double
-    const int N = 4096;
-    std::vector<double> cs(N), sn(N);
-    for (int i = 0; i < N; i++) {
-        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
-        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
-    }
-    std::vector<float> hf(2 * N);
-    for (int f = 0; f < N; f++) {
-        double re = 0, im = 0;
-        for (size_t k = 0; k < ntaps; k++) {
-            const double hr = complex_taps ? taps[2 * k] : taps[k], hi = complex_taps ? taps[2 * k + 1] : 0.0;
-            const int idx = (int)(((long long)f * (long long)k) & (N - 1));
-            re += hr * cs[idx] - hi * sn[idx];
-            im += hr * sn[idx] + hi * cs[idx];
-        }
-        hf[2 * f] = (float)(re / N);
-        hf[2 * f + 1] = (float)(im / N);
-    }
-    if (!p.d_hf) B200C_CUDA_TRY(cudaMalloc(&p.d_hf, sizeof(float) * 2 * N));
-    B200C_CUDA_TRY(cudaMemcpy(p.d_hf, hf.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
-    p.K = (int)ntaps;
-    p.ready = true;
-    return B200C_OK;
-}
-
-void fir_os_destroy(FirOsPlan &p)
-{
-    if (p.have_fwd) fft_plan_destroy(p.fwd);
-    if (p.d_hf) cudaFree(p.d_hf);
-    p.d_hf = nullptr; p.have_fwd = false; p.ready = false;
-}
-
-int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
-                  cudaStream_t stream)
-{
-    if (n_out == 0) return B200C_OK;
-    FirOsArgs a;
-    a.in = d_in; a.out = d_out; a.hf = p.d_hf;
-    a.tw1 = p.fwd.d_fast[0]; a.tw2 = p.fwd.d_fast[1]; a.tw3 = p.fwd.d_fast[2];
-    a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
-    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
-    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * 12);
-    static const int variant = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 3; }();
-    if (variant == 2) fir_os4096_kernel<2><<<grid, 256, 0, stream>>>(a);
-    else fir_os4096_kernel<3><<<grid, 256, 0, stream>>>(a);
-    B200C_CUDA_TRY(cudaGetLastError());
-    return B200C_OK;
 }
 
 } // namespace b200c

@@ -38,11 +38,11 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
 void fft_plan_destroy(FftPlan &p);
 int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream);
 
-// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps) on the 4096-point FFT core.
+// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps), fir_os.cu.
 struct FirOsPlan {
-    FftPlan fwd;              // forward 4096 cf32 plan (its fast-path tables are reused for the inverse)
-    bool have_fwd = false;
     void *d_hf = nullptr;     // [4096] float2: spectrum of the taps / 4096
+    void *d_twa = nullptr;    // [8][64] float2: W4096^(8*a*t)
+    void *d_twb = nullptr;    // [8][64] float2: W4096^(b*t)
     int K = 0;
     bool ready = false;
     int hop() const { return 4096 - (K - 1); }

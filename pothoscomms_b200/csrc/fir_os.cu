@@ -1,0 +1,258 @@
+// Fused overlap-save FIR for /comms/fir_filter, complex float32, L = M = 1, 2..2049 taps.
+//
+// The reference convolves in the time domain (filter/FIRFilter.cpp:286-302): 8K flop per
+// sample for K complex taps, which on B200 is FMA-bound from K ~ 22 taps up.
+// Here every CTA takes 4096 consecutive input samples (K-1 of them history), transforms them,
+// multiplies by the taps' spectrum Hf (computed once per setTaps() on the host in double,
+// pre-scaled by 1/4096), transforms back and stores the 4096-(K-1) alias-free outputs: ONE
+// pass over HBM, 8 B in + 8 B out per sample whatever K is.
+//
+// Kernel shape (os64_core.cuh): 64 threads per transform, 64 points (128 registers) per
+// thread, 4096 = 64 x 64.  Forward = two decimation-in-time register passes around one
+// shared-memory exchange; inverse = the mirrored decimation-in-frequency passes, so the
+// pointwise product sits between two passes that share registers and one overlap-save block
+// costs TWO exchanges.  All arithmetic is packed f32x2 (packed.cuh).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "fft.hpp"
+#include "os64_core.cuh"
+
+namespace b200c {
+
+struct FirOs64Args {
+    const void *in;     // element 0 = first history sample
+    void *out;
+    const void *hf;     // [4096] spectrum of the taps / 4096, natural order
+    const void *twa;    // [8][64]  W4096^(8*a*t)
+    const void *twb;    // [8][64]  W4096^(b*t)
+    long long n_in;     // valid input elements (beyond: zeros -> burst zero tail)
+    long long n_out;    // outputs to produce
+    int K;              // taps
+};
+
+// v[slot(j)] *= W4096^(j*t) (CONJ: conjugate), j = 8a + b, from the two 8-entry tables.
+// SLOT_REV: element j lives in register rev64(j) (decimation-in-frequency output order).
+template <bool CONJ, bool SLOT_REV>
+__device__ __forceinline__ void step_twiddle(c2 (&v)[64], const c2 *__restrict__ twa, const c2 *__restrict__ twb, const int t)
+{
+    c2 A[8], B[8];
+#pragma unroll
+    for (int i = 1; i < 8; i++) { A[i] = twa[i * 64 + t]; B[i] = twb[i * 64 + t]; }
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int j = 8 * a + b, r = SLOT_REV ? rev64(j) : j;
+            if (a) v[r] = cmul_p<CONJ>(v[r], A[a]);
+            if (b) v[r] = cmul_p<CONJ>(v[r], B[b]);
+        }
+}
+
+// ---- bulk-async (TMA) prefetch of the next block's input into the exchange buffer ----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: order the CTA's earlier generic-proxy accesses of `dst` before the async-proxy
+// write, arm the barrier with the byte count and start the copy
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kBulkElems = 4098;   // 4096 + 2: room to start one element early when the block start is not 16-byte aligned
+
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
+{
+    __shared__ __align__(16) c2 F[kOs64SmemElems];
+    __shared__ __align__(8) unsigned long long bar;
+    const int t = threadIdx.x;
+    const c2 *__restrict__ twa = static_cast<const c2 *>(a.twa);
+    const c2 *__restrict__ twb = static_cast<const c2 *>(a.twb);
+    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    c2 *__restrict__ out = static_cast<c2 *>(a.out);
+    const int Km1 = a.K - 1;
+    const int hop = 4096 - Km1;
+    const long long nblk = (a.n_out + hop - 1) / hop;
+    // A block whose 4096 inputs (plus alignment slack) are all inside the stream is fetched by one
+    // bulk copy, issued while the previous block is still in its last register pass; the few
+    // edge blocks (zero tail, unaligned stream start) use guarded loads.
+    const int in_mis = (int)((reinterpret_cast<unsigned long long>(in) >> 3) & 1);
+    auto bulk_ok = [&](long long blk) {
+        const long long base = blk * hop;
+        const int mis = (int)((base + in_mis) & 1);
+        return blk < nblk && base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
+    };
+    auto bulk_issue = [&](long long blk) {
+        const long long base = blk * hop;
+        const int mis = (int)((base + in_mis) & 1);
+        bulk_load(F, in + (base - mis), kBulkElems * (unsigned)sizeof(c2), &bar);
+    };
+    if (t == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    bool pending = bulk_ok(blockIdx.x);
+    if (pending && t == 0) bulk_issue(blockIdx.x);
+    unsigned parity = 0;
+
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long base = blk * hop;
+        c2 v[64];
+        // ---- forward step 1: thread n2 = t, x[64 n1 + n2] over n1
+        if (pending) {
+            const int mis = (int)((base + in_mis) & 1);
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) v[rev64(n1)] = F[mis + 64 * n1 + t];
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const long long g = base + 64 * n1 + t;
+                v[rev64(n1)] = g < a.n_in ? __ldcg(in + g) : 0ull;
+            }
+        }
+        dft64_dit<false>(v);                                 // v[k1] = Y[n2 = t][k1]
+        step_twiddle<false, false>(v, twa, twb, t);          // * W4096^(n2 k1)
+        __syncthreads();                                     // every thread has taken its input out of F
+#pragma unroll
+        for (int k1 = 0; k1 < 64; k1++) F[k1 * kOs64Stride + t] = v[k1];
+        __syncthreads();
+        // ---- forward step 2: thread k1 = t, over n2
+#pragma unroll
+        for (int n2 = 0; n2 < 64; n2++) v[rev64(n2)] = F[t * kOs64Stride + n2];
+        dft64_dit<false>(v);                                 // v[k2] = X[k1 + 64 k2]
+        // ---- tap spectrum
+#pragma unroll
+        for (int k2 = 0; k2 < 64; k2++) v[k2] = cmul_p<false>(v[k2], hf[64 * k2 + t]);
+        // ---- inverse step 2': same thread, same registers, over k2 -> n2 (register rev64(n2))
+        dft64_dif<true>(v);
+        step_twiddle<true, true>(v, twa, twb, t);            // * conj W4096^(n2 k1)
+        __syncthreads();                                     // step-2 readers are done
+#pragma unroll
+        for (int n2 = 0; n2 < 64; n2++) F[t * kOs64Stride + n2] = v[rev64(n2)];
+        __syncthreads();
+        // ---- inverse step 1': thread n2 = t, over k1 -> n1 (register rev64(n1))
+#pragma unroll
+        for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
+        __syncthreads();                                     // F is free: fetch the next block into it
+        pending = bulk_ok(blk + gridDim.x);
+        if (pending && t == 0) bulk_issue(blk + gridDim.x);
+        dft64_dif<true>(v);
+        // circular result c[i], i = 64 n1 + t; the alias-free part i >= K-1 is y[base + i - (K-1)]
+        c2 *o = out + (base - Km1);
+        if (base + hop <= a.n_out) {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const int i = 64 * n1 + t;
+                if (i >= Km1) __stcg(o + i, v[rev64(n1)]);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const int i = 64 * n1 + t;
+                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev64(n1)]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- host ---
+int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t /*smem_budget*/)
+{
+    p.ready = false;
+    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
+    const int N = 4096;
+    std::vector<double> cs(N), sn(N);
+    for (int i = 0; i < N; i++) {
+        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
+        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
+    }
+    if (!p.d_twa) {
+        // step twiddles W4096^(j t) = W^(8 a t) * W^(b t), j = 8a + b
+        std::vector<float> ta(2 * 8 * 64), tb(2 * 8 * 64);
+        for (int i = 0; i < 8; i++)
+            for (int t = 0; t < 64; t++) {
+                const int ea = (8 * i * t) & (N - 1), eb = (i * t) & (N - 1);
+                ta[2 * (i * 64 + t)] = (float)cs[ea]; ta[2 * (i * 64 + t) + 1] = (float)sn[ea];
+                tb[2 * (i * 64 + t)] = (float)cs[eb]; tb[2 * (i * 64 + t) + 1] = (float)sn[eb];
+            }
+        B200C_CUDA_TRY(cudaMalloc(&p.d_twa, ta.size() * sizeof(float)));
+        B200C_CUDA_TRY(cudaMalloc(&p.d_twb, tb.size() * sizeof(float)));
+        B200C_CUDA_TRY(cudaMemcpy(p.d_twa, ta.data(), ta.size() * sizeof(float), cudaMemcpyHostToDevice));
+        B200C_CUDA_TRY(cudaMemcpy(p.d_twb, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // Hf[f] = (1/4096) * sum_k h[k] exp(-2*pi*i*f*k/4096), accumulated in double
+    std::vector<float> hf(2 * N);
+    for (int f = 0; f < N; f++) {
+        double re = 0, im = 0;
+        for (size_t k = 0; k < ntaps; k++) {
+            const double hr = complex_taps ? taps[2 * k] : taps[k], hi = complex_taps ? taps[2 * k + 1] : 0.0;
+            const int idx = (int)(((long long)f * (long long)k) & (N - 1));
+            re += hr * cs[idx] - hi * sn[idx];
+            im += hr * sn[idx] + hi * cs[idx];
+        }
+        hf[2 * f] = (float)(re / N);
+        hf[2 * f + 1] = (float)(im / N);
+    }
+    if (!p.d_hf) B200C_CUDA_TRY(cudaMalloc(&p.d_hf, sizeof(float) * 2 * N));
+    B200C_CUDA_TRY(cudaMemcpy(p.d_hf, hf.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
+    p.K = (int)ntaps;
+    p.ready = true;
+    return B200C_OK;
+}
+
+void fir_os_destroy(FirOsPlan &p)
+{
+    if (p.d_hf) cudaFree(p.d_hf);
+    if (p.d_twa) cudaFree(p.d_twa);
+    if (p.d_twb) cudaFree(p.d_twb);
+    p.d_hf = p.d_twa = p.d_twb = nullptr;
+    p.ready = false;
+}
+
+int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                  cudaStream_t stream)
+{
+    if (n_out == 0) return B200C_OK;
+    FirOs64Args a;
+    a.in = d_in; a.out = d_out; a.hf = p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
+    a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
+    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
+    static const int minb = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 4; }();
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
+    switch (minb) {
+    case 2: fir_os64_kernel<2><<<grid, 64, 0, stream>>>(a); break;
+    case 3: fir_os64_kernel<3><<<grid, 64, 0, stream>>>(a); break;
+    case 4: fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a); break;
+    case 6: fir_os64_kernel<6><<<grid, 64, 0, stream>>>(a); break;
+    case 5: fir_os64_kernel<5><<<grid, 64, 0, stream>>>(a); break;
+    default: fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a); break;
+    }
+    B200C_CUDA_TRY(cudaGetLastError());
+    return B200C_OK;
+}
+
+} // namespace b200c
