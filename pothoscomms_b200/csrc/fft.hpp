@@ -38,16 +38,21 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
 void fft_plan_destroy(FftPlan &p);
 int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream);
 
-// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps), fir_os.cu.
+// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps), fir_os.cu.  Two transform lengths:
+// 1024 (one warp per block) for the shorter tap counts, 4096 (64 threads per block) above.
 struct FirOsPlan {
+    int N = 4096;             // transform length in use
     void *d_hf = nullptr;     // [4096] float2: spectrum of the taps / 4096
     void *d_twa = nullptr;    // [8][64] float2: W4096^(8*a*t)
     void *d_twb = nullptr;    // [8][64] float2: W4096^(b*t)
+    void *d_hf1k = nullptr;   // [1024] float2: spectrum of the taps / 1024
+    void *d_tw1k = nullptr;   // [32][32] float2: W1024^(j*t)
     int K = 0;
     bool ready = false;
-    int hop() const { return 4096 - (K - 1); }
+    int hop() const { return N - (K - 1); }
 };
 constexpr size_t kFirOsMaxTaps = 2049;
+constexpr size_t kFirOs1kMaxTaps = 300;
 int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t smem_budget);
 void fir_os_destroy(FirOsPlan &p);
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,

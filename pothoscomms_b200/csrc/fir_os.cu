@@ -179,33 +179,97 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
     }
 }
 
-// ------------------------------------------------------------------------------- host ---
-int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t /*smem_budget*/)
+// ---------------------------------------------------------------- 1024-point variant ---
+// Same algorithm on 1024 = 32 x 32: ONE WARP per transform, 32 points (64 registers) per
+// thread, exchanges through a per-warp shared-memory tile with __syncwarp() only.  Less
+// register state per thread => ~2.5x the resident warps of the 4096-point kernel, which is
+// what keeps the FMA pipe fed; the price is a shorter hop (1024 - (K-1)), so it is used for
+// the shorter tap counts (fir_os_launch).
+struct FirOs32Args {
+    const void *in;
+    void *out;
+    const void *hf;     // [1024] spectrum of the taps / 1024
+    const void *tw;     // [32][32] W1024^(j*t)
+    long long n_in, n_out;
+    int K;
+};
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
 {
-    p.ready = false;
-    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
-    const int N = 4096;
+    __shared__ c2 Fs[WARPS][kOs32SmemElems];
+    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+    c2 *F = Fs[w];
+    const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    c2 *__restrict__ out = static_cast<c2 *>(a.out);
+    const int Km1 = a.K - 1;
+    const int hop = 1024 - Km1;
+    const long long nblk = (a.n_out + hop - 1) / hop;
+    const long long stride = (long long)gridDim.x * WARPS;
+    for (long long blk = (long long)blockIdx.x * WARPS + w; blk < nblk; blk += stride) {
+        const long long base = blk * hop;
+        c2 v[32];
+        if (base + 1024 <= a.n_in) {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = __ldcg(in + base + 32 * n1 + t);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const long long g = base + 32 * n1 + t;
+                v[rev32(n1)] = g < a.n_in ? __ldcg(in + g) : 0ull;
+            }
+        }
+        dft32_dit<false>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
+        dft32_dit<false>(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(v[k2], hf[32 * k2 + t]);
+        dft32_dif<true>(v);
+#pragma unroll
+        for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) F[t * kOs32Stride + n2] = v[rev32(n2)];
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
+        dft32_dif<true>(v);
+        c2 *o = out + (base - Km1);
+        if (base + hop <= a.n_out) {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const int i = 32 * n1 + t;
+                if (i >= Km1) __stcg(o + i, v[rev32(n1)]);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const int i = 32 * n1 + t;
+                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev32(n1)]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- host ---
+static void taps_spectrum(std::vector<float> &hf, int N, const double *taps, size_t ntaps, bool complex_taps)
+{
+    // Hf[f] = (1/N) * sum_k h[k] exp(-2*pi*i*f*k/N), accumulated in double
     std::vector<double> cs(N), sn(N);
     for (int i = 0; i < N; i++) {
         const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
         cs[i] = std::cos(ph); sn[i] = std::sin(ph);
     }
-    if (!p.d_twa) {
-        // step twiddles W4096^(j t) = W^(8 a t) * W^(b t), j = 8a + b
-        std::vector<float> ta(2 * 8 * 64), tb(2 * 8 * 64);
-        for (int i = 0; i < 8; i++)
-            for (int t = 0; t < 64; t++) {
-                const int ea = (8 * i * t) & (N - 1), eb = (i * t) & (N - 1);
-                ta[2 * (i * 64 + t)] = (float)cs[ea]; ta[2 * (i * 64 + t) + 1] = (float)sn[ea];
-                tb[2 * (i * 64 + t)] = (float)cs[eb]; tb[2 * (i * 64 + t) + 1] = (float)sn[eb];
-            }
-        B200C_CUDA_TRY(cudaMalloc(&p.d_twa, ta.size() * sizeof(float)));
-        B200C_CUDA_TRY(cudaMalloc(&p.d_twb, tb.size() * sizeof(float)));
-        B200C_CUDA_TRY(cudaMemcpy(p.d_twa, ta.data(), ta.size() * sizeof(float), cudaMemcpyHostToDevice));
-        B200C_CUDA_TRY(cudaMemcpy(p.d_twb, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    // Hf[f] = (1/4096) * sum_k h[k] exp(-2*pi*i*f*k/4096), accumulated in double
-    std::vector<float> hf(2 * N);
+    hf.assign(2 * (size_t)N, 0.f);
     for (int f = 0; f < N; f++) {
         double re = 0, im = 0;
         for (size_t k = 0; k < ntaps; k++) {
@@ -217,8 +281,63 @@ int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex
         hf[2 * f] = (float)(re / N);
         hf[2 * f + 1] = (float)(im / N);
     }
-    if (!p.d_hf) B200C_CUDA_TRY(cudaMalloc(&p.d_hf, sizeof(float) * 2 * N));
-    B200C_CUDA_TRY(cudaMemcpy(p.d_hf, hf.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
+}
+
+static void unit_root_table(std::vector<float> &tb, int N, int rows, int cols, int row_mul)
+{
+    // tb[r][c] = exp(-2*pi*i*(row_mul*r*c)/N)
+    const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
+    tb.assign(2 * (size_t)rows * cols, 0.f);
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < cols; c++) {
+            const int e = (row_mul * r * c) & (N - 1);
+            tb[2 * ((size_t)r * cols + c)] = (float)std::cos(-two_pi * e / N);
+            tb[2 * ((size_t)r * cols + c) + 1] = (float)std::sin(-two_pi * e / N);
+        }
+}
+
+static int upload(void **d, const std::vector<float> &h)
+{
+    if (!*d) B200C_CUDA_TRY(cudaMalloc(d, h.size() * sizeof(float)));
+    B200C_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return B200C_OK;
+}
+
+// Transform length for K taps: the 1024-point warp kernel while its hop keeps >= ~70 % of the
+// block (measured crossover), the 4096-point kernel above.  B200C_OS_N overrides.
+static int pick_length(size_t ntaps)
+{
+    static const int forced = [] { const char *e = std::getenv("B200C_OS_N"); return e ? std::atoi(e) : 0; }();
+    if (forced == 1024 && ntaps <= 769) return 1024;
+    if (forced == 4096) return 4096;
+    return ntaps <= kFirOs1kMaxTaps ? 1024 : 4096;
+}
+
+int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t /*smem_budget*/)
+{
+    p.ready = false;
+    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
+    std::vector<float> tb, hf;
+    int rc;
+    p.N = pick_length(ntaps);
+    if (p.N == 4096) {
+        if (!p.d_twa) {
+            // step twiddles W4096^(j t) = W^(8 a t) * W^(b t), j = 8a + b
+            unit_root_table(tb, 4096, 8, 64, 8);
+            if ((rc = upload(&p.d_twa, tb))) return rc;
+            unit_root_table(tb, 4096, 8, 64, 1);
+            if ((rc = upload(&p.d_twb, tb))) return rc;
+        }
+        taps_spectrum(hf, 4096, taps, ntaps, complex_taps);
+        if ((rc = upload(&p.d_hf, hf))) return rc;
+    } else {
+        if (!p.d_tw1k) {
+            unit_root_table(tb, 1024, 32, 32, 1);
+            if ((rc = upload(&p.d_tw1k, tb))) return rc;
+        }
+        taps_spectrum(hf, 1024, taps, ntaps, complex_taps);
+        if ((rc = upload(&p.d_hf1k, hf))) return rc;
+    }
     p.K = (int)ntaps;
     p.ready = true;
     return B200C_OK;
@@ -226,10 +345,10 @@ int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex
 
 void fir_os_destroy(FirOsPlan &p)
 {
-    if (p.d_hf) cudaFree(p.d_hf);
-    if (p.d_twa) cudaFree(p.d_twa);
-    if (p.d_twb) cudaFree(p.d_twb);
-    p.d_hf = p.d_twa = p.d_twb = nullptr;
+    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k}) {
+        if (*d) cudaFree(*d);
+        *d = nullptr;
+    }
     p.ready = false;
 }
 
@@ -237,18 +356,26 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
                   cudaStream_t stream)
 {
     if (n_out == 0) return B200C_OK;
+    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
+    if (p.N == 1024) {
+        FirOs32Args a;
+        a.in = d_in; a.out = d_out; a.hf = p.d_hf1k; a.tw = p.d_tw1k;
+        a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
+        constexpr int kWarps = 4;
+        const int grid = (int)std::min<long long>((nblk + kWarps - 1) / kWarps, (long long)sm_count * 5 * 4);
+        fir_os32_kernel<kWarps, 5><<<grid, 32 * kWarps, 0, stream>>>(a);
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
     FirOs64Args a;
     a.in = d_in; a.out = d_out; a.hf = p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
-    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
     static const int minb = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 4; }();
     const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
     switch (minb) {
-    case 2: fir_os64_kernel<2><<<grid, 64, 0, stream>>>(a); break;
     case 3: fir_os64_kernel<3><<<grid, 64, 0, stream>>>(a); break;
-    case 4: fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a); break;
-    case 6: fir_os64_kernel<6><<<grid, 64, 0, stream>>>(a); break;
     case 5: fir_os64_kernel<5><<<grid, 64, 0, stream>>>(a); break;
+    case 6: fir_os64_kernel<6><<<grid, 64, 0, stream>>>(a); break;
     default: fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a); break;
     }
     B200C_CUDA_TRY(cudaGetLastError());

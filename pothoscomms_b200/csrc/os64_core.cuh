@@ -109,4 +109,57 @@ template <bool INV> B200C_HD void dft64_dif(c2 (&v)[64])
 constexpr int kOs64Stride = 65;
 constexpr int kOs64SmemElems = 64 * kOs64Stride;
 
+// ---------------------------------------------------------------- 32-point transforms ---
+// Radix 4, 4, 2.  Element n = q + 2 q' + 8 n'' (q < 2, q' < 4, n'' < 4) sits in register
+// rev32(n) = 16 q + 4 q' + n'' for the decimation-in-time input / decimation-in-frequency output.
+B200C_HD constexpr int rev32(int n) { return 16 * (n & 1) + 4 * ((n >> 1) & 3) + ((n >> 3) & 3); }
+
+template <bool INV> B200C_HD void dft32_dit(c2 (&v)[32])
+{
+#pragma unroll
+    for (int g = 0; g < 8; g++) dft4_p<INV>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = 16 * g + k;
+            v[i + 4] = mul_w64<INV>(v[i + 4], 4 * k);
+            v[i + 8] = mul_w64<INV>(v[i + 8], 8 * k);
+            v[i + 12] = mul_w64<INV>(v[i + 12], 12 * k);
+            dft4_p<INV>(v[i], v[i + 4], v[i + 8], v[i + 12]);
+        }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const c2 b = mul_w64<INV>(v[k + 16], 2 * k);   // W32^k
+        v[k + 16] = sub2(v[k], b);
+        v[k] = add2(v[k], b);
+    }
+}
+
+template <bool INV> B200C_HD void dft32_dif(c2 (&v)[32])
+{
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const c2 d = sub2(v[k], v[k + 16]);
+        v[k] = add2(v[k], v[k + 16]);
+        v[k + 16] = mul_w64<INV>(d, 2 * k);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = 16 * g + k;
+            dft4_p<INV>(v[i], v[i + 4], v[i + 8], v[i + 12]);
+            v[i + 4] = mul_w64<INV>(v[i + 4], 4 * k);
+            v[i + 8] = mul_w64<INV>(v[i + 8], 8 * k);
+            v[i + 12] = mul_w64<INV>(v[i + 12], 12 * k);
+        }
+#pragma unroll
+    for (int g = 0; g < 8; g++) dft4_p<INV>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+
+// exchange buffer of one 1024-point transform (one warp): element (r, c) at r*33 + c
+constexpr int kOs32Stride = 33;
+constexpr int kOs32SmemElems = 32 * kOs32Stride;
+
 } // namespace b200c
