@@ -197,9 +197,11 @@ struct FirOs32Args {
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
 {
-    __shared__ c2 Fs[WARPS][kOs32SmemElems];
+    __shared__ __align__(16) c2 Fs[WARPS][kOs32SmemElems];
+    __shared__ __align__(8) unsigned long long bars[WARPS];
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
     c2 *F = Fs[w];
+    unsigned long long *bar = &bars[w];
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
     const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
@@ -208,12 +210,35 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     const int hop = 1024 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
     const long long stride = (long long)gridDim.x * WARPS;
-    for (long long blk = (long long)blockIdx.x * WARPS + w; blk < nblk; blk += stride) {
+    // the warp's next block is fetched into its exchange tile by one bulk copy while the warp is
+    // in its last register pass (see fir_os64_kernel); edge blocks use guarded loads
+    constexpr int kBulk = 1026;
+    const int in_mis = (int)((reinterpret_cast<unsigned long long>(in) >> 3) & 1);
+    auto bulk_ok = [&](long long blk) {
+        const long long base = blk * hop;
+        const int mis = (int)((base + in_mis) & 1);
+        return blk < nblk && base - mis >= 0 && base - mis + kBulk <= a.n_in;
+    };
+    auto bulk_issue = [&](long long blk) {
+        const long long base = blk * hop;
+        const int mis = (int)((base + in_mis) & 1);
+        bulk_load(F, in + (base - mis), kBulk * (unsigned)sizeof(c2), bar);
+    };
+    long long blk = (long long)blockIdx.x * WARPS + w;
+    if (t == 0) mbar_init(bar, 1);
+    __syncwarp();
+    bool pending = bulk_ok(blk);
+    if (pending && t == 0) bulk_issue(blk);
+    unsigned parity = 0;
+    for (; blk < nblk; blk += stride) {
         const long long base = blk * hop;
         c2 v[32];
-        if (base + 1024 <= a.n_in) {
+        if (pending) {
+            const int mis = (int)((base + in_mis) & 1);
+            mbar_wait(bar, parity);
+            parity ^= 1;
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = __ldcg(in + base + 32 * n1 + t);
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = F[mis + 32 * n1 + t];
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) {
@@ -242,6 +267,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
+        __syncwarp();                                        // the tile is free: fetch the next block into it
+        pending = bulk_ok(blk + stride);
+        if (pending && t == 0) bulk_issue(blk + stride);
         dft32_dif<true>(v);
         c2 *o = out + (base - Km1);
         if (base + hop <= a.n_out) {
@@ -361,9 +389,24 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         FirOs32Args a;
         a.in = d_in; a.out = d_out; a.hf = p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
-        constexpr int kWarps = 4;
-        const int grid = (int)std::min<long long>((nblk + kWarps - 1) / kWarps, (long long)sm_count * 5 * 4);
-        fir_os32_kernel<kWarps, 5><<<grid, 32 * kWarps, 0, stream>>>(a);
+        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 112; }();
+#define OS32_LAUNCH(W, MB)                                                                                        \
+    {                                                                                                             \
+        const int grid = (int)std::min<long long>((nblk + (W) - 1) / (W), (long long)sm_count * (MB) * 4);        \
+        fir_os32_kernel<W, MB><<<grid, 32 * (W), 0, stream>>>(a);                                                  \
+    }
+        switch (cfg) {   // (warps per CTA)(CTAs per SM)
+        case 42: OS32_LAUNCH(4, 2) break;
+        case 25: OS32_LAUNCH(2, 5) break;
+        case 26: OS32_LAUNCH(2, 6) break;
+        case 24: OS32_LAUNCH(2, 4) break;
+        case 43: OS32_LAUNCH(4, 3) break;
+        case 110: OS32_LAUNCH(1, 10) break;
+        case 114: OS32_LAUNCH(1, 14) break;
+        case 116: OS32_LAUNCH(1, 16) break;
+        default: OS32_LAUNCH(1, 12) break;
+        }
+#undef OS32_LAUNCH
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
