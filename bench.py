@@ -396,10 +396,12 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                "kernel": "fir_tile_kernel", "kernel_ms": kernel_ms,
-                "note": "FFMA-issue bound at 256 complex taps (2048 flop/sample); see DESIGN.md"}
+                "kernel": fir.kernel, "kernel_ms": kernel_ms,
+                "note": ("fused overlap-save (fast convolution): one pass over HBM, 16 B per sample whatever the tap count"
+                         if fir.kernel.startswith("fir_os") else
+                         "direct form: FMA/IMAD-issue bound once taps x MACs/tap exceed ~11 flop/B; see DESIGN.md")}
     flops = {"c1": 512, "c1_real": 256, "headline": 2048, "c3": 510, "c5": 8192}.get(args.workload)
-    if flops:
+    if flops and not fir.kernel.startswith("fir_os"):
         roofline["fp32_tflops"] = flops * n_seg / (kernel_ms * 1e-3) / 1e12
 
     cpu = None

@@ -36,6 +36,7 @@ SYMBOLS = {
     "b200c_fir_set_taps": (_i, [_vp, _vp, _sz]),
     "b200c_fir_set_rates": (_i, [_vp, _sz, _sz]),
     "b200c_fir_info": (_i, [_vp, _psz, _psz, _psz, _psz]),
+    "b200c_fir_kernel": (ctypes.c_char_p, [_vp]),
     "b200c_fir_plan": (_i, [_vp, _sz, _sz, _i, _psz, _psz]),
     "b200c_fir_run": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _psz, _psz, _vp]),
     "b200c_fir_run_host": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _psz, _psz]),

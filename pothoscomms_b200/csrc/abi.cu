@@ -48,9 +48,6 @@ static int dev_info(int device, DevInfo &di)
 }
 
 constexpr int kHostSlots = 3;
-// automatic switch to the overlap-save kernel (cf32, L = M = 1): direct FFMA cost grows with K,
-// the fused FFT kernel's does not; below this many taps the direct kernel is near the HBM roof
-constexpr size_t kFirOsAutoMinTaps = 24;
 
 struct HostPipe {   // staging for the *_run_host entry points
     cudaStream_t streams[kHostSlots] = {nullptr, nullptr, nullptr};
@@ -154,12 +151,12 @@ static int fir_refresh(b200c_fir *h)
     // pass over HBM whatever K is.  B200C_FIR_ALGO=direct|fft overrides the automatic choice
     // (fft: whenever applicable; direct: never).
     h->use_os = false;
-    if (h->dtype == B200C_CF32 && h->M == 1 && h->L == 1 && h->ntaps >= 2 && h->ntaps <= kFirOsMaxTaps) {
+    {
         const char *algo = std::getenv("B200C_FIR_ALGO");
         const bool force_direct = algo && std::strcmp(algo, "direct") == 0, force_fft = algo && std::strcmp(algo, "fft") == 0;
-        if (!force_direct && (force_fft || h->ntaps >= kFirOsAutoMinTaps)) {
-            rc = fir_os_set_taps(h->os, h->taps.data(), h->ntaps, h->taps_kind == B200C_TAPS_COMPLEX,
-                                 std::min<size_t>(h->di.smem_optin, 200 * 1024));
+        if (!force_direct) {
+            rc = fir_os_configure(h->os, h->dtype, h->taps.data(), h->ntaps, h->taps_kind == B200C_TAPS_COMPLEX, h->M, h->L,
+                                  force_fft);
             if (rc) return rc;
             h->use_os = h->os.ready;
         }
@@ -272,6 +269,13 @@ int b200c_fir_info(const b200c_fir *h, size_t *K, size_t *input_require, size_t 
     return B200C_OK;
 }
 
+const char *b200c_fir_kernel(const b200c_fir *h)
+{
+    if (!h) return "";
+    if (h->use_os) return fir_os_kernel_name(h->os);
+    return h->table.smem_path ? "fir_tile_kernel" : "fir_generic_kernel";
+}
+
 int b200c_fir_plan(const b200c_fir *h, size_t in_elems, size_t out_capacity, int zero_tail, size_t *consume,
                    size_t *produce)
 {
@@ -292,7 +296,7 @@ int b200c_fir_run(b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, 
     if (!d_in || !d_out) { set_error("b200c_fir_run: null device buffer"); return B200C_ERR_INVALID; }
     DeviceGuard g(h->device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", h->device); return B200C_ERR_CUDA; }
-    if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, c, h->di.sm_count, (cudaStream_t)stream);
+    if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, c / h->M, h->di.sm_count, (cudaStream_t)stream);
     return fir_launch(h->table, h->ds, d_in, in_elems, d_out, c / h->M, h->di.sm_count, (cudaStream_t)stream);
 }
 

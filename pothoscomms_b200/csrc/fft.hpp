@@ -38,24 +38,42 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
 void fft_plan_destroy(FftPlan &p);
 int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_count, cudaStream_t stream);
 
-// Fused overlap-save FIR (cf32, L = M = 1, 2..2049 taps), fir_os.cu.  Two transform lengths:
-// 1024 (one warp per block) for the shorter tap counts, 4096 (64 threads per block) above.
+// Fused overlap-save FIR, fir_os.cu.
+//  * complex float32, L = M = 1, 2..2049 taps: 1024-point (one warp per block) kernel for the
+//    shorter tap counts, 4096-point (64 threads per block) above;
+//  * complex float32 / float32 with M <= 2, any L <= 64 (polyphase resampler) and real data:
+//    generalised 1024-point kernel over the L*M tap-phase spectra.
 struct FirOsPlan {
+    bool ready = false;
+    bool general = false;     // polyphase / real-data kernel
+    bool real = false;        // float32 data: two stream blocks per complex transform
     int N = 4096;             // transform length in use
+    int K = 0;                // L = M = 1 kernels: taps; general: K = ceil(ntaps / L)
+    int M = 1, L = 1;
+    int hopq = 0;             // general: output blocks q per transform block
+    long long start0 = 0;     // general: input element of b_0[0] for block 0
     void *d_hf = nullptr;     // [4096] float2: spectrum of the taps / 4096
     void *d_twa = nullptr;    // [8][64] float2: W4096^(8*a*t)
     void *d_twb = nullptr;    // [8][64] float2: W4096^(b*t)
     void *d_hf1k = nullptr;   // [1024] float2: spectrum of the taps / 1024
     void *d_tw1k = nullptr;   // [32][32] float2: W1024^(j*t)
-    int K = 0;
-    bool ready = false;
-    int hop() const { return N - (K - 1); }
+    void *d_H = nullptr;      // general: [L*M][1024] float2 tap-phase spectra / 1024
+    size_t H_floats = 0;
+    // output blocks q covered by one kernel block (host-buffer chunking aligns to this)
+    int hop() const { return general ? hopq * (real ? 2 : 1) : N - (K - 1); }
 };
 constexpr size_t kFirOsMaxTaps = 2049;
 constexpr size_t kFirOs1kMaxTaps = 300;
-int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t smem_budget);
+// automatic switch from the direct kernel: taps per output at or above this take the fused path
+constexpr size_t kFirOsAutoMinTaps = 12;
+constexpr long long kFirOsGenMaxSpan = 400;   // general kernel: keep hop >= ~60 % of the block
+constexpr size_t kFirOsGenMaxInterp = 64;
+int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
+                     bool force);
 void fir_os_destroy(FirOsPlan &p);
-int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+const char *fir_os_kernel_name(const FirOsPlan &p);
+// nq = output blocks q (= consumed / M); outputs written = nq * L
+int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
                   cudaStream_t stream);
 
 } // namespace b200c

@@ -288,6 +288,139 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     }
 }
 
+// ------------------------------------------------- polyphase / real-data generalisation ---
+// The reference's resampling nest (filter/FIRFilter.cpp:286-302) in polyphase form (fir.hpp):
+//   y[q L + p] = sum_e sum_a g_{p,e}[a] * x_e[q + a],   x_e[i] = x[i M + e],  a in [a_min, a_max]
+// i.e. L*M stride-1 correlations over the M de-interleaved input streams.  One overlap-save
+// block: forward-transform the M residue streams (b_e[i] = x_e[Q0 + a_min + i], i < 1024), form
+// C_p = sum_e H_{p,e} . B_e for each output slot p, inverse-transform and keep the first
+// hop = 1024 - (a_max - a_min) results c_p[u] = y[(Q0 + u) L + p].  M forward + L inverse
+// transforms per hop*M inputs instead of 2 K L flop-pairs per input.
+// REAL: float32 data (always REAL taps): the filter is linear and real, so two consecutive
+// blocks ride in one complex transform, z = x_A + i x_B  ->  Re = y_A, Im = y_B.
+struct FirOs32GArgs {
+    const void *in;      // element 0 = first history sample
+    void *out;
+    const void *H;       // [L*M][1024] tap-phase spectra / 1024
+    const void *tw;      // [32][32] W1024^(j*t)
+    long long n_in;      // valid input elements (beyond: zeros)
+    long long nq;        // output blocks q to produce (outputs = nq * L)
+    long long start0;    // input element index of b_0[0] for block 0: K-1 + a_min*M (may be < 0)
+    int L, hop;
+};
+
+// one 1024-point transform of the warp's 32 x 32 register tile through its shared-memory tile
+template <bool INV>
+__device__ __forceinline__ void fft1024_fwd(c2 (&v)[32], c2 *F, const c2 *__restrict__ tw, const int t)
+{
+    // in: v[rev32(n1)] = x[32 n1 + t]; out: v[k2] = X[t + 32 k2]
+    dft32_dit<INV>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<INV>(v[k1], tw[k1 * 32 + t]);
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
+    dft32_dit<INV>(v);
+}
+__device__ __forceinline__ void fft1024_inv(c2 (&v)[32], c2 *F, const c2 *__restrict__ tw, const int t)
+{
+    // in: v[k2] = X[t + 32 k2]; out: v[rev32(n1)] = x[32 n1 + t] (unnormalised inverse)
+    dft32_dif<true>(v);
+#pragma unroll
+    for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) F[t * kOs32Stride + n2] = v[rev32(n2)];
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
+    dft32_dif<true>(v);
+}
+
+template <int M, bool MULTI_L, bool REAL, int MINB>
+__global__ void __launch_bounds__(32, MINB) fir_os32g_kernel(const FirOs32GArgs a)
+{
+    __shared__ c2 F[kOs32SmemElems];
+    const int t = threadIdx.x;
+    const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ H = static_cast<const c2 *>(a.H);
+    const int L = a.L, hop = a.hop;
+    constexpr int NB = REAL ? 2 : 1;                      // stream blocks per transform
+    const long long nblk = (a.nq + (long long)hop * NB - 1) / ((long long)hop * NB);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long Q0 = blk * hop * NB;              // first output block q of stream block A
+        c2 B[M][32];
+#pragma unroll
+        for (int e = 0; e < M; e++) {
+            const long long s0 = a.start0 + Q0 * M + e;   // input element of b_e[0] (block A)
+            if constexpr (REAL) {
+                const float *__restrict__ in = static_cast<const float *>(a.in);
+                const long long s1 = s0 + (long long)hop * M;
+                const bool inner = s0 >= 0 && s1 + 1023LL * M < a.n_in;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const long long ia = s0 + (long long)(32 * n1 + t) * M, ib = s1 + (long long)(32 * n1 + t) * M;
+                    const float xa = (inner || (ia >= 0 && ia < a.n_in)) ? __ldg(in + ia) : 0.f;
+                    const float xb = (inner || (ib >= 0 && ib < a.n_in)) ? __ldg(in + ib) : 0.f;
+                    B[e][rev32(n1)] = pk(xa, xb);
+                }
+            } else {
+                const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+                const bool inner = s0 >= 0 && s0 + 1023LL * M < a.n_in;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const long long ia = s0 + (long long)(32 * n1 + t) * M;
+                    B[e][rev32(n1)] = (inner || (ia >= 0 && ia < a.n_in)) ? __ldg(in + ia) : 0ull;
+                }
+            }
+            fft1024_fwd<false>(B[e], F, tw, t);
+        }
+        for (int p = 0; p < L; p++) {
+            c2 wloc[MULTI_L ? 32 : 1];
+            c2(&w)[32] = *reinterpret_cast<c2(*)[32]>(MULTI_L ? &wloc[0] : &B[0][0]);
+            const c2 *__restrict__ Hp = H + (size_t)p * M * 1024 + t;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) {
+                c2 acc = cmul_p<false>(B[0][k2], Hp[32 * k2]);
+#pragma unroll
+                for (int e = 1; e < M; e++) {
+                    // acc += B_e * H_{p,e}
+                    float fx, fy, hx, hy;
+                    upk(B[e][k2], fx, fy); upk(Hp[e * 1024 + 32 * k2], hx, hy);
+                    acc = fma2(B[e][k2], pk(hx, hx), fma2(pk(-fy, fx), pk(hy, hy), acc));
+                }
+                w[k2] = acc;
+            }
+            fft1024_inv(w, F, tw, t);
+            // c_p[u], u = 32 n1 + t < hop, is y[(Q0 + u) L + p]  (REAL: Im part belongs to block B)
+            if constexpr (REAL) {
+                float *__restrict__ out = static_cast<float *>(a.out);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const int u = 32 * n1 + t;
+                    float ya, yb;
+                    upk(w[rev32(n1)], ya, yb);
+                    if (u < hop) {
+                        const long long qa = Q0 + u, qb = qa + hop;
+                        if (qa < a.nq) __stcg(out + qa * L + p, ya);
+                        if (qb < a.nq) __stcg(out + qb * L + p, yb);
+                    }
+                }
+            } else {
+                c2 *__restrict__ out = static_cast<c2 *>(a.out);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const int u = 32 * n1 + t;
+                    if (u < hop && Q0 + u < a.nq) __stcg(out + (Q0 + u) * L + p, w[rev32(n1)]);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- host ---
 static void taps_spectrum(std::vector<float> &hf, int N, const double *taps, size_t ntaps, bool complex_taps)
 {
@@ -341,49 +474,160 @@ static int pick_length(size_t ntaps)
     return ntaps <= kFirOs1kMaxTaps ? 1024 : 4096;
 }
 
-int fir_os_set_taps(FirOsPlan &p, const double *taps, size_t ntaps, bool complex_taps, size_t /*smem_budget*/)
+static inline long long floordiv_ll(long long x, long long y)
 {
-    p.ready = false;
-    if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;   // not applicable: caller keeps the direct kernel
-    std::vector<float> tb, hf;
-    int rc;
-    p.N = pick_length(ntaps);
-    if (p.N == 4096) {
-        if (!p.d_twa) {
-            // step twiddles W4096^(j t) = W^(8 a t) * W^(b t), j = 8a + b
-            unit_root_table(tb, 4096, 8, 64, 8);
-            if ((rc = upload(&p.d_twa, tb))) return rc;
-            unit_root_table(tb, 4096, 8, 64, 1);
-            if ((rc = upload(&p.d_twb, tb))) return rc;
+    long long q = x / y;
+    if ((x % y != 0) && ((x < 0) != (y < 0))) q--;
+    return q;
+}
+
+// Polyphase / real-data plan: spectra of the L*M tap phases on the 1024-point grid.
+static int configure_general(FirOsPlan &p, bool real_data, const double *taps, size_t ntaps, bool complex_taps, size_t M,
+                             size_t L)
+{
+    const int N = 1024;
+    const long long K = (long long)((ntaps + L - 1) / L);   // filter/FIRFilter.cpp:335
+    struct Term { int p, e; long long a; double hr, hi; };
+    std::vector<Term> terms;
+    long long a_min = 0, a_max = 0;
+    bool first = true;
+    for (size_t ps = 0; ps < L; ps++) {
+        const long long i = (long long)((ps + 1) * M - 1), j = i % (long long)L, d = i / (long long)L;
+        for (long long k = 0; j + k * (long long)L < (long long)ntaps; k++) {
+            const size_t ti = (size_t)(j + k * (long long)L);
+            const long long a = floordiv_ll(d - k, (long long)M);
+            const int e = (int)((d - k) - a * (long long)M);
+            terms.push_back({(int)ps, e, a, complex_taps ? taps[2 * ti] : taps[ti], complex_taps ? taps[2 * ti + 1] : 0.0});
+            if (first) { a_min = a_max = a; first = false; }
+            a_min = std::min(a_min, a); a_max = std::max(a_max, a);
         }
-        taps_spectrum(hf, 4096, taps, ntaps, complex_taps);
-        if ((rc = upload(&p.d_hf, hf))) return rc;
-    } else {
-        if (!p.d_tw1k) {
-            unit_root_table(tb, 1024, 32, 32, 1);
-            if ((rc = upload(&p.d_tw1k, tb))) return rc;
-        }
-        taps_spectrum(hf, 1024, taps, ntaps, complex_taps);
-        if ((rc = upload(&p.d_hf1k, hf))) return rc;
     }
-    p.K = (int)ntaps;
+    const long long span = a_max - a_min;
+    if (first || span > kFirOsGenMaxSpan) return B200C_OK;   // not applicable: the direct kernel keeps the job
+    std::vector<double> cs(N), sn(N);
+    for (int i = 0; i < N; i++) {
+        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
+        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
+    }
+    // c_p[u] = sum_e sum_a g[a] b_e[u + (a - a_min)]  ==  circular convolution with g'[(N - (a - a_min)) mod N] = g[a]
+    std::vector<double> acc(2 * (size_t)L * M * N, 0.0);
+    for (const Term &t : terms) {
+        const int spos = (int)((N - (t.a - a_min)) % N);
+        double *dst = acc.data() + 2 * ((size_t)t.p * M + t.e) * N;
+        for (int f = 0; f < N; f++) {
+            const int idx = (int)(((long long)f * spos) & (N - 1));
+            dst[2 * f] += t.hr * cs[idx] - t.hi * sn[idx];
+            dst[2 * f + 1] += t.hr * sn[idx] + t.hi * cs[idx];
+        }
+    }
+    std::vector<float> H(acc.size());
+    for (size_t i = 0; i < acc.size(); i++) H[i] = (float)(acc[i] / N);
+    if (p.d_H && p.H_floats < H.size()) { cudaFree(p.d_H); p.d_H = nullptr; }
+    int rc;
+    if ((rc = upload(&p.d_H, H))) return rc;
+    p.H_floats = std::max(p.H_floats, H.size());
+    if (!p.d_tw1k) {
+        std::vector<float> tb;
+        unit_root_table(tb, 1024, 32, 32, 1);
+        if ((rc = upload(&p.d_tw1k, tb))) return rc;
+    }
+    p.general = true; p.real = real_data;
+    p.N = N; p.M = (int)M; p.L = (int)L;
+    p.hopq = (int)(N - span);
+    p.start0 = (K - 1) + a_min * (long long)M;
+    p.K = (int)K;
     p.ready = true;
+    return B200C_OK;
+}
+
+// Decides whether (and how) the fused overlap-save path serves this configuration; leaves
+// p.ready false when the direct kernel (fir.cu) should run instead.
+int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
+                     bool force)
+{
+    p.ready = false; p.general = false; p.real = false;
+    if (dtype == B200C_CF32 && M == 1 && L == 1) {
+        if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
+        if (!force && ntaps < kFirOsAutoMinTaps) return B200C_OK;
+        std::vector<float> tb, hf;
+        int rc;
+        p.N = pick_length(ntaps);
+        if (p.N == 4096) {
+            if (!p.d_twa) {
+                // step twiddles W4096^(j t) = W^(8 a t) * W^(b t), j = 8a + b
+                unit_root_table(tb, 4096, 8, 64, 8);
+                if ((rc = upload(&p.d_twa, tb))) return rc;
+                unit_root_table(tb, 4096, 8, 64, 1);
+                if ((rc = upload(&p.d_twb, tb))) return rc;
+            }
+            taps_spectrum(hf, 4096, taps, ntaps, complex_taps);
+            if ((rc = upload(&p.d_hf, hf))) return rc;
+        } else {
+            if (!p.d_tw1k) {
+                unit_root_table(tb, 1024, 32, 32, 1);
+                if ((rc = upload(&p.d_tw1k, tb))) return rc;
+            }
+            taps_spectrum(hf, 1024, taps, ntaps, complex_taps);
+            if ((rc = upload(&p.d_hf1k, hf))) return rc;
+        }
+        p.K = (int)ntaps;
+        p.ready = true;
+        return B200C_OK;
+    }
+    if ((dtype == B200C_CF32 || dtype == B200C_F32) && M <= 2 && L <= kFirOsGenMaxInterp) {
+        const size_t per_phase = (ntaps + L - 1) / L;
+        if (!force && per_phase < kFirOsAutoMinTaps) return B200C_OK;
+        if (ntaps < 2) return B200C_OK;
+        return configure_general(p, dtype == B200C_F32, taps, ntaps, complex_taps, M, L);
+    }
     return B200C_OK;
 }
 
 void fir_os_destroy(FirOsPlan &p)
 {
-    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k}) {
+    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k, &p.d_H}) {
         if (*d) cudaFree(*d);
         *d = nullptr;
     }
+    p.H_floats = 0;
     p.ready = false;
 }
 
-int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+const char *fir_os_kernel_name(const FirOsPlan &p)
+{
+    if (p.general) return "fir_os32g_kernel";
+    return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
+}
+
+template <int M, bool MULTI_L, bool REAL, int MINB>
+static void launch_general(const FirOs32GArgs &a, long long nblk, int sm_count, cudaStream_t stream)
+{
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * MINB * 4);
+    fir_os32g_kernel<M, MULTI_L, REAL, MINB><<<grid, 32, 0, stream>>>(a);
+}
+
+int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
                   cudaStream_t stream)
 {
-    if (n_out == 0) return B200C_OK;
+    if (nq == 0) return B200C_OK;
+    if (p.general) {
+        FirOs32GArgs a;
+        a.in = d_in; a.out = d_out; a.H = p.d_H; a.tw = p.d_tw1k;
+        a.n_in = (long long)in_elems; a.nq = (long long)nq; a.start0 = p.start0; a.L = p.L; a.hop = p.hopq;
+        const long long per = (long long)p.hopq * (p.real ? 2 : 1);
+        const long long nblk = ((long long)nq + per - 1) / per;
+        const bool ml = p.L > 1;
+        if (p.M == 1) {
+            if (p.real) { if (ml) launch_general<1, true, true, 10>(a, nblk, sm_count, stream); else launch_general<1, false, true, 12>(a, nblk, sm_count, stream); }
+            else { if (ml) launch_general<1, true, false, 10>(a, nblk, sm_count, stream); else launch_general<1, false, false, 12>(a, nblk, sm_count, stream); }
+        } else {
+            if (p.real) { if (ml) launch_general<2, true, true, 8>(a, nblk, sm_count, stream); else launch_general<2, false, true, 10>(a, nblk, sm_count, stream); }
+            else { if (ml) launch_general<2, true, false, 8>(a, nblk, sm_count, stream); else launch_general<2, false, false, 10>(a, nblk, sm_count, stream); }
+        }
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
+    const size_t n_out = nq;
     const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
     if (p.N == 1024) {
         FirOs32Args a;

@@ -89,6 +89,10 @@ class FirFilter:
         return K.value, req.value, M.value, L.value
 
     @property
+    def kernel(self) -> str:
+        return _abi.lib().b200c_fir_kernel(self._h).decode()
+
+    @property
     def K(self) -> int:
         return self.info()[0]
 

@@ -202,27 +202,34 @@ def test_burst_zero_tail(oracle, cuda_device, M, L):
 
 def test_streaming_in_pieces_equals_one_shot(oracle, cuda_device):
     """work() is stateless in the history: feeding consecutive windows that each start K-1
-    elements before the new data reproduces the single-call result (FIRFilter.cpp:304-307)."""
+    elements before the new data reproduces the single-call result (FIRFilter.cpp:304-307).
+    Integer streams: bit for bit.  Float streams on the fused overlap-save path: the transform
+    block partition depends on where a call starts, so pieces agree to rounding (2e-6 of RMS,
+    well inside the 1e-5 parity bar), and bit for bit on the direct kernel."""
     import torch
     from pothoscomms_b200 import FirFilter
     rng = np.random.default_rng(21)
     taps = rng.standard_normal(255)
-    code = oracle.CF32
-    x = _rand_input(oracle, code, 50000, rng)
-    f = FirFilter(code, "REAL")
-    f.set_taps(taps)
-    f.set_rates(2, 3)
-    d = torch.from_numpy(x).cuda()
-    whole, cons_all, _ = f.run(d)
-    pos, outs = 0, []
-    for piece in (1000, 37, 4096, 2, 10000, 12345, 50000):
-        avail = min(piece, x.shape[0] - pos)
-        y, cons, prod = f.run(d[pos: pos + avail].contiguous())
-        outs.append(y.clone())
-        pos += cons           # K-1 (+ remainder) elements stay in the "input buffer"
-    got = torch.cat(outs)
-    assert pos == cons_all
-    assert torch.equal(got, whole[: got.shape[0]]) and got.shape[0] == whole.shape[0]
+    for code in (oracle.CF32, oracle.CI16):
+        x = _rand_input(oracle, code, 50000, rng)
+        f = FirFilter(code, "REAL")
+        f.set_taps(taps * (1.0 if code == oracle.CF32 else 0.01))
+        f.set_rates(2, 3)
+        d = torch.from_numpy(x).cuda()
+        whole, cons_all, _ = f.run(d)
+        pos, outs = 0, []
+        for piece in (1000, 37, 4096, 2, 10000, 12345, 50000):
+            avail = min(piece, x.shape[0] - pos)
+            y, cons, prod = f.run(d[pos: pos + avail].contiguous())
+            outs.append(y.clone())
+            pos += cons           # K-1 (+ remainder) elements stay in the "input buffer"
+        got = torch.cat(outs)
+        assert pos == cons_all and got.shape[0] == whole.shape[0]
+        if code == oracle.CI16 or not f.kernel.startswith("fir_os"):
+            assert torch.equal(got, whole)
+        else:
+            a, b = got.double().cpu().numpy(), whole.double().cpu().numpy()
+            assert np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2)) < 2e-6
 
 
 def test_host_buffer_entry_point(oracle, cuda_device):
@@ -342,7 +349,7 @@ def test_overlap_save_path_matches_oracle_and_direct(oracle, cuda_device, ntaps,
 
 
 def test_overlap_save_limits_fall_back_to_direct(oracle, cuda_device):
-    """More than 2049 taps, resampling, real data and integer types never take the FFT path."""
+    """More than 2049 taps (L = M = 1) and integer types never take the FFT path."""
     rng = np.random.default_rng(4)
     with _with_algo("fft"):
         taps = rng.standard_normal(2050) / 45.0
@@ -357,6 +364,37 @@ def test_overlap_save_limits_fall_back_to_direct(oracle, cuda_device):
         yi_ref, _, _ = oracle.fir(oracle.CI16, False, t2, 1, 1, xi)
         yi, _, _, _ = _run_gpu(oracle.CI16, "REAL", t2, 1, 1, xi)
         assert np.array_equal(yi, yi_ref)
+
+
+@pytest.mark.parametrize("M,L", [(1, 1), (2, 1), (1, 2), (1, 3), (2, 2), (2, 3), (2, 5), (1, 16)])
+@pytest.mark.parametrize("dt,taps_type", [("CF32", "COMPLEX"), ("CF32", "REAL"), ("F32", "REAL")])
+def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type, M, L):
+    """The generalised fused kernel (decimation <= 2, any interpolation, complex or real float32
+    data) against the oracle and against the direct kernel: ragged lengths around the transform
+    hop, tiny inputs, the burst zero tail, tap counts that leave the last phases one tap short."""
+    code = getattr(oracle, dt)
+    if (dt, M, L) == ("CF32", 1, 1):
+        pytest.skip("covered by test_overlap_save_path_matches_oracle_and_direct")
+    rng = np.random.default_rng(7000 + 97 * M + L + (taps_type == "COMPLEX"))
+    for ntaps in (L * 13 + 1, 255):
+        taps = rng.standard_normal(ntaps) / np.sqrt(ntaps / L)
+        if taps_type == "COMPLEX":
+            taps = taps + 1j * rng.standard_normal(ntaps) / np.sqrt(ntaps / L)
+        K = -(-ntaps // L)
+        rms_hint = float(np.sqrt(np.sum(np.abs(taps) ** 2) / L))
+        for n_new, zero_tail in ((M, False), (M * 700 + 1, False), (M * 2049, False), (M * 5000 + M - 1, False), (997, True), (1, True)):
+            x = _rand_input(oracle, code, K - 1 + n_new, rng)
+            y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, zero_tail=zero_tail)
+            with _with_algo("fft"):
+                y_os, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
+                assert f.kernel == "fir_os32g_kernel", f.kernel
+            assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
+            _compare(oracle, code, y_os, y_ref, f"os32g {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
+            with _with_algo("direct"):
+                y_d, cons_d, prod_d, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
+                assert f.kernel == "fir_tile_kernel", f.kernel
+            assert (cons_d, prod_d) == (c_ref, p_ref)
+            _compare(oracle, code, y_d, y_ref, f"direct {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new}", rms_hint)
 
 
 def test_overlap_save_strong_attenuation_stays_in_tolerance(oracle, cuda_device):
