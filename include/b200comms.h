@@ -93,6 +93,24 @@ int b200c_fir_run(b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, 
 int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_out, size_t out_capacity,
                        int zero_tail, size_t *consumed, size_t *produced);
 
+/* ------------------------------------------------------- bank of /comms/fir_filter blocks --- */
+/* `nchan` independent FIRFilter instances of one element type (one per channel of a channeliser /
+ * filter bank: every reference block instance holds all of its own state, filter/FIRFilter.cpp:356-363),
+ * driven together: channel c reads d_in + c*in_stride and writes d_out + c*out_stride (strides in
+ * elements), all channels see the same in_elems / out_capacity, so consume / produce are common.
+ * Every channel has its own taps (b200c_fir_bank_set_taps) but the same tap COUNT and rates.
+ * complex float32 streams run as ONE launch over (channel, block); other types run the
+ * channels' kernels back to back on `stream`.  Results per channel are exactly b200c_fir_run's. */
+typedef struct b200c_fir_bank b200c_fir_bank;
+int b200c_fir_bank_create(b200c_fir_bank **out, int dtype, int taps_kind, size_t nchan, int device);
+int b200c_fir_bank_destroy(b200c_fir_bank *b);
+int b200c_fir_bank_set_taps(b200c_fir_bank *b, size_t chan, const double *taps, size_t ntaps);
+int b200c_fir_bank_set_rates(b200c_fir_bank *b, size_t decim, size_t interp);
+int b200c_fir_bank_info(const b200c_fir_bank *b, size_t *nchan, size_t *K, size_t *input_require);
+int b200c_fir_bank_run(b200c_fir_bank *b, const void *d_in, size_t in_stride, size_t in_elems, void *d_out,
+                       size_t out_stride, size_t out_capacity, int zero_tail, size_t *consumed, size_t *produced,
+                       void *stream);
+
 /* ------------------------------------------------------------------------- /comms/fft --- */
 typedef struct b200c_fft b200c_fft;
 

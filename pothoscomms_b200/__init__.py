@@ -15,6 +15,6 @@ from ._abi import B200CommsError, InvalidArgumentError
 
 _abi.lib()  # fail loudly at import time if the CUDA library is not built
 
-from .handles import DeviceRing, Fft, FirFilter  # noqa: E402
+from .handles import DeviceRing, Fft, FirFilter, FirFilterBank  # noqa: E402
 
-__all__ = ["FirFilter", "Fft", "DeviceRing", "B200CommsError", "InvalidArgumentError"]
+__all__ = ["FirFilter", "FirFilterBank", "Fft", "DeviceRing", "B200CommsError", "InvalidArgumentError"]

@@ -40,6 +40,12 @@ SYMBOLS = {
     "b200c_fir_plan": (_i, [_vp, _sz, _sz, _i, _psz, _psz]),
     "b200c_fir_run": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _psz, _psz, _vp]),
     "b200c_fir_run_host": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _psz, _psz]),
+    "b200c_fir_bank_create": (_i, [_pvp, _i, _i, _sz, _i]),
+    "b200c_fir_bank_destroy": (_i, [_vp]),
+    "b200c_fir_bank_set_taps": (_i, [_vp, _sz, _vp, _sz]),
+    "b200c_fir_bank_set_rates": (_i, [_vp, _sz, _sz]),
+    "b200c_fir_bank_info": (_i, [_vp, _psz, _psz, _psz]),
+    "b200c_fir_bank_run": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _psz, _psz, _vp]),
     "b200c_fft_create": (_i, [_pvp, _i, _sz, _i, _i]),
     "b200c_fft_destroy": (_i, [_vp]),
     "b200c_fft_info": (_i, [_vp, _psz, _pi]),

@@ -103,6 +103,16 @@ struct b200c_fir {
     bool use_os = false;
 };
 
+struct b200c_fir_bank {
+    int device = 0;
+    int dtype = B200C_CF32, taps_kind = B200C_TAPS_REAL;
+    DevInfo di;
+    std::vector<b200c_fir *> ch;   // one /comms/fir_filter state per channel
+    void *d_hf_all = nullptr;      // [nchan][N] tap spectra gathered for the one-launch path
+    size_t hf_capacity = 0;
+    bool dirty = true;
+};
+
 struct b200c_fft {
     int device = 0;
     DevInfo di;
@@ -340,6 +350,121 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
         B200C_CUDA_TRY(cudaMemcpyAsync(dst + b0 * L * esz, h->pipe.d_out[slot], nb * L * esz, cudaMemcpyDeviceToHost, s));
     }
     for (auto s : h->pipe.streams) B200C_CUDA_TRY(cudaStreamSynchronize(s));
+    return B200C_OK;
+}
+
+/* ----------------------------------------------------------------------- filter bank --- */
+int b200c_fir_bank_destroy(b200c_fir_bank *b)
+{
+    if (!b) return B200C_OK;
+    for (auto *c : b->ch) b200c_fir_destroy(c);
+    {
+        DeviceGuard g(b->device);
+        if (b->d_hf_all) cudaFree(b->d_hf_all);
+    }
+    delete b;
+    return B200C_OK;
+}
+
+int b200c_fir_bank_create(b200c_fir_bank **out, int dtype, int taps_kind, size_t nchan, int device)
+{
+    if (!out) return B200C_ERR_INVALID;
+    *out = nullptr;
+    if (nchan == 0 || nchan > (1u << 20)) { set_error("filter bank: channel count %zu out of range", nchan); return B200C_ERR_INVALID; }
+    b200c_fir_bank *b = new (std::nothrow) b200c_fir_bank();
+    if (!b) { set_error("out of host memory"); return B200C_ERR_NOMEM; }
+    b->device = device; b->dtype = dtype; b->taps_kind = taps_kind;
+    b->ch.reserve(nchan);
+    for (size_t i = 0; i < nchan; i++) {
+        b200c_fir *c = nullptr;
+        const int rc = b200c_fir_create(&c, dtype, taps_kind, device);
+        if (rc) { b200c_fir_bank_destroy(b); return rc; }
+        b->ch.push_back(c);
+    }
+    b->di = b->ch[0]->di;
+    *out = b;
+    return B200C_OK;
+}
+
+int b200c_fir_bank_set_taps(b200c_fir_bank *b, size_t chan, const double *taps, size_t ntaps)
+{
+    if (!b) return B200C_ERR_INVALID;
+    if (chan >= b->ch.size()) { set_error("filter bank: channel %zu out of range (have %zu)", chan, b->ch.size()); return B200C_ERR_INVALID; }
+    b->dirty = true;
+    return b200c_fir_set_taps(b->ch[chan], taps, ntaps);
+}
+
+int b200c_fir_bank_set_rates(b200c_fir_bank *b, size_t decim, size_t interp)
+{
+    if (!b) return B200C_ERR_INVALID;
+    b->dirty = true;
+    for (auto *c : b->ch) {
+        const int rc = b200c_fir_set_rates(c, decim, interp);
+        if (rc) return rc;
+    }
+    return B200C_OK;
+}
+
+int b200c_fir_bank_info(const b200c_fir_bank *b, size_t *nchan, size_t *K, size_t *input_require)
+{
+    if (!b) return B200C_ERR_INVALID;
+    if (nchan) *nchan = b->ch.size();
+    return b200c_fir_info(b->ch[0], K, input_require, nullptr, nullptr);
+}
+
+int b200c_fir_bank_run(b200c_fir_bank *b, const void *d_in, size_t in_stride, size_t in_elems, void *d_out, size_t out_stride,
+                       size_t out_capacity, int zero_tail, size_t *consumed, size_t *produced, void *stream)
+{
+    if (!b) return B200C_ERR_INVALID;
+    b200c_fir *h0 = b->ch[0];
+    for (auto *c : b->ch)
+        if (c->table.K != h0->table.K || c->ntaps != h0->ntaps) {
+            set_error("filter bank: all channels must have the same number of taps (%zu vs %zu)", c->ntaps, h0->ntaps);
+            return B200C_ERR_INVALID;
+        }
+    size_t c = 0, p = 0;
+    fir_plan_counts(h0, in_elems, out_capacity, zero_tail, &c, &p);
+    if (consumed) *consumed = c;
+    if (produced) *produced = p;
+    if (c == 0) return B200C_OK;
+    if (!d_in || !d_out) { set_error("b200c_fir_bank_run: null device buffer"); return B200C_ERR_INVALID; }
+    const size_t nch = b->ch.size(), esz = dtype_bytes(b->dtype);
+    if (nch > 1 && (in_stride < in_elems || out_stride < p)) { set_error("filter bank: channel stride shorter than the channel"); return B200C_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", b->device); return B200C_ERR_CUDA; }
+    bool fast = h0->use_os && !h0->os.general;
+    for (auto *ch : b->ch) fast = fast && ch->use_os && !ch->os.general && ch->os.N == h0->os.N;
+    if (fast) {
+        // one launch over (channel, block): gather the channels' tap spectra once per setTaps()
+        const size_t N = (size_t)h0->os.N, row = N * 2 * sizeof(float);
+        if (b->dirty) {
+            if (b->hf_capacity < nch * row) {
+                if (b->d_hf_all) cudaFree(b->d_hf_all);
+                b->d_hf_all = nullptr; b->hf_capacity = 0;
+                B200C_CUDA_TRY(cudaMalloc(&b->d_hf_all, nch * row));
+                b->hf_capacity = nch * row;
+            }
+            for (size_t i = 0; i < nch; i++) {
+                const void *src = N == 1024 ? b->ch[i]->os.d_hf1k : b->ch[i]->os.d_hf;
+                B200C_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(b->d_hf_all) + i * row, src, row, cudaMemcpyDeviceToDevice,
+                                               (cudaStream_t)stream));
+            }
+            b->dirty = false;
+        }
+        FirOsBatch batch;
+        batch.nchan = (int)nch; batch.in_stride = (long long)in_stride; batch.out_stride = (long long)out_stride;
+        batch.d_hf = b->d_hf_all;
+        return fir_os_launch(h0->os, d_in, in_elems, d_out, c / h0->M, b->di.sm_count, (cudaStream_t)stream, &batch);
+    }
+    // every other type / rate: the channels' own kernels back to back on the stream
+    for (size_t i = 0; i < nch; i++) {
+        b200c_fir *h = b->ch[i];
+        const char *src = static_cast<const char *>(d_in) + i * in_stride * esz;
+        char *dst = static_cast<char *>(d_out) + i * out_stride * esz;
+        const int rc = h->use_os ? fir_os_launch(h->os, src, in_elems, dst, c / h->M, h->di.sm_count, (cudaStream_t)stream)
+                                 : fir_launch(h->table, h->ds, src, in_elems, dst, c / h->M, h->di.sm_count, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     return B200C_OK;
 }
 

@@ -72,8 +72,15 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
                      bool force);
 void fir_os_destroy(FirOsPlan &p);
 const char *fir_os_kernel_name(const FirOsPlan &p);
+// Filter bank: `nchan` equal-length streams `in_stride` / `out_stride` elements apart, each with its
+// own tap spectrum in d_hf[chan][N] (same tap count, so same transform length and hop), one launch.
+struct FirOsBatch {
+    int nchan = 1;
+    long long in_stride = 0, out_stride = 0;
+    const void *d_hf = nullptr;
+};
 // nq = output blocks q (= consumed / M); outputs written = nq * L
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const FirOsBatch *batch = nullptr);
 
 } // namespace b200c

@@ -14,6 +14,7 @@
 // costs TWO exchanges.  All arithmetic is packed f32x2 (packed.cuh).
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <vector>
 
@@ -23,13 +24,15 @@
 namespace b200c {
 
 struct FirOs64Args {
-    const void *in;     // element 0 = first history sample
+    const void *in;     // channel 0, element 0 = first history sample
     void *out;
-    const void *hf;     // [4096] spectrum of the taps / 4096, natural order
+    const void *hf;     // [nchan][4096] spectrum of the taps / 4096, natural order
     const void *twa;    // [8][64]  W4096^(8*a*t)
     const void *twb;    // [8][64]  W4096^(b*t)
-    long long n_in;     // valid input elements (beyond: zeros -> burst zero tail)
-    long long n_out;    // outputs to produce
+    long long n_in;     // valid input elements per channel (beyond: zeros -> burst zero tail)
+    long long n_out;    // outputs to produce per channel
+    long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
+    int nchan;
     int K;              // taps
 };
 
@@ -91,38 +94,44 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
     const int t = threadIdx.x;
     const c2 *__restrict__ twa = static_cast<const c2 *>(a.twa);
     const c2 *__restrict__ twb = static_cast<const c2 *>(a.twb);
-    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
-    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
-    c2 *__restrict__ out = static_cast<c2 *>(a.out);
     const int Km1 = a.K - 1;
     const int hop = 4096 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
+    // Tasks = (channel, block), channel-major, taken grid-stride: at any moment the resident CTAs
+    // sweep one contiguous window of the stream(s) (DRAM-page friendly; a contiguous run per CTA
+    // measured 18 % slower), and a block's overlap with its neighbour is an L2 hit.
+    // (one 64-bit division per launch, none per task: the step is kept as (channels, blocks))
+    const long long tstep = gridDim.x, dch = tstep / nblk, dblk = tstep - dch * nblk;
+    long long ch = (long long)blockIdx.x / nblk, blk = (long long)blockIdx.x - ch * nblk;
     // A block whose 4096 inputs (plus alignment slack) are all inside the stream is fetched by one
     // bulk copy, issued while the previous block is still in its last register pass; the few
     // edge blocks (zero tail, unaligned stream start) use guarded loads.
-    const int in_mis = (int)((reinterpret_cast<unsigned long long>(in) >> 3) & 1);
-    auto bulk_ok = [&](long long blk) {
+    auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
+        if (ch >= a.nchan) return false;
         const long long base = blk * hop;
-        const int mis = (int)((base + in_mis) & 1);
-        return blk < nblk && base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
-    };
-    auto bulk_issue = [&](long long blk) {
-        const long long base = blk * hop;
-        const int mis = (int)((base + in_mis) & 1);
-        bulk_load(F, in + (base - mis), kBulkElems * (unsigned)sizeof(c2), &bar);
+        const c2 *in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
+        src = in + (base - mis);
+        return base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
     };
     if (t == 0) mbar_init(&bar, 1);
     __syncthreads();
-    bool pending = bulk_ok(blockIdx.x);
-    if (pending && t == 0) bulk_issue(blockIdx.x);
+    const c2 *src = nullptr;
+    bool pending = bulk_src(ch, blk, src);
+    if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), &bar);
     unsigned parity = 0;
 
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    while (ch < a.nchan) {
         const long long base = blk * hop;
+        long long nch = ch + dch, nblkpos = blk + dblk;      // this CTA's next task
+        if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
+        const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 4096;
+        c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
         c2 v[64];
         // ---- forward step 1: thread n2 = t, x[64 n1 + n2] over n1
         if (pending) {
-            const int mis = (int)((base + in_mis) & 1);
+            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
             mbar_wait(&bar, parity);
             parity ^= 1;
 #pragma unroll
@@ -158,8 +167,8 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
 #pragma unroll
         for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
         __syncthreads();                                     // F is free: fetch the next block into it
-        pending = bulk_ok(blk + gridDim.x);
-        if (pending && t == 0) bulk_issue(blk + gridDim.x);
+        pending = bulk_src(nch, nblkpos, src);
+        if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), &bar);
         dft64_dif<true>(v);
         // circular result c[i], i = 64 n1 + t; the alias-free part i >= K-1 is y[base + i - (K-1)]
         c2 *o = out + (base - Km1);
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
                 if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev64(n1)]);
             }
         }
+        ch = nch; blk = nblkpos;
     }
 }
 
@@ -188,9 +198,11 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
 struct FirOs32Args {
     const void *in;
     void *out;
-    const void *hf;     // [1024] spectrum of the taps / 1024
+    const void *hf;     // [nchan][1024] spectrum of the taps / 1024
     const void *tw;     // [32][32] W1024^(j*t)
-    long long n_in, n_out;
+    long long n_in, n_out;             // per channel
+    long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
+    int nchan;
     int K;
 };
 
@@ -203,38 +215,40 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     c2 *F = Fs[w];
     unsigned long long *bar = &bars[w];
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
-    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
-    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
-    c2 *__restrict__ out = static_cast<c2 *>(a.out);
     const int Km1 = a.K - 1;
     const int hop = 1024 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
-    const long long stride = (long long)gridDim.x * WARPS;
+    // tasks = (channel, block), channel-major, taken grid-stride by the warps (see fir_os64_kernel)
+    const long long tstep = (long long)gridDim.x * WARPS, dch = tstep / nblk, dblk = tstep - dch * nblk;
+    const long long task0 = (long long)blockIdx.x * WARPS + w;
+    long long ch = task0 / nblk, blk = task0 - ch * nblk;
     // the warp's next block is fetched into its exchange tile by one bulk copy while the warp is
-    // in its last register pass (see fir_os64_kernel); edge blocks use guarded loads
+    // in its last register pass; edge blocks use guarded loads
     constexpr int kBulk = 1026;
-    const int in_mis = (int)((reinterpret_cast<unsigned long long>(in) >> 3) & 1);
-    auto bulk_ok = [&](long long blk) {
+    auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
+        if (ch >= a.nchan) return false;
         const long long base = blk * hop;
-        const int mis = (int)((base + in_mis) & 1);
-        return blk < nblk && base - mis >= 0 && base - mis + kBulk <= a.n_in;
+        const c2 *in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
+        src = in + (base - mis);
+        return base - mis >= 0 && base - mis + kBulk <= a.n_in;
     };
-    auto bulk_issue = [&](long long blk) {
-        const long long base = blk * hop;
-        const int mis = (int)((base + in_mis) & 1);
-        bulk_load(F, in + (base - mis), kBulk * (unsigned)sizeof(c2), bar);
-    };
-    long long blk = (long long)blockIdx.x * WARPS + w;
     if (t == 0) mbar_init(bar, 1);
     __syncwarp();
-    bool pending = bulk_ok(blk);
-    if (pending && t == 0) bulk_issue(blk);
+    const c2 *src = nullptr;
+    bool pending = bulk_src(ch, blk, src);
+    if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
-    for (; blk < nblk; blk += stride) {
+    while (ch < a.nchan) {
         const long long base = blk * hop;
+        long long nch = ch + dch, nblkpos = blk + dblk;      // this warp's next task
+        if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
+        const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 1024;
+        c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
         c2 v[32];
         if (pending) {
-            const int mis = (int)((base + in_mis) & 1);
+            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
             mbar_wait(bar, parity);
             parity ^= 1;
 #pragma unroll
@@ -268,8 +282,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
         __syncwarp();                                        // the tile is free: fetch the next block into it
-        pending = bulk_ok(blk + stride);
-        if (pending && t == 0) bulk_issue(blk + stride);
+        pending = bulk_src(nch, nblkpos, src);
+        if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), bar);
         dft32_dif<true>(v);
         c2 *o = out + (base - Km1);
         if (base + hop <= a.n_out) {
@@ -285,6 +299,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
                 if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev32(n1)]);
             }
         }
+        ch = nch; blk = nblkpos;
     }
 }
 
@@ -340,14 +355,23 @@ __device__ __forceinline__ void fft1024_inv(c2 (&v)[32], c2 *F, const c2 *__rest
     dft32_dif<true>(v);
 }
 
-template <int M, bool MULTI_L, bool REAL, int MINB>
+// Shared memory of one warp: the 32 x 33 exchange tile, or -- when the L output slots are staged
+// for a coalesced store (TILE_OUT) -- L planes of `plane` elements [p][u] with the exchange tile
+// aliased onto the LAST plane (slot L-1 is written into its plane only after its own exchanges).
+// Without staging, stores of slot p would touch every L-th element: partial 32-byte sectors,
+// which cost 3x the L2 write transactions and read-modify-write DRAM traffic (ncu, C3).
+constexpr int kOsgPlane = 1024 + 37;   // >= kOs32SmemElems; odd offset between planes spreads the banks
+__host__ __device__ constexpr int osg_smem_elems(int L, bool tile_out) { return tile_out ? L * kOsgPlane : kOs32SmemElems; }
+
+template <int M, bool MULTI_L, bool REAL, bool TILE_OUT, int MINB>
 __global__ void __launch_bounds__(32, MINB) fir_os32g_kernel(const FirOs32GArgs a)
 {
-    __shared__ c2 F[kOs32SmemElems];
+    extern __shared__ __align__(16) c2 smem_g[];
     const int t = threadIdx.x;
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ H = static_cast<const c2 *>(a.H);
     const int L = a.L, hop = a.hop;
+    c2 *F = TILE_OUT ? smem_g + (L - 1) * kOsgPlane : smem_g;
     constexpr int NB = REAL ? 2 : 1;                      // stream blocks per transform
     const long long nblk = (a.nq + (long long)hop * NB - 1) / ((long long)hop * NB);
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
@@ -396,7 +420,12 @@ __global__ void __launch_bounds__(32, MINB) fir_os32g_kernel(const FirOs32GArgs 
             }
             fft1024_inv(w, F, tw, t);
             // c_p[u], u = 32 n1 + t < hop, is y[(Q0 + u) L + p]  (REAL: Im part belongs to block B)
-            if constexpr (REAL) {
+            if constexpr (TILE_OUT) {
+                __syncwarp();                             // the last plane doubles as the exchange tile
+                c2 *plane = smem_g + p * kOsgPlane;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) plane[32 * n1 + t] = w[rev32(n1)];
+            } else if constexpr (REAL) {
                 float *__restrict__ out = static_cast<float *>(a.out);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1++) {
@@ -418,29 +447,75 @@ __global__ void __launch_bounds__(32, MINB) fir_os32g_kernel(const FirOs32GArgs 
                 }
             }
         }
+        if constexpr (TILE_OUT) {
+            // flush: output j = u L + p of this block, contiguous in memory, lane-contiguous here
+            __syncwarp();
+            const long long left = a.nq - Q0;             // output blocks q still wanted from Q0 on
+            const int nu = left < hop ? (int)left : hop;  // block A
+            const int total = nu * L;
+            const int dq = 32 / L, dr = 32 - dq * L;      // (u, p) step for j += 32, no division in the loop
+            if constexpr (REAL) {
+                float *__restrict__ out = static_cast<float *>(a.out);
+                const long long leftb = left - hop;
+                const int totalb = (leftb <= 0 ? 0 : (leftb < hop ? (int)leftb : hop)) * L;
+                float *oa = out + Q0 * L, *ob = oa + (long long)hop * L;
+                int u = t / L, p = t - u * L;
+                for (int j = t; j < total; j += 32) {
+                    float ya, yb;
+                    upk(smem_g[p * kOsgPlane + u], ya, yb);
+                    __stcg(oa + j, ya);
+                    if (j < totalb) __stcg(ob + j, yb);
+                    u += dq; p += dr;
+                    if (p >= L) { p -= L; u++; }
+                }
+            } else {
+                c2 *__restrict__ o = static_cast<c2 *>(a.out) + Q0 * L;
+                int u = t / L, p = t - u * L;
+                for (int j = t; j < total; j += 32) {
+                    __stcg(o + j, smem_g[p * kOsgPlane + u]);
+                    u += dq; p += dr;
+                    if (p >= L) { p -= L; u++; }
+                }
+            }
+            __syncwarp();                                 // planes are free for the next block
+        }
     }
 }
 
 // ------------------------------------------------------------------------------- host ---
+// in-place forward DFT (e^{-2 pi i nk/N}), N a power of two, double precision (host, setTaps path)
+static void host_fft(std::vector<std::complex<double>> &x)
+{
+    const size_t n = x.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(x[i], x[j]);
+    }
+    const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        std::vector<std::complex<double>> w(len / 2);
+        for (size_t k = 0; k < len / 2; k++) w[k] = std::polar(1.0, -two_pi * (double)k / (double)len);
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const std::complex<double> u = x[i + k], v = x[i + k + len / 2] * w[k];
+                x[i + k] = u + v;
+                x[i + k + len / 2] = u - v;
+            }
+    }
+}
+
 static void taps_spectrum(std::vector<float> &hf, int N, const double *taps, size_t ntaps, bool complex_taps)
 {
-    // Hf[f] = (1/N) * sum_k h[k] exp(-2*pi*i*f*k/N), accumulated in double
-    std::vector<double> cs(N), sn(N);
-    for (int i = 0; i < N; i++) {
-        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
-        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
-    }
-    hf.assign(2 * (size_t)N, 0.f);
+    // Hf[f] = (1/N) * sum_k h[k] exp(-2*pi*i*f*k/N) in double, rounded once to float
+    std::vector<std::complex<double>> x((size_t)N);
+    for (size_t k = 0; k < ntaps; k++) x[k] = complex_taps ? std::complex<double>(taps[2 * k], taps[2 * k + 1]) : std::complex<double>(taps[k], 0.0);
+    host_fft(x);
+    hf.resize(2 * (size_t)N);
     for (int f = 0; f < N; f++) {
-        double re = 0, im = 0;
-        for (size_t k = 0; k < ntaps; k++) {
-            const double hr = complex_taps ? taps[2 * k] : taps[k], hi = complex_taps ? taps[2 * k + 1] : 0.0;
-            const int idx = (int)(((long long)f * (long long)k) & (N - 1));
-            re += hr * cs[idx] - hi * sn[idx];
-            im += hr * sn[idx] + hi * cs[idx];
-        }
-        hf[2 * f] = (float)(re / N);
-        hf[2 * f + 1] = (float)(im / N);
+        hf[2 * f] = (float)(x[f].real() / N);
+        hf[2 * f + 1] = (float)(x[f].imag() / N);
     }
 }
 
@@ -504,24 +579,17 @@ static int configure_general(FirOsPlan &p, bool real_data, const double *taps, s
     }
     const long long span = a_max - a_min;
     if (first || span > kFirOsGenMaxSpan) return B200C_OK;   // not applicable: the direct kernel keeps the job
-    std::vector<double> cs(N), sn(N);
-    for (int i = 0; i < N; i++) {
-        const double ph = -2.0 * 3.14159265358979323846264338327950288 * i / N;
-        cs[i] = std::cos(ph); sn[i] = std::sin(ph);
-    }
     // c_p[u] = sum_e sum_a g[a] b_e[u + (a - a_min)]  ==  circular convolution with g'[(N - (a - a_min)) mod N] = g[a]
-    std::vector<double> acc(2 * (size_t)L * M * N, 0.0);
-    for (const Term &t : terms) {
-        const int spos = (int)((N - (t.a - a_min)) % N);
-        double *dst = acc.data() + 2 * ((size_t)t.p * M + t.e) * N;
+    std::vector<std::vector<std::complex<double>>> gp((size_t)L * M, std::vector<std::complex<double>>((size_t)N));
+    for (const Term &t : terms) gp[(size_t)t.p * M + t.e][(size_t)((N - (t.a - a_min)) % N)] += std::complex<double>(t.hr, t.hi);
+    std::vector<float> H(2 * (size_t)L * M * N);
+    for (size_t sub = 0; sub < gp.size(); sub++) {
+        host_fft(gp[sub]);
         for (int f = 0; f < N; f++) {
-            const int idx = (int)(((long long)f * spos) & (N - 1));
-            dst[2 * f] += t.hr * cs[idx] - t.hi * sn[idx];
-            dst[2 * f + 1] += t.hr * sn[idx] + t.hi * cs[idx];
+            H[2 * (sub * N + f)] = (float)(gp[sub][f].real() / N);
+            H[2 * (sub * N + f) + 1] = (float)(gp[sub][f].imag() / N);
         }
     }
-    std::vector<float> H(acc.size());
-    for (size_t i = 0; i < acc.size(); i++) H[i] = (float)(acc[i] / N);
     if (p.d_H && p.H_floats < H.size()) { cudaFree(p.d_H); p.d_H = nullptr; }
     int rc;
     if ((rc = upload(&p.d_H, H))) return rc;
@@ -599,40 +667,55 @@ const char *fir_os_kernel_name(const FirOsPlan &p)
     return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
 }
 
-template <int M, bool MULTI_L, bool REAL, int MINB>
-static void launch_general(const FirOs32GArgs &a, long long nblk, int sm_count, cudaStream_t stream)
+template <int M, bool MULTI_L, bool REAL, bool TILE_OUT, int MINB>
+static int launch_general(const FirOs32GArgs &a, long long nblk, int sm_count, cudaStream_t stream)
 {
-    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * MINB * 4);
-    fir_os32g_kernel<M, MULTI_L, REAL, MINB><<<grid, 32, 0, stream>>>(a);
+    auto kern = fir_os32g_kernel<M, MULTI_L, REAL, TILE_OUT, MINB>;
+    const size_t smem = sizeof(c2) * (size_t)osg_smem_elems(a.L, TILE_OUT);
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    B200C_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+        B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured[dev] = true;
+    }
+    const long long by_smem = std::max<long long>(1, (220 * 1024) / (long long)(smem + 1024));
+    const int per_sm = (int)std::min<long long>(MINB, by_smem);
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * per_sm * 4);
+    kern<<<grid, 32, smem, stream>>>(a);
+    B200C_CUDA_TRY(cudaGetLastError());
+    return B200C_OK;
 }
 
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
-                  cudaStream_t stream)
+                  cudaStream_t stream, const FirOsBatch *batch)
 {
     if (nq == 0) return B200C_OK;
+    const int nchan = batch ? batch->nchan : 1;
     if (p.general) {
+        if (batch) { set_error("filter bank: the batched launch serves complex float32 L = M = 1 only"); return B200C_ERR_UNSUPPORTED; }
         FirOs32GArgs a;
         a.in = d_in; a.out = d_out; a.H = p.d_H; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.nq = (long long)nq; a.start0 = p.start0; a.L = p.L; a.hop = p.hopq;
         const long long per = (long long)p.hopq * (p.real ? 2 : 1);
         const long long nblk = ((long long)nq + per - 1) / per;
-        const bool ml = p.L > 1;
-        if (p.M == 1) {
-            if (p.real) { if (ml) launch_general<1, true, true, 10>(a, nblk, sm_count, stream); else launch_general<1, false, true, 12>(a, nblk, sm_count, stream); }
-            else { if (ml) launch_general<1, true, false, 10>(a, nblk, sm_count, stream); else launch_general<1, false, false, 12>(a, nblk, sm_count, stream); }
-        } else {
-            if (p.real) { if (ml) launch_general<2, true, true, 8>(a, nblk, sm_count, stream); else launch_general<2, false, true, 10>(a, nblk, sm_count, stream); }
-            else { if (ml) launch_general<2, true, false, 8>(a, nblk, sm_count, stream); else launch_general<2, false, false, 10>(a, nblk, sm_count, stream); }
-        }
-        B200C_CUDA_TRY(cudaGetLastError());
-        return B200C_OK;
+        // slot staging for a coalesced store pays from L = 2 and fits shared memory up to L = 4
+        const bool ml = p.L > 1, tile = p.L >= 2 && p.L <= 4;
+#define OSG(MM, RR, MB1, MBL)                                                                                      \
+    (!ml ? launch_general<MM, false, RR, false, MB1>(a, nblk, sm_count, stream)                                      \
+         : tile ? launch_general<MM, true, RR, true, MBL>(a, nblk, sm_count, stream)                                 \
+                : launch_general<MM, true, RR, false, MBL>(a, nblk, sm_count, stream))
+        if (p.M == 1) return p.real ? OSG(1, true, 12, 10) : OSG(1, false, 12, 10);
+        return p.real ? OSG(2, true, 10, 8) : OSG(2, false, 10, 8);
+#undef OSG
     }
     const size_t n_out = nq;
-    const long long nblk = ((long long)n_out + p.hop() - 1) / p.hop();
+    const long long nblk = (((long long)n_out + p.hop() - 1) / p.hop()) * nchan;
     if (p.N == 1024) {
         FirOs32Args a;
-        a.in = d_in; a.out = d_out; a.hf = p.d_hf1k; a.tw = p.d_tw1k;
+        a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
+        a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
         static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 112; }();
 #define OS32_LAUNCH(W, MB)                                                                                        \
     {                                                                                                             \
@@ -655,8 +738,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         return B200C_OK;
     }
     FirOs64Args a;
-    a.in = d_in; a.out = d_out; a.hf = p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
+    a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
+    a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
     static const int minb = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 4; }();
     const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
     switch (minb) {

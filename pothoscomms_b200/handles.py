@@ -142,6 +142,54 @@ class FirFilter:
         return out.reshape(-1, nc)[: p.value], c.value, p.value
 
 
+class FirFilterBank:
+    """Owner of a b200c_fir_bank handle: `nchan` FIR filter states run by one call (channeliser)."""
+
+    def __init__(self, dtype, taps_type: str = "REAL", nchan: int = 1, device: int = 0):
+        self.dtype = dtype_code(dtype)
+        if taps_type not in ("REAL", "COMPLEX"):
+            raise _abi.InvalidArgumentError(_abi.ERR_UNSUPPORTED, f"FIRFilterFactory: unsupported tapsType {taps_type!r}")
+        self.complex_taps = taps_type == "COMPLEX"
+        self.nchan = int(nchan)
+        self.device = device
+        self._h = ctypes.c_void_p()
+        _abi.check(_abi.lib().b200c_fir_bank_create(ctypes.byref(self._h), self.dtype, int(self.complex_taps), self.nchan, device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _abi.lib().b200c_fir_bank_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def set_taps(self, chan: int, taps):
+        t = _taps_array(taps, self.complex_taps)
+        n = t.size // (2 if self.complex_taps else 1)
+        _abi.check(_abi.lib().b200c_fir_bank_set_taps(self._h, chan, t.ctypes.data, n))
+
+    def set_rates(self, decim: int, interp: int):
+        _abi.check(_abi.lib().b200c_fir_bank_set_rates(self._h, decim, interp))
+
+    def info(self):
+        n, K, req = (ctypes.c_size_t() for _ in range(3))
+        _abi.check(_abi.lib().b200c_fir_bank_info(self._h, ctypes.byref(n), ctypes.byref(K), ctypes.byref(req)))
+        return n.value, K.value, req.value
+
+    def run(self, d_in, out, zero_tail: bool = False, stream=None):
+        """d_in: CUDA tensor [nchan, n_in, ncomp]; out: CUDA tensor [nchan, capacity, ncomp].
+        Returns (consumed, produced) per channel."""
+        import torch
+        nc = ncomp(self.dtype)
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.dtype == torch_scalar(self.dtype) and d_in.shape[0] == self.nchan
+        assert out.is_cuda and out.is_contiguous() and out.shape[0] == self.nchan
+        n_in, cap = d_in.shape[1], out.shape[1]
+        c, p = ctypes.c_size_t(), ctypes.c_size_t()
+        _abi.check(_abi.lib().b200c_fir_bank_run(self._h, ctypes.c_void_p(d_in.data_ptr()), n_in, n_in, ctypes.c_void_p(out.data_ptr()),
+                                                 cap, cap, int(zero_tail), ctypes.byref(c), ctypes.byref(p),
+                                                 _stream_ptr(stream, d_in.device)))
+        return c.value, p.value
+
+
 class Fft:
     """Owner of a b200c_fft handle (the FFTAux of one /comms/fft block)."""
 

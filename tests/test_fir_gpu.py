@@ -408,3 +408,39 @@ def test_overlap_save_strong_attenuation_stays_in_tolerance(oracle, cuda_device)
     with _with_algo("fft"):
         y, _, _, _ = _run_gpu(oracle.CF32, tt, taps, 1, 1, x)
     _compare(oracle, oracle.CF32, y, y_ref, "headline via overlap-save")
+
+
+@pytest.mark.parametrize("dt,taps_type,ntaps", [("CF32", "COMPLEX", 64), ("CF32", "COMPLEX", 1024), ("CF32", "REAL", 300),
+                                                ("CI16", "COMPLEX", 33), ("F32", "REAL", 40)])
+def test_filter_bank_matches_per_channel_filters(oracle, cuda_device, dt, taps_type, ntaps):
+    """b200c_fir_bank_run: every channel's output equals what its own FIRFilter instance gives
+    (the oracle per channel): one launch over (channel, block) for complex float32, the
+    channels' kernels back to back otherwise; padded channel strides; zero tail."""
+    import torch
+    from pothoscomms_b200 import FirFilterBank
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(ntaps + code)
+    nchan, n_in = 7, ntaps - 1 + 9001
+    nc = 2 if code & 1 else 1
+    bank = FirFilterBank(code, taps_type, nchan)
+    taps = []
+    for c in range(nchan):
+        h = rng.standard_normal(ntaps) / np.sqrt(ntaps)
+        if taps_type == "COMPLEX":
+            h = h + 1j * rng.standard_normal(ntaps) / np.sqrt(ntaps)
+        taps.append(h)
+        bank.set_taps(c, h)
+    assert bank.info()[:2] == (nchan, ntaps)
+    x = np.stack([_rand_input(oracle, code, n_in, rng) for _ in range(nchan)])
+    d = torch.from_numpy(x).cuda()
+    for zero_tail in (False, True):
+        cap = n_in + 5
+        out = torch.zeros((nchan, cap, nc), dtype=d.dtype, device=d.device)
+        cons, prod = bank.run(d, out, zero_tail=zero_tail)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for c in range(nchan):
+            y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps[c], 1, 1, x[c], zero_tail=zero_tail)
+            assert (cons, prod) == (c_ref, p_ref)
+            _compare(oracle, code, got[c, :prod], y_ref, f"bank {dt} chan {c} zt={zero_tail}")
+            assert not got[c, prod:].any(), "wrote past the channel's produced count"
