@@ -257,13 +257,105 @@ def bench_fft(args):
     return 0
 
 
+def bench_bank(args):
+    """BASELINE config 5: 1024-channel filter bank, one 1024-tap complex band-pass per channel,
+    2^20 samples per channel, channels sharded over the ranks (no exchange: SURVEY.md 8e).
+    Strong scaling: the bank is fixed, every rank takes 1024/N channels.  One step = one
+    b200c_fir_bank_run over the rank's channels (one launch over (channel, block))."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pothoscomms_b200 import FirFilterBank, sharding
+    from pothoscomms_b200 import workloads as wl
+    from pothoscomms_b200.handles import dtype_code
+    args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    code = dtype_code("complex_float32")
+    nchan_total, ntaps = args.channels or 1024, 1024
+    log2n = args.log2_samples or 20
+    c0, c1 = sharding.channel_range(nchan_total, world, rank)
+    nch = c1 - c0
+    n_new = 1 << log2n
+    bank = FirFilterBank(code, "COMPLEX", nch, device=local_rank)
+    for c in range(c0, c1):
+        bank.set_taps(c - c0, wl.bank_taps(c, nchan_total, ntaps))
+    K = bank.info()[1]
+    x = torch.empty((nch, K - 1 + n_new, 2), dtype=torch.float32, device=dev)
+    base = [wl.tone_noise_torch(code, K - 1 + n_new, 0xC0FFEE05 + i, dev) for i in range(8)]
+    for c in range(nch):
+        x[c] = base[(c0 + c) % 8]
+    del base
+    out = torch.empty((nch, n_new, 2), dtype=torch.float32, device=dev)
+    for _ in range(args.warmup):
+        cons, prod = bank.run(x, out)
+    torch.cuda.synchronize()
+    assert (cons, prod) == (n_new, n_new), (cons, prod)
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        bank.run(x, out)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = tmax.item()
+    total = nchan_total * n_new
+    value = total / (ms * 1e-3) / 1e6
+    # spot check: channel 0 of this rank against a single-stream filter (same library path the tests pin to the oracle)
+    from pothoscomms_b200 import FirFilter
+    f1 = FirFilter(code, "COMPLEX", device=local_rank)
+    f1.set_taps(wl.bank_taps(c0, nchan_total, ntaps))
+    y1, _, _ = f1.run(x[0].contiguous())
+    assert torch.equal(y1[:4096], out[0, :4096]), "bank channel differs from its single-stream filter"
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks, peak_kind = measured_peaks()
+    achieved = 16.0 * nch * n_new / (ms * 1e-3) / 1e9      # this rank's kernel: its channels' bytes over the step time
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c5_bank: {nchan_total}-channel filter bank, {ntaps}-tap complex_float32 band-pass per channel, "
+                               f"2^{log2n} samples per channel, channels sharded over {world} GPU(s), no exchange",
+                   "channels_per_gpu": nch, "l2_policy": "inputs larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "kernel": "fir_os64_kernel",
+                     "note": "fused overlap-save, one launch over (channel, block); 16 B per sample"},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4", "c4_i16"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4", "c4_i16", "c5_bank"])
+    ap.add_argument("--ntaps", type=int, default=None, help="tap-count sweep: cf32 L=M=1 with this many complex taps")
+    ap.add_argument("--channels", type=int, default=None, help="c5_bank: total channels (default 1024)")
     ap.add_argument("--log2-samples", type=int, default=None, help="override samples per GPU (debug)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -272,6 +364,8 @@ def main():
         return reference_arm(args)
     if args.workload in ("c4", "c4_i16"):
         return bench_fft(args)
+    if args.workload == "c5_bank":
+        return bench_bank(args)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np
@@ -292,6 +386,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.ntaps:   # tap-count sweeps: cf32 stream, `ntaps` complex band-pass taps
+        WORKLOADS[args.workload] = ("complex_float32", f"sweep{args.ntaps}", 1, 1, 28, 16.0)
     dt_name, taps_name, M, L, log2n, bytes_per_sample = WORKLOADS[args.workload]
     if args.log2_samples:
         log2n = args.log2_samples

@@ -63,9 +63,11 @@ struct FirOsPlan {
     int hop() const { return general ? hopq * (real ? 2 : 1) : N - (K - 1); }
 };
 constexpr size_t kFirOsMaxTaps = 2049;
-constexpr size_t kFirOs1kMaxTaps = 300;
-// automatic switch from the direct kernel: taps per output at or above this take the fused path
-constexpr size_t kFirOsAutoMinTaps = 12;
+constexpr size_t kFirOs1kMaxTaps = 448;       // measured crossover of the 1024- and 4096-point kernels
+// automatic switch from the direct kernel (taps per output phase at or above this take the fused
+// path): real float32 streams, and resamplers where the direct kernel still wins for short phases
+constexpr size_t kFirOsAutoMinTapsReal = 8;
+constexpr size_t kFirOsAutoMinTapsResamp = 24;
 constexpr long long kFirOsGenMaxSpan = 400;   // general kernel: keep hop >= ~60 % of the block
 constexpr size_t kFirOsGenMaxInterp = 64;
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,

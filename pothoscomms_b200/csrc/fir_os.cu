@@ -615,8 +615,8 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
 {
     p.ready = false; p.general = false; p.real = false;
     if (dtype == B200C_CF32 && M == 1 && L == 1) {
+        // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up
         if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
-        if (!force && ntaps < kFirOsAutoMinTaps) return B200C_OK;
         std::vector<float> tb, hf;
         int rc;
         p.N = pick_length(ntaps);
@@ -644,7 +644,8 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
     }
     if ((dtype == B200C_CF32 || dtype == B200C_F32) && M <= 2 && L <= kFirOsGenMaxInterp) {
         const size_t per_phase = (ntaps + L - 1) / L;
-        if (!force && per_phase < kFirOsAutoMinTaps) return B200C_OK;
+        const size_t min_taps = (M == 1 && L == 1) ? kFirOsAutoMinTapsReal : kFirOsAutoMinTapsResamp;
+        if (!force && per_phase < min_taps) return B200C_OK;
         if (ntaps < 2) return B200C_OK;
         return configure_general(p, dtype == B200C_F32, taps, ntaps, complex_taps, M, L);
     }

@@ -71,7 +71,15 @@ def config_taps(name: str):
         return root_raised_cosine(48, 3.0, 0.5), "REAL"
     if name == "real64":     # real data, 64 real taps
         return sinc_lowpass(64, 0.1), "REAL"
+    if name.startswith("sweep"):   # bench.py --ntaps N
+        return complex_bandpass(int(name[5:]), F0 / FS, 0.1), "COMPLEX"
     raise KeyError(name)
+
+
+def bank_taps(chan: int, nchan: int, ntaps: int = 1024) -> np.ndarray:
+    """Channel `chan` of an `nchan`-channel channeliser: the low-pass prototype (half-width
+    0.5/nchan of fs) shifted to the channel centre (chan/nchan - 0.5) * fs: complex taps."""
+    return complex_bandpass(ntaps, chan / nchan - 0.5, 0.5 / nchan)
 
 
 def tone_noise_numpy(dtype_code: int, n: int, seed: int, start: int = 0) -> np.ndarray:
