@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.hpp"
+#include "fir_imma.hpp"
 #include "fft.hpp"
 #include "fir.hpp"
 
@@ -101,6 +102,8 @@ struct b200c_fir {
     HostPipe pipe;
     FirOsPlan os;               // fused overlap-save path (cf32, L = M = 1, long taps)
     bool use_os = false;
+    FirImmaPlan imma;           // int8 tensor-core path (int16 / complex int16, L = M = 1)
+    bool use_imma = false;
 };
 
 struct b200c_fir_bank {
@@ -170,8 +173,25 @@ static int fir_refresh(b200c_fir *h)
             if (rc) return rc;
             h->use_os = h->os.ready;
         }
+        // int16 streams: byte-limb Toeplitz GEMMs on the int8 tensor cores, bit-exact
+        // (B200C_FIR_ALGO=imma forces it below the automatic tap threshold, direct disables it)
+        h->use_imma = false;
+        if (!force_direct) {
+            rc = fir_imma_configure(h->imma, h->dtype, h->taps.data(), h->ntaps, h->taps_kind == B200C_TAPS_COMPLEX, h->M, h->L,
+                                    algo && std::strcmp(algo, "imma") == 0);
+            if (rc) return rc;
+            h->use_imma = h->imma.ready;
+        }
     }
     return B200C_OK;
+}
+
+// one convolution pass over `nblocks` = N/M blocks with whichever kernel the setters selected
+static int fir_dispatch(const b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, size_t nblocks, cudaStream_t s)
+{
+    if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
+    if (h->use_imma) return fir_imma_launch(h->imma, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
+    return fir_launch(h->table, h->ds, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
 }
 
 static void fir_plan_counts(const b200c_fir *h, size_t in_elems, size_t out_capacity, int zero_tail, size_t *consume,
@@ -237,6 +257,7 @@ int b200c_fir_destroy(b200c_fir *h)
         if (h->ds.d_taps) cudaFree(h->ds.d_taps);
         if (h->ds.d_off) cudaFree(h->ds.d_off);
         fir_os_destroy(h->os);
+        fir_imma_destroy(h->imma);
         h->pipe.release();
     }
     delete h;
@@ -283,6 +304,7 @@ const char *b200c_fir_kernel(const b200c_fir *h)
 {
     if (!h) return "";
     if (h->use_os) return fir_os_kernel_name(h->os);
+    if (h->use_imma) return "fir_imma_kernel";
     return h->table.smem_path ? "fir_tile_kernel" : "fir_generic_kernel";
 }
 
@@ -306,8 +328,7 @@ int b200c_fir_run(b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, 
     if (!d_in || !d_out) { set_error("b200c_fir_run: null device buffer"); return B200C_ERR_INVALID; }
     DeviceGuard g(h->device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", h->device); return B200C_ERR_CUDA; }
-    if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, c / h->M, h->di.sm_count, (cudaStream_t)stream);
-    return fir_launch(h->table, h->ds, d_in, in_elems, d_out, c / h->M, h->di.sm_count, (cudaStream_t)stream);
+    return fir_dispatch(h, d_in, in_elems, d_out, c / h->M, (cudaStream_t)stream);
 }
 
 int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_out, size_t out_capacity, int zero_tail,
@@ -344,8 +365,7 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
         const size_t have = in_elems > first ? std::min(want, in_elems - first) : 0;   // beyond: zero tail
         cudaStream_t s = h->pipe.streams[slot];
         if (have) B200C_CUDA_TRY(cudaMemcpyAsync(h->pipe.d_in[slot], src + first * esz, have * esz, cudaMemcpyHostToDevice, s));
-        rc = h->use_os ? fir_os_launch(h->os, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, h->di.sm_count, s)
-                       : fir_launch(h->table, h->ds, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, h->di.sm_count, s);
+        rc = fir_dispatch(h, h->pipe.d_in[slot], have, h->pipe.d_out[slot], nb, s);
         if (rc) return rc;
         B200C_CUDA_TRY(cudaMemcpyAsync(dst + b0 * L * esz, h->pipe.d_out[slot], nb * L * esz, cudaMemcpyDeviceToHost, s));
     }
@@ -461,8 +481,7 @@ int b200c_fir_bank_run(b200c_fir_bank *b, const void *d_in, size_t in_stride, si
         b200c_fir *h = b->ch[i];
         const char *src = static_cast<const char *>(d_in) + i * in_stride * esz;
         char *dst = static_cast<char *>(d_out) + i * out_stride * esz;
-        const int rc = h->use_os ? fir_os_launch(h->os, src, in_elems, dst, c / h->M, h->di.sm_count, (cudaStream_t)stream)
-                                 : fir_launch(h->table, h->ds, src, in_elems, dst, c / h->M, h->di.sm_count, (cudaStream_t)stream);
+        const int rc = fir_dispatch(h, src, in_elems, dst, c / h->M, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return B200C_OK;

@@ -1,0 +1,36 @@
+// Bit-exact int16 / complex-int16 FIR on the int8 tensor cores (fir_imma.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "common.hpp"
+
+namespace b200c {
+
+// The reference accumulates int16 data times Q16 taps in wrapping int32 (QType, filter/FIRFilter.cpp:381)
+// and keeps bits [16, 32) of the sum (fromQ, :300).  Everything is therefore arithmetic mod 2^32,
+// which byte limbs reproduce exactly:  x = xl + 2^8 xh  (xl unsigned, xh signed),
+// tap q = sum_l 2^(8 l) q_l with balanced signed digits q_l in [-128, 127], and
+//   x q  =  sum_{dl, l}  2^(8 (dl + l))  x_dl q_l        (terms with 8 (dl + l) >= 32 vanish).
+// Each limb product is one int8 Toeplitz GEMM accumulated in int32 (wrapping, like the reference).
+struct FirImmaPlan {
+    bool ready = false;
+    int K = 0;          // taps
+    int NB = 0;         // 32-sample k-blocks per output row: ceil((K + 7) / 32)
+    int nlt = 2;        // tap limbs (2: |q| < 2^15 - 128, i.e. |h| < 0.498; 3; 4: any int32)
+    int dc = 1, tc = 1; // data / tap components (1 real, 2 complex)
+    void *d_frag = nullptr;   // [NB][tc][nlt][32] uint2: per-lane B fragments of the tap Toeplitz blocks
+    size_t frag_capacity = 0;
+};
+
+constexpr size_t kFirImmaMinTaps = 12;     // below this the IMAD tile kernel is still HBM-bound
+constexpr size_t kFirImmaMaxTaps = 2048;
+
+// Decides whether the tensor-core path serves (dtype, taps, M, L); leaves p.ready false otherwise.
+int fir_imma_configure(FirImmaPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
+                       bool force);
+void fir_imma_destroy(FirImmaPlan &p);
+int fir_imma_launch(const FirImmaPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                    cudaStream_t stream);
+
+} // namespace b200c

@@ -444,3 +444,78 @@ def test_filter_bank_matches_per_channel_filters(oracle, cuda_device, dt, taps_t
             assert (cons, prod) == (c_ref, p_ref)
             _compare(oracle, code, got[c, :prod], y_ref, f"bank {dt} chan {c} zt={zero_tail}")
             assert not got[c, prod:].any(), "wrote past the channel's produced count"
+
+
+# ---------------------------------------------------------------- int8 tensor-core path ---
+@pytest.mark.parametrize("ntaps", [2, 12, 25, 26, 57, 121, 128, 129, 255, 1000, 2048])
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_imma_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
+    """int16 streams (L = M = 1) take the byte-limb Toeplitz GEMM kernel (fir_imma.cu); it must
+    reproduce the reference's wrapping int32 accumulation and >>16 bit for bit, for ragged
+    lengths, tiles that end mid-row, the burst zero tail and full-scale inputs, and agree with
+    the direct IMAD kernel it replaces."""
+    code = getattr(oracle, dt)
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(ntaps * 7 + code)
+    taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    if cx:
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    for n_new, zero_tail in ((1, False), (127, False), (128, False), (4095, False), (4096, False), (4097, False),
+                             (3 * 4096 + 1001, False), (70001, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, code, ntaps - 1 + n_new, rng, full_scale=True)
+        y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("imma"):
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+            assert f.kernel == "fir_imma_kernel"
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, code, y, y_ref, f"imma K={ntaps} n={n_new} zt={zero_tail}")
+    with _with_algo("direct"):
+        y_d, _, _, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+        assert f.kernel != "fir_imma_kernel"
+    _compare(oracle, code, y_d, y_ref, "direct")
+
+
+@pytest.mark.parametrize("scale,limbs", [(0.4, 2), (0.6, 3), (100.0, 3), (200.0, 4), (30000.0, 4)])
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, scale, limbs):
+    """Q16 taps of any magnitude: 2, 3 or 4 balanced byte digits per tap; the int32 accumulator
+    wraps exactly like the reference's (filter/FIRFilter.cpp:381) however large the taps are."""
+    code = getattr(oracle, dt)
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(int(scale * 10) + code)
+    ntaps = 77
+    taps = rng.uniform(-scale, scale, ntaps)
+    taps[5] = scale * 0.999                                  # make sure the top digit is in use
+    taps[6] = -scale * 0.999
+    if cx:
+        taps = taps + 1j * rng.uniform(-scale, scale, ntaps)
+    x = _rand_input(oracle, code, 9000, rng, full_scale=True)
+    y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x)
+    y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x)
+    assert f.kernel == "fir_imma_kernel"
+    assert (cons, prod) == (c_ref, p_ref)
+    _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
+
+
+@pytest.mark.parametrize("dt", ["CI16", "I16"])
+def test_imma_unaligned_device_pointers(oracle, cuda_device, dt):
+    """A ring-buffer window starts at any element: the kernel's 16-byte loads and 8-byte stores
+    need their guarded fallbacks."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(99)
+    taps = rng.standard_normal(64) * 0.05
+    f = FirFilter(code, "REAL")
+    f.set_taps(taps)
+    assert f.kernel == "fir_imma_kernel"
+    x = _rand_input(oracle, code, 12000, rng, full_scale=True)
+    y_ref, _, _ = oracle.fir(code, False, taps, 1, 1, x)
+    xd = torch.from_numpy(x).cuda()
+    for off in (1, 2, 3):                                    # base pointers shifted by `off` elements
+        shifted = torch.empty(x.shape[0] + off, x.shape[1], dtype=xd.dtype, device="cuda")
+        shifted[off:] = xd
+        out_big = torch.zeros(y_ref.shape[0] + off + 1, x.shape[1], dtype=xd.dtype, device="cuda")
+        y, cons, prod = f.run(shifted[off:], out=out_big[off:])
+        torch.cuda.synchronize()
+        assert np.array_equal(y.cpu().numpy()[:prod], y_ref), off
