@@ -387,7 +387,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     if args.ntaps:   # tap-count sweeps: cf32 stream, `ntaps` complex band-pass taps
-        WORKLOADS[args.workload] = ("complex_float32", f"sweep{args.ntaps}", 1, 1, 28, 16.0)
+        w0 = WORKLOADS[args.workload]   # the named workload's stream type, `ntaps` complex band-pass taps
+        dt0 = w0[0] if w0[0] in ("complex_float32", "complex_int16") else "complex_float32"
+        WORKLOADS[args.workload] = (dt0, f"sweep{args.ntaps}", 1, 1, 28, 16.0 if dt0 == "complex_float32" else 8.0)
     dt_name, taps_name, M, L, log2n, bytes_per_sample = WORKLOADS[args.workload]
     if args.log2_samples:
         log2n = args.log2_samples

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <vector>
 
+#include "bulk.cuh"
 #include "fir_imma.hpp"
 
 namespace b200c {
@@ -80,18 +81,39 @@ __global__ void __launch_bounds__(32 * kImmaWarps, MINB) fir_imma_kernel(const F
     unsigned char *planes = smem_i + (size_t)NB * TC * NLT * 32 * sizeof(uint2);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
 
+    unsigned char *raw = planes + (size_t)NPL * PL;          // landing zone of the bulk prefetch
+    __shared__ __align__(8) unsigned long long bar;
+    constexpr int ESZ = DC * 2;                              // bytes per input sample
+
     for (int i = tid; i < NB * TC * NLT * 32; i += NTH) fragS[i] = a.frag[i];
+    // A tile whose whole PL-sample window lies inside the stream (and a 16-byte aligned base) is
+    // fetched by ONE bulk copy issued before the previous tile's MMA phase; edge tiles and
+    // unaligned streams use guarded loads.
+    const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
+    auto bulk_ok = [&](long long tile) { return al && tile < a.ntiles && tile * kImmaTile + PL <= a.n_in; };
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    bool pending = bulk_ok(blockIdx.x);
+    if (pending && tid == 0)
+        bulk_load(raw, static_cast<const unsigned char *>(a.in) + (size_t)blockIdx.x * kImmaTile * ESZ, (unsigned)(NPL * PL), &bar);
+    unsigned parity = 0;
 
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long o0 = tile * kImmaTile;
         // ---- stage: de-interleave the tile's input window into byte planes
+        if (pending) {
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+        }
         if constexpr (DC == 2) {
             const unsigned *__restrict__ in32 = static_cast<const unsigned *>(a.in);
-            const bool al = (reinterpret_cast<unsigned long long>(in32) & 15) == 0;
             for (int q = tid; q < PL / 4; q += NTH) {
                 const long long s = o0 + 4LL * q;
                 unsigned s0, s1, s2, s3;
-                if (al && s + 4 <= a.n_in) {
+                if (pending) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(raw)[q];
+                    s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
+                } else if (al && s + 4 <= a.n_in) {
                     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in32 + s));
                     s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
                 } else {
@@ -110,11 +132,13 @@ __global__ void __launch_bounds__(32 * kImmaWarps, MINB) fir_imma_kernel(const F
             }
         } else {
             const unsigned short *__restrict__ in16 = static_cast<const unsigned short *>(a.in);
-            const bool al = (reinterpret_cast<unsigned long long>(in16) & 7) == 0;
             for (int q = tid; q < PL / 4; q += NTH) {
                 const long long s = o0 + 4LL * q;
                 unsigned w0, w1;
-                if (al && s + 4 <= a.n_in) {
+                if (pending) {
+                    const uint2 v = reinterpret_cast<const uint2 *>(raw)[q];
+                    w0 = v.x; w1 = v.y;
+                } else if (al && s + 4 <= a.n_in) {
                     const uint2 v = __ldg(reinterpret_cast<const uint2 *>(in16 + s));
                     w0 = v.x; w1 = v.y;
                 } else {
@@ -127,7 +151,11 @@ __global__ void __launch_bounds__(32 * kImmaWarps, MINB) fir_imma_kernel(const F
                 p[PL / 4] = prmt(w0, w1, 0x7531);
             }
         }
-        __syncthreads();
+        __syncthreads();                                     // planes complete, landing zone consumed
+        pending = bulk_ok(tile + gridDim.x);
+        if (pending && tid == 0)
+            bulk_load(raw, static_cast<const unsigned char *>(a.in) + (size_t)(tile + gridDim.x) * kImmaTile * ESZ,
+                      (unsigned)(NPL * PL), &bar);
 
         // ---- R x 128 outputs per warp pass
         for (int u = w; u < UNITS; u += kImmaWarps) {
@@ -304,7 +332,7 @@ void fir_imma_destroy(FirImmaPlan &p)
 template <int DC, int TC, int NLT>
 static int launch_imma(const FirImmaArgs &a, size_t smem, int sm_count, cudaStream_t stream)
 {
-    constexpr int R = 2, MINB = 3;
+    constexpr int R = 2, MINB = NLT == 2 ? 4 : 3;
     auto kern = fir_imma_kernel<DC, TC, NLT, R, MINB>;
     static thread_local bool configured[16] = {false};
     int dev = 0;
@@ -313,7 +341,8 @@ static int launch_imma(const FirImmaArgs &a, size_t smem, int sm_count, cudaStre
         B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[dev] = true;
     }
-    const long long per_sm = std::max<long long>(1, std::min<long long>(MINB, (220 * 1024) / (long long)(smem + 1024)));
+    static const int forced = [] { const char *e = std::getenv("B200C_IMMA_PERSM"); return e ? std::atoi(e) : 0; }();
+    const long long per_sm = std::max<long long>(1, std::min<long long>(forced > 0 ? forced : MINB, (220 * 1024) / (long long)(smem + 1024)));
     const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count * per_sm);
     kern<<<grid, 32 * kImmaWarps, smem, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
@@ -329,7 +358,7 @@ int fir_imma_launch(const FirImmaPlan &p, const void *d_in, size_t in_elems, voi
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out;
     a.ntiles = ((long long)n_out + kImmaTile - 1) / kImmaTile;
     a.K = p.K; a.NB = p.NB; a.PL = kImmaTile + 32 * p.NB;
-    const size_t smem = (size_t)p.NB * p.tc * p.nlt * 32 * sizeof(uint2) + (size_t)p.dc * 2 * a.PL;
+    const size_t smem = (size_t)p.NB * p.tc * p.nlt * 32 * sizeof(uint2) + 2 * ((size_t)p.dc * 2 * a.PL);   // fragments, planes, landing zone
     if (smem > 200 * 1024) { set_error("fir_imma: tap count too large for the tensor-core path"); return B200C_ERR_UNSUPPORTED; }
 #define IMMA_NLT(DC, TC)                                                                 \
     (p.nlt == 2 ? launch_imma<DC, TC, 2>(a, smem, sm_count, stream)                        \

@@ -23,7 +23,7 @@ struct FirImmaPlan {
     size_t frag_capacity = 0;
 };
 
-constexpr size_t kFirImmaMinTaps = 12;     // below this the IMAD tile kernel is still HBM-bound
+constexpr size_t kFirImmaMinTaps = 2;      // measured (tools/sweep_i16.sh): ahead of the IMAD tile kernel from 2 taps up
 constexpr size_t kFirImmaMaxTaps = 2048;
 
 // Decides whether the tensor-core path serves (dtype, taps, M, L); leaves p.ready false otherwise.

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "bulk.cuh"
 #include "fft.hpp"
 #include "os64_core.cuh"
 
@@ -52,36 +53,6 @@ __device__ __forceinline__ void step_twiddle(c2 (&v)[64], const c2 *__restrict__
             if (a) v[r] = cmul_p<CONJ>(v[r], A[a]);
             if (b) v[r] = cmul_p<CONJ>(v[r], B[b]);
         }
-}
-
-// ---- bulk-async (TMA) prefetch of the next block's input into the exchange buffer ----------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// one thread: order the CTA's earlier generic-proxy accesses of `dst` before the async-proxy
-// write, arm the barrier with the byte count and start the copy
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 constexpr int kBulkElems = 4098;   // 4096 + 2: room to start one element early when the block start is not 16-byte aligned
