@@ -47,6 +47,7 @@ struct FirOsPlan {
     bool ready = false;
     bool general = false;     // polyphase / real-data kernel
     bool real = false;        // float32 data: two stream blocks per complex transform
+    bool osp = false;         // general: the multi-warp resampler kernel (fir_osp_kernel) serves it
     int N = 4096;             // transform length in use
     int K = 0;                // L = M = 1 kernels: taps; general: K = ceil(ntaps / L)
     int M = 1, L = 1;

@@ -453,6 +453,88 @@ __global__ void __launch_bounds__(32, MINB) fir_os32g_kernel(const FirOs32GArgs 
     }
 }
 
+// ------------------------------------------- polyphase resampler, one warp per transform ---
+// Same algebra as fir_os32g_kernel for complex float32 streams with 2 <= max(L, M) <= 4, spread
+// over a CTA of NW = max(L, M) warps so that no thread ever holds more than ONE 1024-point
+// sequence (64 data registers instead of 192): warp e < M transforms residue stream e and leaves
+// its spectrum in shared memory, warp p < L forms C_p = sum_e H_{p,e} . B_e from those, inverse
+// transforms it and stages its output slot as a plane [u]; the CTA then stores the L planes
+// interleaved, fully coalesced.  ~110 registers x 96 threads and 42 KB of shared memory per CTA
+// (L = 3, M = 2) keep 15 warps per SM resident where the one-warp kernel had 8.
+// Plane stride (elements) of the staged output slots: a half-warp of the interleaved flush reads
+// 16 consecutive outputs j = u L + p, i.e. ~16/L consecutive u from each of the L planes; the
+// stride mod 16 (8-byte banks) is chosen so that those 16 reads hit 16 different banks.
+__host__ __device__ constexpr int osp_plane_stride(int L) { return kOs32SmemElems + (L == 2 ? 8 : L == 3 ? 11 : 12); }
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) fir_osp_kernel(const FirOs32GArgs a, const int M)
+{
+    extern __shared__ __align__(16) c2 smem_p[];
+    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    const int L = a.L, hop = a.hop;
+    c2 *S = smem_p;                                    // [M][kOs32SmemElems]: exchange tile, then spectrum [k2][t]
+    c2 *P = smem_p + M * kOs32SmemElems;               // [L][pstride]: exchange tile, then output slot [u]
+    const int pstride = osp_plane_stride(L);
+    const long long nblk = (a.nq + hop - 1) / hop;
+    const int dq = (32 * NW) / L, dr = (32 * NW) - dq * L;   // (u, p) step of the flush, no division in the loop
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long Q0 = blk * hop;
+        if (w < M) {
+            c2 *F = S + w * kOs32SmemElems;
+            const long long s0 = a.start0 + Q0 * M + w;   // input element of b_e[0]
+            const bool inner = s0 >= 0 && s0 + 1023LL * M < a.n_in;
+            c2 v[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const long long ia = s0 + (long long)(32 * n1 + t) * M;
+                v[rev32(n1)] = (inner || (ia >= 0 && ia < a.n_in)) ? __ldg(in + ia) : 0ull;
+            }
+            fft1024_fwd<false>(v, F, tw, t);
+            __syncwarp();
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) F[32 * k2 + t] = v[k2];
+        }
+        __syncthreads();                                // spectra complete; the previous block's flush is done
+        if (w < L) {
+            c2 *plane = P + w * pstride;
+            const c2 *__restrict__ Hp = static_cast<const c2 *>(a.H) + (size_t)w * M * 1024 + t;
+            c2 v[32];
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(S[32 * k2 + t], Hp[32 * k2]);
+            for (int e = 1; e < M; e++) {
+                const c2 *Se = S + e * kOs32SmemElems + t;
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) {
+                    float fx, fy, hx, hy;
+                    const c2 b = Se[32 * k2];
+                    upk(b, fx, fy); upk(Hp[e * 1024 + 32 * k2], hx, hy);
+                    v[k2] = fma2(b, pk(hx, hx), fma2(pk(-fy, fx), pk(hy, hy), v[k2]));
+                }
+            }
+            fft1024_inv(v, plane, tw, t);
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) plane[32 * n1 + t] = v[rev32(n1)];
+        }
+        __syncthreads();                                // all L slots staged
+        {
+            const long long left = a.nq - Q0;
+            const int nu = left < hop ? (int)left : hop;
+            const int total = nu * L;
+            c2 *__restrict__ o = static_cast<c2 *>(a.out) + Q0 * L;
+            int u = (int)threadIdx.x / L, p = (int)threadIdx.x - u * L;
+            for (int j = threadIdx.x; j < total; j += 32 * NW) {
+                __stcg(o + j, P[p * pstride + u]);
+                u += dq; p += dr;
+                if (p >= L) { p -= L; u++; }
+            }
+        }
+        // no barrier here: the planes are next written after the next block's first barrier
+    }
+}
+
 // ------------------------------------------------------------------------------- host ---
 // in-place forward DFT (e^{-2 pi i nk/N}), N a power of two, double precision (host, setTaps path)
 static void host_fft(std::vector<std::complex<double>> &x)
@@ -584,7 +666,7 @@ static int configure_general(FirOsPlan &p, bool real_data, const double *taps, s
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
                      bool force)
 {
-    p.ready = false; p.general = false; p.real = false;
+    p.ready = false; p.general = false; p.real = false; p.osp = false;
     if (dtype == B200C_CF32 && M == 1 && L == 1) {
         // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up
         if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
@@ -613,11 +695,15 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
         p.ready = true;
         return B200C_OK;
     }
-    if ((dtype == B200C_CF32 || dtype == B200C_F32) && M <= 2 && L <= kFirOsGenMaxInterp) {
+    // multi-warp resampler kernel: complex float32, 2 <= max(L, M) <= 4 (pure M <= 2 decimators stay on the one-warp kernel)
+    const bool osp = dtype == B200C_CF32 && L <= 4 && M <= 4 && std::max(L, M) >= 2 && !(L == 1 && M <= 2) &&
+                     !(std::getenv("B200C_OSP") && std::atoi(std::getenv("B200C_OSP")) == 0);
+    if ((dtype == B200C_CF32 || dtype == B200C_F32) && (M <= 2 || osp) && L <= kFirOsGenMaxInterp) {
         const size_t per_phase = (ntaps + L - 1) / L;
         const size_t min_taps = (M == 1 && L == 1) ? kFirOsAutoMinTapsReal : kFirOsAutoMinTapsResamp;
         if (!force && per_phase < min_taps) return B200C_OK;
         if (ntaps < 2) return B200C_OK;
+        p.osp = osp;
         return configure_general(p, dtype == B200C_F32, taps, ntaps, complex_taps, M, L);
     }
     return B200C_OK;
@@ -635,7 +721,7 @@ void fir_os_destroy(FirOsPlan &p)
 
 const char *fir_os_kernel_name(const FirOsPlan &p)
 {
-    if (p.general) return "fir_os32g_kernel";
+    if (p.general) return p.osp ? "fir_osp_kernel" : "fir_os32g_kernel";
     return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
 }
 
@@ -659,6 +745,23 @@ static int launch_general(const FirOs32GArgs &a, long long nblk, int sm_count, c
     return B200C_OK;
 }
 
+template <int NW, int MINB>
+static void launch_osp(const FirOs32GArgs &a, int M, size_t smem, long long nblk, int sm_count, cudaStream_t stream)
+{
+    auto kern = fir_osp_kernel<NW, MINB>;
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev < 16 && !configured[dev]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (const char *e = std::getenv("B200C_OSP_CARVE")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
+        configured[dev] = true;
+    }
+    static const int forced = [] { const char *e = std::getenv("B200C_OSP_PERSM"); return e ? std::atoi(e) : 0; }();
+    const long long per_sm = std::max<long long>(1, std::min<long long>(forced > 0 ? forced : MINB, (224 * 1024) / (long long)(smem + 1024)));
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * per_sm * 2);
+    kern<<<grid, 32 * NW, smem, stream>>>(a, M);
+}
+
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
                   cudaStream_t stream, const FirOsBatch *batch)
 {
@@ -669,6 +772,16 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         FirOs32GArgs a;
         a.in = d_in; a.out = d_out; a.H = p.d_H; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.nq = (long long)nq; a.start0 = p.start0; a.L = p.L; a.hop = p.hopq;
+        if (p.osp) {
+            const int nw = std::max(p.L, p.M);
+            const size_t smem = sizeof(c2) * ((size_t)p.M * kOs32SmemElems + (size_t)p.L * osp_plane_stride(p.L));
+            const long long nblk = ((long long)nq + p.hopq - 1) / p.hopq;
+            if (nw == 2) launch_osp<2, 7>(a, p.M, smem, nblk, sm_count, stream);
+            else if (nw == 3) launch_osp<3, 5>(a, p.M, smem, nblk, sm_count, stream);
+            else launch_osp<4, 3>(a, p.M, smem, nblk, sm_count, stream);
+            B200C_CUDA_TRY(cudaGetLastError());
+            return B200C_OK;
+        }
         const long long per = (long long)p.hopq * (p.real ? 2 : 1);
         const long long nblk = ((long long)nq + per - 1) / per;
         // slot staging for a coalesced store pays from L = 2 and fits shared memory up to L = 4

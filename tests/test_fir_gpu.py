@@ -366,7 +366,8 @@ def test_overlap_save_limits_fall_back_to_direct(oracle, cuda_device):
         assert np.array_equal(yi, yi_ref)
 
 
-@pytest.mark.parametrize("M,L", [(1, 1), (2, 1), (1, 2), (1, 3), (2, 2), (2, 3), (2, 5), (1, 16)])
+@pytest.mark.parametrize("M,L", [(1, 1), (2, 1), (1, 2), (1, 3), (2, 2), (2, 3), (2, 5), (1, 16), (1, 4), (3, 1), (3, 2),
+                                 (4, 3), (3, 4), (4, 4), (2, 4)])
 @pytest.mark.parametrize("dt,taps_type", [("CF32", "COMPLEX"), ("CF32", "REAL"), ("F32", "REAL")])
 def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type, M, L):
     """The generalised fused kernel (decimation <= 2, any interpolation, complex or real float32
@@ -375,6 +376,10 @@ def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type
     code = getattr(oracle, dt)
     if (dt, M, L) == ("CF32", 1, 1):
         pytest.skip("covered by test_overlap_save_path_matches_oracle_and_direct")
+    if dt == "F32" and M > 2:
+        pytest.skip("real float32 data: the fused kernel serves decimation <= 2")
+    # complex float32 with 2 <= max(L, M) <= 4 (pure M <= 2 decimators aside): the multi-warp resampler kernel
+    osp = dt == "CF32" and L <= 4 and M <= 4 and max(L, M) >= 2 and not (L == 1 and M <= 2)
     rng = np.random.default_rng(7000 + 97 * M + L + (taps_type == "COMPLEX"))
     for ntaps in (L * 13 + 1, 255):
         taps = rng.standard_normal(ntaps) / np.sqrt(ntaps / L)
@@ -387,7 +392,7 @@ def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type
             y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, zero_tail=zero_tail)
             with _with_algo("fft"):
                 y_os, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
-                assert f.kernel == "fir_os32g_kernel", f.kernel
+                assert f.kernel == ("fir_osp_kernel" if osp else "fir_os32g_kernel"), f.kernel
             assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
             _compare(oracle, code, y_os, y_ref, f"os32g {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
             with _with_algo("direct"):
