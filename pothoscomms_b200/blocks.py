@@ -70,6 +70,14 @@ def lib():
         L.b200c_blk_num_out_labels.argtypes = [vp]
         L.b200c_blk_out_label.argtypes = [vp, sz, cp, sz, ctypes.POINTER(ull), ctypes.POINTER(sz), ctypes.POINTER(i),
                                           ctypes.POINTER(ctypes.c_double)]
+        L.b200c_blk_make_noargs.restype = vp
+        L.b200c_blk_make_noargs.argtypes = [cp, ctypes.POINTER(i)]
+        L.b200c_blk_call_double.argtypes = [vp, cp, ctypes.c_double]
+        L.b200c_blk_get_double.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_double)]
+        L.b200c_blk_get_doubles.argtypes = [vp, cp, vp, sz, ctypes.POINTER(sz)]
+        L.b200c_blk_connect_signal.argtypes = [vp, cp, vp, cp]
+        L.b200c_blk_last_signal.argtypes = [vp, cp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(i), ctypes.POINTER(sz)]
+        L.b200c_blk_has_signal.argtypes = [vp, cp]
         _lib = L
     return _lib
 
@@ -239,6 +247,86 @@ class Block:
         return res
 
 
-def make(path: str, dtype: str, *args, **kw) -> Block:
-    """BlockRegistry::make(path, dtype, ...) -- /comms/fir_filter, /blocks/fir_filter, /comms/fft."""
+_D_STRING = {"setFilterType": "filterType", "setBandType": "bandType", "setWindowType": "windowType"}
+_D_DOUBLE = {"setSampleRate": "sampleRate", "setFrequencyLower": "frequencyLower", "setFrequencyUpper": "frequencyUpper",
+             "setBandwidthTrans": "bandwidthTrans", "setAlpha": "alpha", "setStopDB": "stopDB", "setPassDB": "passDB",
+             "setGain": "gain"}
+_D_SIZE = {"setNumTaps": "numTaps"}
+_D_VECTOR = {"setWindowArgs": "windowArgs", "setFrequencies": None}
+
+
+class HostBlock:
+    """A port-less host block (/comms/fir_designer, /blocks/fir_designer, /comms/window_designer):
+    registered calls, activate() and the "tapsChanged" signal (filter/FIRDesigner.cpp:143-169)."""
+
+    def __init__(self, path: str):
+        status = ctypes.c_int(0)
+        self._h = lib().b200c_blk_make_noargs(path.encode(), ctypes.byref(status))
+        _check(status.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200c_blk_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def has_call(self, name: str) -> bool:
+        return bool(lib().b200c_blk_has_call(self._h, name.encode()))
+
+    def has_signal(self, name: str) -> bool:
+        return bool(lib().b200c_blk_has_signal(self._h, name.encode()))
+
+    def activate(self):
+        _check(lib().b200c_blk_activate(self._h))
+
+    def call(self, name: str, *args):
+        n, L = name.encode(), lib()
+        if name in _D_STRING:
+            return _check(L.b200c_blk_call_string(self._h, n, str(args[0]).encode()))
+        if name in _D_DOUBLE:
+            return _check(L.b200c_blk_call_double(self._h, n, float(args[0])))
+        if name in _D_SIZE:
+            return _check(L.b200c_blk_call_size(self._h, n, int(args[0])))
+        if name in _D_VECTOR:
+            v = np.ascontiguousarray(args[0], dtype=np.float64)
+            return _check(L.b200c_blk_call_taps(self._h, n, v.ctypes.data, v.size, 0))
+        if name in _D_STRING.values():
+            buf = ctypes.create_string_buffer(256)
+            _check(L.b200c_blk_get_string(self._h, n, buf, 256))
+            return buf.value.decode()
+        if name in _D_DOUBLE.values():
+            v = ctypes.c_double(0)
+            _check(L.b200c_blk_get_double(self._h, n, ctypes.byref(v)))
+            return v.value
+        if name in _D_SIZE.values():
+            v = ctypes.c_size_t(0)
+            _check(L.b200c_blk_get_size(self._h, n, ctypes.byref(v)))
+            return v.value
+        if name == "windowArgs":
+            cnt, buf = ctypes.c_size_t(0), np.zeros(64)
+            _check(L.b200c_blk_get_doubles(self._h, n, buf.ctypes.data, buf.size, ctypes.byref(cnt)))
+            return buf[: cnt.value].copy()
+        raise PothosException(f"HostBlock.call({name}): no such registered call in the driver")
+
+    def connect(self, signal: str, dst, slot: str):
+        """Topology::connect(self, signal, dst, slot): every emission calls dst.<slot>(payload)."""
+        _check(lib().b200c_blk_connect_signal(self._h, signal.encode(), dst._h, slot.encode()))
+
+    def last_signal(self, signal: str = "tapsChanged"):
+        """(payload of the last emission or None, number of emissions so far)"""
+        cnt, cx, count = ctypes.c_size_t(0), ctypes.c_int(0), ctypes.c_size_t(0)
+        buf = np.zeros(1 << 16, dtype=np.float64)
+        _check(lib().b200c_blk_last_signal(self._h, signal.encode(), buf.ctypes.data, buf.size, ctypes.byref(cnt), ctypes.byref(cx),
+                                           ctypes.byref(count)))
+        if count.value == 0:
+            return None, 0
+        return (buf[: 2 * cnt.value].view(np.complex128).copy() if cx.value else buf[: cnt.value].copy()), count.value
+
+
+def make(path: str, dtype: str | None = None, *args, **kw):
+    """BlockRegistry::make(path, ...) -- /comms/fir_filter, /blocks/fir_filter, /comms/fft (dtype, ...);
+    /comms/fir_designer, /blocks/fir_designer, /comms/window_designer (no arguments)."""
+    if dtype is None:
+        return HostBlock(path)
     return Block(path, dtype, *args, **kw)

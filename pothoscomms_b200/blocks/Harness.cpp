@@ -20,6 +20,7 @@ class Harness {
 public:
     Harness(Block *blk, int device, size_t inBytes, size_t outBytes) : _blk(blk), _device(device)
     {
+        if (blk->numInputs() == 0 && blk->numOutputs() == 0) return;   // host-only block (designers): calls and signals only
         _inMgr = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(blk->getInputBufferManager("0", b200c_blocks::kHbmDomain));
         _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
         if (!_inMgr || !_outMgr) throw Exception("Harness()", "block does not provide device buffer managers");
@@ -226,6 +227,54 @@ int b200c_blk_get_taps(void *h, double *buf, size_t cap, size_t *n, int *is_comp
         }
     });
 }
+// port-less host blocks: /comms/fir_designer, /comms/window_designer
+void *b200c_blk_make_noargs(const char *path, int *status)
+{
+    Harness *h = nullptr;
+    const int rc = guarded([&] { h = new Harness(Pothos::BlockRegistry::make(path), 0, 0, 0); });
+    if (status) *status = rc;
+    return h;
+}
+int b200c_blk_call_double(void *h, const char *name, double v) { return guarded([&] { static_cast<Harness *>(h)->block()->call(name, v); }); }
+int b200c_blk_get_double(void *h, const char *name, double *out)
+{
+    return guarded([&] { *out = static_cast<Harness *>(h)->block()->call(name).convert<double>(); });
+}
+int b200c_blk_get_doubles(void *h, const char *name, double *buf, size_t cap, size_t *n)
+{
+    return guarded([&] {
+        const auto v = static_cast<Harness *>(h)->block()->call(name).convert<std::vector<double>>();
+        *n = v.size();
+        for (size_t i = 0; i < v.size() && i < cap; i++) buf[i] = v[i];
+    });
+}
+// Topology::connect(src, signal, dst, slot)
+int b200c_blk_connect_signal(void *src, const char *signal, void *dst, const char *slot)
+{
+    return guarded([&] { static_cast<Harness *>(src)->block()->connectSignal(signal, static_cast<Harness *>(dst)->block(), slot); });
+}
+// last emitted payload of a taps-carrying signal; *count = emissions so far (0: never emitted, nothing written)
+int b200c_blk_last_signal(void *h, const char *signal, double *buf, size_t cap, size_t *n, int *is_complex, size_t *count)
+{
+    return guarded([&] {
+        Pothos::Block *b = static_cast<Harness *>(h)->block();
+        *count = b->signalCount(signal); *n = 0; *is_complex = 0;
+        const auto *args = b->lastSignal(signal);
+        if (!args || args->empty()) return;
+        const Object &o = args->at(0);
+        if (o.type() == typeid(std::vector<double>)) {
+            const auto &v = o.extract<std::vector<double>>();
+            *n = v.size();
+            for (size_t i = 0; i < v.size() && i < cap; i++) buf[i] = v[i];
+        } else {
+            const auto &v = o.extract<std::vector<std::complex<double>>>();
+            *n = v.size(); *is_complex = 1;
+            for (size_t i = 0; i < v.size() && 2 * i + 1 < cap; i++) { buf[2 * i] = v[i].real(); buf[2 * i + 1] = v[i].imag(); }
+        }
+    });
+}
+int b200c_blk_has_signal(void *h, const char *name) { return static_cast<Harness *>(h)->block()->hasSignal(name) ? 1 : 0; }
+
 int b200c_blk_has_call(void *h, const char *name) { return static_cast<Harness *>(h)->block()->hasCall(name) ? 1 : 0; }
 
 int b200c_blk_activate(void *h) { return guarded([&] { static_cast<Harness *>(h)->activate(); }); }

@@ -278,7 +278,31 @@ public:
     template <typename... A> Object call(const std::string &name, const A &...a) { return call(name, std::vector<Object>{Object(a)...}); }
     bool hasCall(const std::string &name) const { return _calls.count(name) != 0; }
 
+    // Signals: the shim's stand-in for Topology::connect(src, "signal", dst, "slot") -- an emitted
+    // signal calls the connected registered calls synchronously and is remembered for inspection.
+    void connectSignal(const std::string &signal, Block *dst, const std::string &slot)
+    {
+        if (!_signals.count(signal)) throw Exception("Block::connectSignal(" + signal + ")", "no such registered signal");
+        _signalConns[signal].push_back(std::make_pair(dst, slot));
+    }
+    bool hasSignal(const std::string &name) const { return _signals.count(name) != 0; }
+    const std::vector<Object> *lastSignal(const std::string &name) const
+    {
+        auto it = _lastSignal.find(name);
+        return it == _lastSignal.end() ? nullptr : &it->second;
+    }
+    size_t signalCount(const std::string &name) const { auto it = _signalCounts.find(name); return it == _signalCounts.end() ? 0 : it->second; }
+
 protected:
+    void registerSignal(const std::string &name) { _signals[name] = true; }
+    template <typename... A> void emitSignal(const std::string &name, const A &...a)
+    {
+        if (!_signals.count(name)) throw Exception("Block::emitSignal(" + name + ")", "no such registered signal");
+        const std::vector<Object> args{Object(a)...};
+        _lastSignal[name] = args;
+        _signalCounts[name]++;
+        for (auto &c : _signalConns[name]) c.first->call(c.second, args);
+    }
     void setupInput(size_t index, const DType &dt)
     {
         if (_inputs.size() <= index) _inputs.resize(index + 1);
@@ -315,6 +339,10 @@ private:
     std::vector<InputPort> _inputs;
     std::vector<OutputPort> _outputs;
     std::map<std::string, std::function<Object(const std::vector<Object> &)>> _calls;
+    std::map<std::string, bool> _signals;
+    std::map<std::string, std::vector<std::pair<Block *, std::string>>> _signalConns;
+    std::map<std::string, std::vector<Object>> _lastSignal;
+    std::map<std::string, size_t> _signalCounts;
     bool _active = false;
 };
 

@@ -273,3 +273,53 @@ def test_fir_then_fft_chain_stays_consistent(oracle, cuda_device):
     fft.activate()
     Y = fft.push_through(y)
     assert np.array_equal(Y, oracle.fft(oracle.CI16, 4096, False, y_ref))
+
+
+def _designer_matrix():
+    from _designer_cases import reference_matrix
+    return list(reference_matrix())
+
+
+@pytest.mark.parametrize("filter_type,band_type", _designer_matrix())
+def test_fir_designer(oracle, cuda_device, filter_type, band_type):
+    """filter/TestFIRDesigner.cpp:126-275, the whole topology: /comms/fir_designer emits
+    "tapsChanged" into the filter's setTaps slot (:176) while the filter waits for taps, the
+    START-labelled impulse burst goes FIR -> FFT in HBM, and the power spectrum must meet the
+    reference's pass/stop mask for every (filter type, band type) pair it tests (:255-273)."""
+    from pothoscomms_b200 import blocks
+    from _designer_cases import configure, mask_points
+    fft_size, rate, lower, upper = 1024, 1e6, 1.5e5, 3.0e5
+    dtype = "complex_float64"                            # :141
+    code = oracle.DTYPE_CODES[dtype]
+    impulse = np.zeros(fft_size, dtype=complex)
+    impulse[-1] = fft_size                               # :145-146
+    fir = blocks.make("/comms/fir_filter", dtype, "COMPLEX")
+    fir.call("setDecimation", 1)
+    fir.call("setInterpolation", 1)
+    fir.call("setWaitTaps", True)
+    fir.call("setFrameStartId", "START")
+    designer = blocks.make("/comms/fir_designer")
+    configure(designer, filter_type, band_type, rate, lower, upper, 101)
+    designer.connect("tapsChanged", fir, "setTaps")      # topology.connect(designer, "tapsChanged", filter, "setTaps")
+    fir.activate()
+    fir.post_label("START", 0, data=fft_size)
+    fir.feed(oracle.to_raw(impulse, code))
+    fir.run()
+    assert fir.collect().shape[0] == 0                   # still waiting for taps
+    designer.activate()                                  # emits the taps -> filter.setTaps (real taps convert to complex)
+    taps, count = designer.last_signal()
+    assert count == 1
+    assert np.allclose(fir.call("getTaps"), taps.astype(complex))
+    fir.run()
+    y = fir.collect()
+    assert y.shape[0] == fft_size                        # :183
+    fft = blocks.make("/comms/fft", dtype, fft_size, False)
+    fft.activate()
+    fft.feed(y)
+    fft.run()
+    bins = fft.collect()
+    spec = bins[:, 0] + 1j * bins[:, 1]
+    power = 20 * np.log10(np.maximum(np.abs(np.fft.fftshift(spec)) / fft_size, 1e-15))
+    for is_pass, freq in mask_points(band_type, rate, lower, upper):
+        level = power[int(fft_size * ((freq + rate / 2) / rate))]
+        assert (level > -30.0) if is_pass else (level < -80.0), (filter_type, band_type, freq, level)
