@@ -104,6 +104,8 @@ struct b200c_fir {
     bool use_os = false;
     FirImmaPlan imma;           // int8 tensor-core path (int16 / complex int16, L = M = 1)
     bool use_imma = false;
+    FirUmmaPlan umma;           // tcgen05 / TMEM variant of the same path
+    bool use_umma = false;
 };
 
 struct b200c_fir_bank {
@@ -182,6 +184,13 @@ static int fir_refresh(b200c_fir *h)
             if (rc) return rc;
             h->use_imma = h->imma.ready;
         }
+        // tcgen05.mma (accumulators in tensor memory) where it applies; B200C_FIR_ALGO=imma keeps mma.sync
+        h->use_umma = false;
+        if (h->use_imma && !(algo && std::strcmp(algo, "imma") == 0)) {
+            rc = fir_umma_configure(h->umma, h->imma, h->taps.data(), algo && std::strcmp(algo, "umma") == 0);
+            if (rc) return rc;
+            h->use_umma = h->umma.ready;
+        }
     }
     return B200C_OK;
 }
@@ -190,6 +199,7 @@ static int fir_refresh(b200c_fir *h)
 static int fir_dispatch(const b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, size_t nblocks, cudaStream_t s)
 {
     if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
+    if (h->use_umma) return fir_umma_launch(h->umma, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
     if (h->use_imma) return fir_imma_launch(h->imma, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
     return fir_launch(h->table, h->ds, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
 }
@@ -258,6 +268,7 @@ int b200c_fir_destroy(b200c_fir *h)
         if (h->ds.d_off) cudaFree(h->ds.d_off);
         fir_os_destroy(h->os);
         fir_imma_destroy(h->imma);
+        fir_umma_destroy(h->umma);
         h->pipe.release();
     }
     delete h;
@@ -304,6 +315,7 @@ const char *b200c_fir_kernel(const b200c_fir *h)
 {
     if (!h) return "";
     if (h->use_os) return fir_os_kernel_name(h->os);
+    if (h->use_umma) return "fir_umma_kernel";
     if (h->use_imma) return "fir_imma_kernel";
     return h->table.smem_path ? "fir_tile_kernel" : "fir_generic_kernel";
 }

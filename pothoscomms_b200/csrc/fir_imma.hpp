@@ -33,4 +33,17 @@ void fir_imma_destroy(FirImmaPlan &p);
 int fir_imma_launch(const FirImmaPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
                     cudaStream_t stream);
 
+// tcgen05 / TMEM variant of the same algebra (fir_umma.cu): 2-limb taps, built on a ready FirImmaPlan.
+struct FirUmmaPlan {
+    bool ready = false;
+    int K = 0, NB = 0;  // NB: 32-sample k-blocks per 16-output row: ceil((K + 15) / 32)
+    int nlt = 2, dc = 1, tc = 1;
+    void *d_btile = nullptr;  // [NB][N x 32 B] canonical K-major B tiles, N = 16 tc nlt
+    size_t capacity = 0;
+};
+int fir_umma_configure(FirUmmaPlan &p, const FirImmaPlan &base, const double *taps, bool force);
+void fir_umma_destroy(FirUmmaPlan &p);
+int fir_umma_launch(const FirUmmaPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                    cudaStream_t stream);
+
 } // namespace b200c

@@ -524,3 +524,28 @@ def test_imma_unaligned_device_pointers(oracle, cuda_device, dt):
         y, cons, prod = f.run(shifted[off:], out=out_big[off:])
         torch.cuda.synchronize()
         assert np.array_equal(y.cpu().numpy()[:prod], y_ref), off
+
+
+# ------------------------------------------------------- tcgen05 / tensor-memory path ---
+@pytest.mark.parametrize("ntaps", [2, 17, 18, 49, 50, 113, 128, 129, 255, 700])
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_umma_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
+    """The tcgen05.mma kind::i8 kernel (fir_umma.cu: Hankel A operand aliased onto the byte planes
+    by the shared-memory descriptor, accumulators in tensor memory) against the oracle: ragged
+    lengths, tiles ending mid-row, the zero tail, full-scale inputs; tap counts either side of
+    the k-block boundaries (K + 15 = 32 j)."""
+    code = getattr(oracle, dt)
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(ntaps * 11 + code)
+    taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    if cx:
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    for n_new, zero_tail in ((1, False), (15, False), (16, False), (2047, False), (2048, False), (2049, False),
+                             (5 * 2048 + 1001, False), (300001, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, code, ntaps - 1 + n_new, rng, full_scale=True)
+        y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("umma"):
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+            assert f.kernel == "fir_umma_kernel"
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, code, y, y_ref, f"umma K={ntaps} n={n_new} zt={zero_tail}")
