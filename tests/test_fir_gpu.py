@@ -497,13 +497,14 @@ def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, s
     x = _rand_input(oracle, code, 9000, rng, full_scale=True)
     y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x)
     y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x)
-    assert f.kernel == "fir_imma_kernel"
+    assert f.kernel == ("fir_umma_kernel" if limbs == 2 else "fir_imma_kernel")   # tcgen05 path: 2-limb taps
     assert (cons, prod) == (c_ref, p_ref)
     _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
 
 
+@pytest.mark.parametrize("kernel", ["fir_imma_kernel", "fir_umma_kernel"])
 @pytest.mark.parametrize("dt", ["CI16", "I16"])
-def test_imma_unaligned_device_pointers(oracle, cuda_device, dt):
+def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     """A ring-buffer window starts at any element: the kernel's 16-byte loads and 8-byte stores
     need their guarded fallbacks."""
     import torch
@@ -511,9 +512,10 @@ def test_imma_unaligned_device_pointers(oracle, cuda_device, dt):
     code = getattr(oracle, dt)
     rng = np.random.default_rng(99)
     taps = rng.standard_normal(64) * 0.05
-    f = FirFilter(code, "REAL")
-    f.set_taps(taps)
-    assert f.kernel == "fir_imma_kernel"
+    with _with_algo("imma" if kernel == "fir_imma_kernel" else "umma"):
+        f = FirFilter(code, "REAL")
+        f.set_taps(taps)
+    assert f.kernel == kernel
     x = _rand_input(oracle, code, 12000, rng, full_scale=True)
     y_ref, _, _ = oracle.fir(code, False, taps, 1, 1, x)
     xd = torch.from_numpy(x).cuda()
