@@ -497,6 +497,11 @@ def main():
                 "kernel": fir.kernel, "kernel_ms": kernel_ms,
                 "note": ("fused overlap-save (fast convolution): one pass over HBM, 16 B per sample whatever the tap count"
                          if fir.kernel.startswith("fir_os") else
+                         "bit-exact int16 as byte-limb Toeplitz GEMMs on the int8 tensor cores (tcgen05 kind::i8, accumulators "
+                         "in tensor memory); the HBM figure is reported next to it, the kernel is shared-memory/tensor bound"
+                         if fir.kernel.startswith("fir_umma") else
+                         "bit-exact int16 as byte-limb Toeplitz GEMMs on mma.sync m16n8k32 (int8 tensor cores)"
+                         if fir.kernel.startswith("fir_imma") else
                          "direct form: FMA/IMAD-issue bound once taps x MACs/tap exceed ~11 flop/B; see DESIGN.md")}
     flops = {"c1": 512, "c1_real": 256, "headline": 2048, "c3": 510, "c5": 8192}.get(args.workload)
     if flops and not fir.kernel.startswith("fir_os"):

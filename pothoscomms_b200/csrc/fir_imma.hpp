@@ -46,4 +46,17 @@ void fir_umma_destroy(FirUmmaPlan &p);
 int fir_umma_launch(const FirUmmaPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
                     cudaStream_t stream);
 
+// Second tcgen05 formulation (fir_umma32.cu): 32-byte-swizzled planes, 32 outputs per row, N = 128.
+struct FirUmma32Plan {
+    bool ready = false;
+    int K = 0, NB = 0;  // NB: k-blocks per 32-output row: ceil((K + 31) / 32)
+    int dc = 1;
+    void *d_bmat = nullptr;   // [dc][NB][N x 32 B] B tiles, N = 32 x dc x 2
+    size_t capacity = 0;
+};
+int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force);
+void fir_umma32_destroy(FirUmma32Plan &p);
+int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                      cudaStream_t stream);
+
 } // namespace b200c

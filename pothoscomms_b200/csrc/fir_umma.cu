@@ -25,6 +25,7 @@
 
 #include "bulk.cuh"
 #include "fir_imma.hpp"
+#include "umma.cuh"
 
 namespace b200c {
 
@@ -40,60 +41,6 @@ struct FirUmmaArgs {
 
 constexpr int kUmmaTile = 2048;    // outputs per CTA tile: 128 rows x 16
 constexpr int kUmmaThreads = 128;
-
-__device__ __forceinline__ unsigned prmt_u(unsigned a, unsigned b, unsigned sel)
-{
-    unsigned r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
-
-// K-major, no swizzle: start address, LBO (between the 16-byte k chunks), SBO (between 8-row groups)
-__device__ __forceinline__ unsigned long long umma_smem_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes)
-{
-    unsigned long long d = 0;
-    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
-    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= 1ull << 46;                                         // descriptor version: Blackwell
-    return d;                                                // base offset 0, layout type 0 = no swizzle
-}
-
-// kind::i8 instruction descriptor: D = int32, A = u8 or s8, B = s8, both K-major, M = 128
-__host__ __device__ constexpr unsigned umma_idesc_i8(bool a_signed, int N)
-{
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, bool accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((unsigned)accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld4(unsigned taddr, unsigned (&v)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-                 : "r"(taddr)
-                 : "memory");
-}
-
-// 16 consecutive columns of this thread's TMEM lane: one wide load instead of four narrow ones
-// (tcgen05.ld cost is per instruction: 4-column loads made the epilogue the longest phase)
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr)
-                 : "memory");
-}
 
 // Epilogue loads for CH consecutive outputs n0.. of one row: columns are output-major
 // (col = n NQ + q), so the CH x NQ accumulators of one data plane are adjacent.
@@ -301,18 +248,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) fir_umma_kernel(const FirUmma
 // complex x complex case, so exactly one CTA may live on an SM.
 constexpr int kWsEpiWarps = 8, kWsStageWarps = 4, kWsMaxRing = 8;
 constexpr int kWsThreads = 32 * (kWsEpiWarps + kWsStageWarps + 2);
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void timed_wait(unsigned long long *bar, unsigned parity, long long &acc)
-{
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
 
 template <int DC, int TC, int NLT>
 __global__ void __launch_bounds__(kWsThreads, 1) fir_umma_ws_kernel(const FirUmmaArgs a)

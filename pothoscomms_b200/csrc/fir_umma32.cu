@@ -1,0 +1,423 @@
+// int16 / complex-int16 FIR on tcgen05, second formulation: 32 outputs per GEMM row.
+//
+// fir_umma.cu aliases the Hankel data matrix onto the byte planes with 16-byte row pitch (no
+// swizzle), which ties N to 16 outputs x 4 tap planes = 64 columns per MMA; measured there
+// (DESIGN.md): every M = 128 MMA costs ~67 cycles of A-operand fetch whatever N is.  This kernel
+// doubles the work per fetched A tile:
+//  * the planes are stored with the 32-byte swizzle (byte offset o lives at o ^ ((o >> 7 & 1) << 4)),
+//    so a K-major SWIZZLE_32B descriptor sees rows of 32-byte pitch: row m is the window
+//    plane[32 m + 32 b + (0..31)], advanced by ONE ROW per k-block b.  That start address is not
+//    aligned to the 256-byte swizzle pattern; tools/probe_umma_swizzle.cu shows the tensor core
+//    swizzles on the absolute shared-memory address (base_offset 0), which makes it exact.
+//  * 32 outputs per row, and the re and im data planes ACCUMULATE INTO THE SAME tensor-memory
+//    region through different B matrices: B_re = [h_re digits -> y_re columns | h_im digits ->
+//    y_im columns], B_im = [-h_im digits | h_re digits].  Only the data limb (lo / hi byte, weights
+//    2^0 and 2^8) needs separate regions: N = 32 outputs x 2 components x 2 tap digits = 128 columns,
+//    2 regions, 8 accumulators per output instead of 16; two stages fill the 512 TMEM columns.
+//  * NB = ceil((K + 31) / 32) k-blocks; a tile is 128 rows x 32 = 4096 outputs.
+// Warp-specialised like fir_umma_ws_kernel: bulk-copy issuer -> stagers -> MMA issuer -> epilogue.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "fir_imma.hpp"
+#include "umma.cuh"
+
+namespace b200c {
+
+struct FirUmma32Args {
+    const void *in;
+    void *out;
+    const void *bmat;    // [DC][NB][N x 32 B] canonical K-major no-swizzle B tiles
+    long long n_in, n_out, ntiles;
+    int K, NB, PL, PLa;  // PL: bytes per plane in use = 4096 + 32 NB; PLa: allocated (multiple of 256)
+    int R;               // depth of the bulk-copy landing ring
+    long long *dbg;
+};
+
+constexpr int kU32Tile = 4096;
+constexpr int kU32EpiWarps = 8, kU32StageWarps = 8, kU32MaxRing = 8;
+constexpr int kU32Batch = 5;      // stager loads in flight per thread: their latency under the MMA's operand traffic is long
+constexpr int kU32Threads = 32 * (kU32EpiWarps + kU32StageWarps + 2);
+
+template <int DC>
+__global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmma32Args a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_v[];
+    constexpr int NQ = DC * 2;                     // (output component, tap digit) per output
+    constexpr int N = 32 * NQ;                     // MMA N = columns of one data-limb region
+    constexpr int COLS = 2 * N;                    // lo and hi regions
+    constexpr int ALLOC = 2 * COLS;                // two stages: 512 (complex) / 256 (real) columns
+    constexpr int NPL = DC * 2, ESZ = DC * 2;
+    constexpr int CH = 16 / NQ;                    // outputs per 16-column epilogue chunk
+    const int NB = a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
+    unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024)
+    unsigned char *planes = bmat + (size_t)DC * NB * N * 32;         // [2][NPL][PLa], 256-byte aligned, swizzled
+    unsigned char *raw = planes + 2 * (size_t)NPL * PLa;             // [R][PL * ESZ]
+    __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
+    __shared__ unsigned tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < DC * NB * N * 2; i += kU32Threads)
+        reinterpret_cast<uint4 *>(bmat)[i] = __ldg(static_cast<const uint4 *>(a.bmat) + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) {
+        for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * kU32StageWarps); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&planes_full[s], 32 * kU32StageWarps); mbar_init(&planes_empty[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * kU32EpiWarps);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ALLOC) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_base_s;
+    const long long first = blockIdx.x, step = gridDim.x;
+    const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;
+    const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
+    auto bulk_ok = [&](long long tile) { return al && tile * kU32Tile + PL <= a.n_in; };
+    long long w0 = 0, w1 = 0, t_conv = 0, t_fence = 0;
+    const long long t_begin = clock64();
+
+    if (warp == kU32EpiWarps + kU32StageWarps + 1) {
+        // ================================================================ bulk-copy issuer
+        if (lane == 0)
+            for (int i = 0, r = 0, ph = 0; i < ntl; i++) {
+                const long long tile = first + (long long)i * step;
+                timed_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
+                if (bulk_ok(tile))
+                    bulk_load(raw + (size_t)r * PL * ESZ, static_cast<const unsigned char *>(a.in) + (size_t)tile * kU32Tile * ESZ,
+                              (unsigned)(PL * ESZ), &raw_full[r]);
+                else
+                    mbar_arrive(&raw_full[r]);
+                if (++r == R) { r = 0; ph ^= 1; }
+            }
+    } else if (warp == kU32EpiWarps + kU32StageWarps) {
+        // ====================================================================== MMA issuer
+        if (lane == 0) {
+            // One thread feeds the tensor core: everything per MMA beyond two 64-bit adds is hoisted out
+            // of the loop (with descriptors rebuilt per MMA the issue rate, not the MMA, set the pace).
+            unsigned long long a_base[2][NPL], b_base[DC];
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int p = 0; p < NPL; p++)      // A: plane p of stage s, rows of 32-byte pitch (SWIZZLE_32B)
+                    a_base[s][p] = umma_smem_desc(smem_u32(planes + ((size_t)s * NPL + p) * PLa), 16, 256, 6);
+#pragma unroll
+            for (int dc = 0; dc < DC; dc++) b_base[dc] = umma_smem_desc(smem_u32(bmat + (size_t)dc * NB * N * 32), 128, 256, 0);
+            constexpr unsigned long long kAStep = 32 >> 4, kBStep = (N * 32) >> 4;   // start-address field is in 16-byte units
+            // the tile loop is unrolled over the two stages so that every index below is a compile-time
+            // constant (dynamically indexed descriptor arrays would live in local memory)
+            auto issue_tile = [&](auto stage_c, const unsigned ph) {
+                constexpr int S = decltype(stage_c)::value;
+                timed_wait(&planes_full[S], ph, w0);
+                timed_wait(&acc_empty[S], ph ^ 1, w1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int dl = 0; dl < 2; dl++) {                       // data limb: its own accumulator region
+                    const unsigned d = tmem_base + (unsigned)(S * COLS + dl * N);
+                    constexpr unsigned idesc_lo = umma_idesc_i8(false, N), idesc_hi = umma_idesc_i8(true, N);
+#pragma unroll
+                    for (int dc = 0; dc < DC; dc++) {
+                        // k-block b: the A window starts one 32-byte row later (Hankel), B is the next tile
+                        unsigned long long ad = a_base[S][2 * dc + dl], bd = b_base[dc];
+                        if (dc == 0) { umma_i8_first(d, ad, bd, dl ? idesc_hi : idesc_lo); ad += kAStep; bd += kBStep; }
+#pragma unroll 4
+                        for (int b = dc == 0 ? 1 : 0; b < NB; b++) {
+                            umma_i8_acc(d, ad, bd, dl ? idesc_hi : idesc_lo);
+                            ad += kAStep; bd += kBStep;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[S])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[S])) : "memory");
+            };
+            for (int i = 0; i < ntl; i += 2) {
+                const unsigned ph = (unsigned)(i >> 1) & 1;
+                issue_tile(std::integral_constant<int, 0>{}, ph);
+                if (i + 1 < ntl) issue_tile(std::integral_constant<int, 1>{}, ph);
+            }
+        }
+    } else if (warp >= kU32EpiWarps) {
+        // ========================================================================= stagers
+        // raw (re, im) int16 samples -> byte planes, stored with the 32-byte swizzle: the 16-byte chunk
+        // c of a plane lives at chunk c ^ (c >> 3 & 1)
+        const int st = tid - 32 * kU32EpiWarps;
+        constexpr int NST = 32 * kU32StageWarps;
+        const int nq = PL / 4;
+        for (int i = 0, r = 0, rph = 0; i < ntl; i++) {
+            const int s = i & 1;
+            const unsigned ph = (unsigned)(i >> 1) & 1;
+            const long long tile = first + (long long)i * step, o0 = tile * kU32Tile;
+            const bool landed = bulk_ok(tile);
+            timed_wait(&raw_full[r], (unsigned)rph, w0);
+            timed_wait(&planes_empty[s], ph ^ 1, w1);
+            unsigned *pl = reinterpret_cast<unsigned *>(planes + (size_t)s * NPL * PLa);
+            const unsigned char *rw = raw + (size_t)r * PL * ESZ;
+            const long long t_c0 = clock64();
+            if constexpr (DC == 2) {
+                const unsigned *__restrict__ in32 = static_cast<const unsigned *>(a.in);
+                for (int q0 = st; q0 < nq; q0 += kU32Batch * NST) {
+                    uint4 v[kU32Batch];
+#pragma unroll
+                    for (int u = 0; u < kU32Batch; u++) {
+                        const int q = q0 + u * NST;
+                        if (q >= nq) { v[u] = make_uint4(0, 0, 0, 0); continue; }
+                        if (landed) {
+                            v[u] = reinterpret_cast<const uint4 *>(rw)[q];
+                        } else {
+                            const long long sm = o0 + 4LL * q;
+                            v[u].x = sm < a.n_in ? __ldg(in32 + sm) : 0u;
+                            v[u].y = sm + 1 < a.n_in ? __ldg(in32 + sm + 1) : 0u;
+                            v[u].z = sm + 2 < a.n_in ? __ldg(in32 + sm + 2) : 0u;
+                            v[u].w = sm + 3 < a.n_in ? __ldg(in32 + sm + 3) : 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU32Batch; u++) {
+                        const int q = q0 + u * NST;
+                        if (q >= nq) continue;
+                        const unsigned t01 = prmt_u(v[u].x, v[u].y, 0x5140), t23 = prmt_u(v[u].z, v[u].w, 0x5140);
+                        const unsigned u01 = prmt_u(v[u].x, v[u].y, 0x7362), u23 = prmt_u(v[u].z, v[u].w, 0x7362);
+                        const int c = q >> 2;
+                        unsigned *p = pl + (((c ^ ((c >> 3) & 1)) << 2) | (q & 3));
+                        p[0] = prmt_u(t01, t23, 0x5410);
+                        p[PLa / 4] = prmt_u(t01, t23, 0x7632);
+                        p[2 * (PLa / 4)] = prmt_u(u01, u23, 0x5410);
+                        p[3 * (PLa / 4)] = prmt_u(u01, u23, 0x7632);
+                    }
+                }
+            } else {
+                const unsigned short *__restrict__ in16 = static_cast<const unsigned short *>(a.in);
+                for (int q0 = st; q0 < nq; q0 += kU32Batch * NST) {
+                    uint2 v[kU32Batch];
+#pragma unroll
+                    for (int u = 0; u < kU32Batch; u++) {
+                        const int q = q0 + u * NST;
+                        if (q >= nq) { v[u] = make_uint2(0, 0); continue; }
+                        if (landed) {
+                            v[u] = reinterpret_cast<const uint2 *>(rw)[q];
+                        } else {
+                            const long long sm = o0 + 4LL * q;
+                            const unsigned x0 = sm < a.n_in ? __ldg(in16 + sm) : 0u, x1 = sm + 1 < a.n_in ? __ldg(in16 + sm + 1) : 0u;
+                            const unsigned x2 = sm + 2 < a.n_in ? __ldg(in16 + sm + 2) : 0u, x3 = sm + 3 < a.n_in ? __ldg(in16 + sm + 3) : 0u;
+                            v[u] = make_uint2(x0 | (x1 << 16), x2 | (x3 << 16));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU32Batch; u++) {
+                        const int q = q0 + u * NST;
+                        if (q >= nq) continue;
+                        const int c = q >> 2;
+                        unsigned *p = pl + (((c ^ ((c >> 3) & 1)) << 2) | (q & 3));
+                        p[0] = prmt_u(v[u].x, v[u].y, 0x6420);
+                        p[PLa / 4] = prmt_u(v[u].x, v[u].y, 0x7531);
+                    }
+                }
+            }
+            const long long t_c1 = clock64();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&planes_full[s]);
+            mbar_arrive(&raw_empty[r]);
+            const long long t_c2 = clock64();
+            t_conv += t_c1 - t_c0; t_fence += t_c2 - t_c1;
+            if (++r == R) { r = 0; rph ^= 1; }
+        }
+    } else {
+        // ======================================================================== epilogue
+        // thread = (row m = TMEM lane, half of the row's 32 outputs); per output and component:
+        //   y = lo_d0 + ((lo_d1 + hi_d0) << 8) + (hi_d1 << 16)  mod 2^32, bits [16, 32) kept (fromQ)
+        const int m = 32 * (warp & 3) + lane, half = warp >> 2;
+        const unsigned lane_addr = tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
+        for (int i = 0; i < ntl; i++) {
+            const int s = i & 1;
+            const unsigned ph = (unsigned)(i >> 1) & 1;
+            const long long tile = first + (long long)i * step, orow = tile * kU32Tile + 32LL * m + 16 * half;
+            timed_wait(&acc_full[s], ph, w0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < 16 / CH; c++) {
+                const int n0 = 16 * half + CH * c;
+                unsigned lo[16], hi[16];
+                tmem_ld16(lane_addr + (unsigned)(s * COLS + n0 * NQ), lo);
+                tmem_ld16(lane_addr + (unsigned)(s * COLS + N + n0 * NQ), hi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == 16 / CH - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[s]);
+                }
+                unsigned res[CH];
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    unsigned y[DC];
+#pragma unroll
+                    for (int cls = 0; cls < DC; cls++)
+                        y[cls] = lo[k * NQ + 2 * cls] + ((lo[k * NQ + 2 * cls + 1] + hi[k * NQ + 2 * cls]) << 8) + (hi[k * NQ + 2 * cls + 1] << 16);
+                    if constexpr (DC == 2) res[k] = prmt_u(y[0], y[DC - 1], 0x7632);
+                    else res[k] = y[0] >> 16;
+                }
+                const long long o = orow + CH * c;
+                if constexpr (DC == 2) {
+                    unsigned *out32 = static_cast<unsigned *>(a.out);
+                    if (o + CH <= a.n_out && (reinterpret_cast<unsigned long long>(out32) & 15) == 0) {
+                        __stcg(reinterpret_cast<uint4 *>(out32 + o), make_uint4(res[0], res[1], res[2], res[3]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CH; k++)
+                            if (o + k < a.n_out) out32[o + k] = res[k];
+                    }
+                } else {
+                    unsigned short *out16 = static_cast<unsigned short *>(a.out);
+                    if (o + CH <= a.n_out && (reinterpret_cast<unsigned long long>(out16) & 15) == 0) {
+                        __stcg(reinterpret_cast<uint4 *>(out16 + o), make_uint4(res[0] | (res[1] << 16), res[2] | (res[3] << 16),
+                                                                               res[4 % CH] | (res[5 % CH] << 16), res[6 % CH] | (res[7 % CH] << 16)));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CH; k++)
+                            if (o + k < a.n_out) out16[o + k] = (unsigned short)res[k];
+                    }
+                }
+            }
+        }
+    }
+    if (a.dbg && lane == 0) {
+        long long *d = a.dbg + (size_t)blockIdx.x * 8;
+        if (warp == 0) { d[0] = clock64() - t_begin; d[1] = ntl; d[7] = w0; }
+        if (warp == kU32EpiWarps) { d[5] = w0; d[6] = w1; a.dbg[(size_t)gridDim.x * 8 + 2 * blockIdx.x] = t_conv; a.dbg[(size_t)gridDim.x * 8 + 2 * blockIdx.x + 1] = t_fence; }
+        if (warp == kU32EpiWarps + kU32StageWarps) { d[3] = w0; d[4] = w1; }
+        if (warp == kU32EpiWarps + kU32StageWarps + 1) d[2] = w0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ALLOC) : "memory");
+}
+
+// ------------------------------------------------------------------------------- host ---
+// balanced byte digits (d0, d1) of q = d0 + 256 d1, both in [-128, 127]; false if q does not fit
+static bool two_digits(long long q, int8_t &d0, int8_t &d1)
+{
+    const long long lo = ((q + 128) & 255) - 128, hi = (q - lo) >> 8;
+    if (hi < -128 || hi > 127) return false;
+    d0 = (int8_t)lo; d1 = (int8_t)hi;
+    return true;
+}
+
+static size_t u32_fixed_smem(int dc, int NB, int PLa) { return (size_t)dc * NB * (32 * dc * 2) * 32 + 2 * ((size_t)dc * 2 * PLa) + 1024; }
+
+int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force)
+{
+    p.ready = false;
+    const bool enabled = [] { const char *e = std::getenv("B200C_UMMA32"); return !e || std::atoi(e) != 0; }();   // B200C_UMMA32=0: stay on fir_umma_kernel
+    if (!base.ready || !(enabled || force) || base.nlt != 2) return B200C_OK;
+    const int K = base.K, dc = base.dc, tc = base.tc, NQ = dc * 2, N = 32 * NQ;
+    const int NB = (K + 31 + 31) / 32;
+    const int PL = kU32Tile + 32 * NB, PLa = (PL + 255) / 256 * 256;
+    // B tiles, two plane stages and at least a 3-deep landing ring must fit
+    if (u32_fixed_smem(dc, NB, PLa) + 3 * (size_t)PL * dc * 2 > 200 * 1024) return B200C_OK;
+    std::vector<uint8_t> bm((size_t)dc * NB * N * 32, 0);
+    for (int d = 0; d < K; d++)
+        for (int c = 0; c < tc; c++) {
+            const long long q = (long long)(int32_t)(long long)std::ldexp(taps[(size_t)d * tc + c], 16);
+            int8_t pos[2], neg[2];
+            if (!two_digits(q, pos[0], pos[1]) || !two_digits(-q, neg[0], neg[1])) return B200C_OK;   // needs 3 digits: other kernels
+            // contributions (data component dcx, output component cls, sign) of tap component c:
+            //   complex x complex: h_re: (re,yr,+) (im,yi,+);  h_im: (re,yi,+) (im,yr,-)
+            //   complex x real:    h_re: (re,yr,+) (im,yi,+);  real x real: (0,0,+)
+            struct Use { int dcx, cls; bool negate; };
+            Use uses[2];
+            int nuse = 0;
+            if (dc == 1) { uses[nuse++] = {0, 0, false}; }
+            else if (c == 0) { uses[nuse++] = {0, 0, false}; uses[nuse++] = {1, 1, false}; }
+            else { uses[nuse++] = {0, 1, false}; uses[nuse++] = {1, 0, true}; }
+            for (int u = 0; u < nuse; u++)
+                for (int n = 0; n < 32; n++) {
+                    const int j = n + K - 1 - d;                         // window position of tap d for output n
+                    const int b = j / 32, jj = j % 32;
+                    for (int l = 0; l < 2; l++) {
+                        const int col = n * NQ + uses[u].cls * 2 + l;
+                        // canonical K-major no-swizzle: [col / 8][k chunk][col % 8][16 bytes]
+                        const size_t at = (size_t)(uses[u].dcx * NB + b) * N * 32 + (size_t)(col / 8) * 256 + (size_t)(jj / 16) * 128 +
+                                          (size_t)(col % 8) * 16 + (jj % 16);
+                        bm[at] = (uint8_t)(uses[u].negate ? neg[l] : pos[l]);
+                    }
+                }
+        }
+    if (bm.size() > p.capacity) {
+        if (p.d_bmat) cudaFree(p.d_bmat);
+        p.d_bmat = nullptr; p.capacity = 0;
+        B200C_CUDA_TRY(cudaMalloc(&p.d_bmat, bm.size()));
+        p.capacity = bm.size();
+    }
+    B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+    p.K = K; p.NB = NB; p.dc = dc;
+    p.ready = true;
+    return B200C_OK;
+}
+
+void fir_umma32_destroy(FirUmma32Plan &p)
+{
+    if (p.d_bmat) cudaFree(p.d_bmat);
+    p.d_bmat = nullptr; p.capacity = 0; p.ready = false;
+}
+
+template <int DC>
+static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
+{
+    auto kern = fir_umma32_kernel<DC>;
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    B200C_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+        B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured[dev] = true;
+    }
+    static const int ring = [] { const char *e = std::getenv("B200C_UMMA_RING"); return e ? std::atoi(e) : kU32MaxRing; }();
+    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa), one = (size_t)a.PL * DC * 2;
+    a.R = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, std::min(ring, kU32MaxRing)), (216 * 1024 - fixed) / one));
+    // one CTA per SM: its two accumulator stages take all (complex) or half (real) of tensor memory
+    const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);
+    const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
+    static const bool dbg = std::getenv("B200C_UMMA_DBG") != nullptr;
+    if (dbg) {
+        B200C_CUDA_TRY(cudaMalloc(&a.dbg, (size_t)grid * 10 * sizeof(long long)));
+        B200C_CUDA_TRY(cudaMemset(a.dbg, 0, (size_t)grid * 10 * sizeof(long long)));
+    }
+    kern<<<grid, kU32Threads, smem, stream>>>(a);
+    B200C_CUDA_TRY(cudaGetLastError());
+    if (dbg) {
+        std::vector<long long> h((size_t)grid * 10);
+        B200C_CUDA_TRY(cudaStreamSynchronize(stream));
+        B200C_CUDA_TRY(cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.dbg);
+        double s8[8] = {0};
+        for (int g = 0; g < grid; g++) for (int k = 0; k < 8; k++) s8[k] += (double)h[(size_t)g * 8 + k] / grid;
+        double tc = 0, tf = 0;
+        for (int g = 0; g < grid; g++) { tc += (double)h[(size_t)grid * 8 + 2 * g] / grid; tf += (double)h[(size_t)grid * 8 + 2 * g + 1] / grid; }
+        std::fprintf(stderr, "umma32: stager convert %.0f fence+arrive %.0f cycles/tile\n", tc / s8[1], tf / s8[1]);
+        std::fprintf(stderr, "umma32: cycles/tile %.0f | issuer wait raw_empty %.0f | mma wait planes_full %.0f acc_empty %.0f | stager wait raw_full %.0f planes_empty %.0f | epilogue wait acc_full %.0f (tiles/CTA %.1f, R %d, smem %zu)\n",
+                     s8[0] / s8[1], s8[2] / s8[1], s8[3] / s8[1], s8[4] / s8[1], s8[5] / s8[1], s8[6] / s8[1], s8[7] / s8[1], s8[1], a.R, smem);
+    }
+    return B200C_OK;
+}
+
+int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
+                      cudaStream_t stream)
+{
+    if (n_out == 0) return B200C_OK;
+    FirUmma32Args a;
+    a.in = d_in; a.out = d_out; a.bmat = p.d_bmat;
+    a.n_in = (long long)in_elems; a.n_out = (long long)n_out;
+    a.ntiles = ((long long)n_out + kU32Tile - 1) / kU32Tile;
+    a.K = p.K; a.NB = p.NB; a.PL = kU32Tile + 32 * p.NB; a.PLa = (a.PL + 255) / 256 * 256; a.R = 2; a.dbg = nullptr;
+    return p.dc == 1 ? launch_u32<1>(a, sm_count, stream) : launch_u32<2>(a, sm_count, stream);
+}
+
+} // namespace b200c

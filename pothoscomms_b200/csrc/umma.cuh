@@ -1,0 +1,103 @@
+// tcgen05 (5th-generation tensor core) building blocks shared by the int16 FIR kernels:
+// shared-memory matrix descriptors, the kind::i8 instruction descriptor, MMA issue, TMEM loads.
+// Field layouts follow CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+// Addressing facts these kernels rely on were measured with tools/probe_umma_swizzle.cu
+// (profiles/r01d_probe_umma_swizzle.txt): with base_offset = 0 the tensor core applies the
+// swizzle XOR to the ABSOLUTE shared-memory address, for any 16-byte aligned start address.
+#pragma once
+#include "bulk.cuh"
+
+namespace b200c {
+
+__device__ __forceinline__ unsigned prmt_u(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// K-major operand: start address, LBO (no swizzle: between the 16-byte k chunks), SBO (between 8-row
+// groups), layout type (0: no swizzle, 6: 32-byte, 4: 64-byte, 2: 128-byte swizzle)
+__device__ __forceinline__ unsigned long long umma_smem_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes, unsigned layout = 0)
+{
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;                                         // descriptor version: Blackwell
+    d |= (unsigned long long)(layout & 7) << 61;
+    return d;                                                // base offset 0
+}
+
+// kind::i8 instruction descriptor: D = int32, A = u8 or s8, B = s8, both K-major, M = 128
+__host__ __device__ constexpr unsigned umma_idesc_i8(bool a_signed, int N)
+{
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((unsigned)accumulate)
+        : "memory");
+}
+
+// the same with the accumulate flag fixed at compile time: D = A.B (first) / D += A.B (acc)
+__device__ __forceinline__ void umma_i8_first(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_acc(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, unsigned (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// 16 consecutive columns of this thread's TMEM lane: one wide load instead of four narrow ones
+// (tcgen05.ld cost is per instruction: 4-column loads made the epilogue the longest phase)
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void timed_wait(unsigned long long *bar, unsigned parity, long long &acc)
+{
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+
+
+} // namespace b200c

@@ -497,12 +497,12 @@ def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, s
     x = _rand_input(oracle, code, 9000, rng, full_scale=True)
     y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x)
     y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x)
-    assert f.kernel == ("fir_umma_kernel" if limbs == 2 else "fir_imma_kernel")   # tcgen05 path: 2-limb taps
+    assert f.kernel == ("fir_umma32_kernel" if limbs == 2 else "fir_imma_kernel")   # tcgen05 path: 2-limb taps
     assert (cons, prod) == (c_ref, p_ref)
     _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
 
 
-@pytest.mark.parametrize("kernel", ["fir_imma_kernel", "fir_umma_kernel"])
+@pytest.mark.parametrize("kernel", ["fir_imma_kernel", "fir_umma_kernel", "fir_umma32_kernel"])
 @pytest.mark.parametrize("dt", ["CI16", "I16"])
 def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     """A ring-buffer window starts at any element: the kernel's 16-byte loads and 8-byte stores
@@ -512,7 +512,7 @@ def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     code = getattr(oracle, dt)
     rng = np.random.default_rng(99)
     taps = rng.standard_normal(64) * 0.05
-    with _with_algo("imma" if kernel == "fir_imma_kernel" else "umma"):
+    with _with_algo({"fir_imma_kernel": "imma", "fir_umma_kernel": "umma", "fir_umma32_kernel": "umma32"}[kernel]):
         f = FirFilter(code, "REAL")
         f.set_taps(taps)
     assert f.kernel == kernel
@@ -551,3 +551,27 @@ def test_umma_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
             assert f.kernel == "fir_umma_kernel"
         assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
         _compare(oracle, code, y, y_ref, f"umma K={ntaps} n={n_new} zt={zero_tail}")
+
+
+@pytest.mark.parametrize("ntaps", [2, 33, 34, 65, 66, 128, 129, 255])
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_umma32_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
+    """The second tcgen05 formulation (fir_umma32.cu): 32-byte-swizzled byte planes read through a
+    SWIZZLE_32B descriptor advanced one row per k-block, re/im planes accumulating into shared
+    tensor-memory regions through signed tap-digit matrices.  Tap counts either side of the k-block
+    boundaries (K + 31 = 32 j), tiles of 4096 outputs ending mid-row, zero tail, full-scale input."""
+    code = getattr(oracle, dt)
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(ntaps * 13 + code)
+    taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    if cx:
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    for n_new, zero_tail in ((1, False), (31, False), (32, False), (4095, False), (4096, False), (4097, False),
+                             (5 * 4096 + 1001, False), (700001, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, code, ntaps - 1 + n_new, rng, full_scale=True)
+        y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("umma32"):
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+            assert f.kernel == "fir_umma32_kernel"
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, code, y, y_ref, f"umma32 K={ntaps} n={n_new} zt={zero_tail}")
