@@ -177,6 +177,31 @@ struct FirOs32Args {
     int K;
 };
 
+#ifndef B200C_OS32_PARTIAL_TW
+#define B200C_OS32_PARTIAL_TW 0   // measured: no gain on B200 (headline 269 vs 272 Gsamples/s), kept for reference
+#endif
+constexpr bool kOs32PartialTwiddles = B200C_OS32_PARTIAL_TW != 0;
+
+// v[slot(k)] *= W1024^(k t) (CONJ: conjugate) for k = 1..31 from TEN loaded twiddles instead of 31:
+// k = 4a + b, W^(kt) = W^(4a t) W^(b t).  The 21 extra complex multiplies cost FMA issue slots, the 21
+// saved loads were a fifth of the kernel's L1/shared data-pipe traffic, which is the busier pipe
+// (profiles/r01c_prof_os32_headline.txt).  One more rounding per twiddled element (~1e-7 relative).
+template <bool CONJ, bool SLOT_REV>
+__device__ __forceinline__ void twiddle32(c2 (&v)[32], const c2 *__restrict__ tw, const int t)
+{
+    c2 A[8], B[4];
+#pragma unroll
+    for (int a = 1; a < 8; a++) A[a] = tw[(4 * a) * 32 + t];
+#pragma unroll
+    for (int b = 1; b < 4; b++) B[b] = tw[b * 32 + t];
+#pragma unroll
+    for (int k = 1; k < 32; k++) {
+        const int a = k >> 2, b = k & 3, r = SLOT_REV ? rev32(k) : k;
+        if (a) v[r] = cmul_p<CONJ>(v[r], A[a]);
+        if (b) v[r] = cmul_p<CONJ>(v[r], B[b]);
+    }
+}
+
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
 {
@@ -232,8 +257,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
             }
         }
         dft32_dit<false>(v);
+        if constexpr (kOs32PartialTwiddles) twiddle32<false, false>(v, tw, t);
+        else {
 #pragma unroll
-        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+            for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+        }
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
@@ -244,8 +272,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
 #pragma unroll
         for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(v[k2], hf[32 * k2 + t]);
         dft32_dif<true>(v);
+        if constexpr (kOs32PartialTwiddles) twiddle32<true, true>(v, tw, t);
+        else {
 #pragma unroll
-        for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+            for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+        }
         __syncwarp();
 #pragma unroll
         for (int n2 = 0; n2 < 32; n2++) F[t * kOs32Stride + n2] = v[rev32(n2)];
