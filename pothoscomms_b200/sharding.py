@@ -33,12 +33,14 @@ def exchange_halo(buf, K: int, rank: int, world: int):
     import torch.distributed as dist
     if world == 1 or K <= 1:
         return
+    import torch
     ops = []
     n = buf.shape[0]
+    # the halo travels as raw bytes: NCCL has no int16 (the complex-int16 streams of config C2)
     if rank + 1 < world:
-        ops.append(dist.P2POp(dist.isend, buf[n - (K - 1):], rank + 1))
+        ops.append(dist.P2POp(dist.isend, buf[n - (K - 1):].view(torch.uint8), rank + 1))
     if rank > 0:
-        ops.append(dist.P2POp(dist.irecv, buf[: K - 1], rank - 1))
+        ops.append(dist.P2POp(dist.irecv, buf[: K - 1].view(torch.uint8), rank - 1))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
