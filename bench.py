@@ -412,13 +412,28 @@ def main():
 
     from pothoscomms_b200 import sharding
 
-    def halo_exchange():
-        sharding.exchange_halo(buf, K, rank, world)
+    # Optional at N > 1 (B200C_BENCH_OVERLAP=1): start the halo P2P first, run the launch over
+    # everything that does not read the halo (blocks q >= q0) while it is in flight, then a second,
+    # tiny launch for the q0 halo-dependent blocks.  Measured on 2 GPUs it does not pay (headline 513
+    # vs 522 Gsamples/s: the persistent FIR grid and the NCCL kernel contend for SMs), so the default
+    # stays exchange-then-one-launch.
+    q0, in0, out0 = sharding.split_at_halo(K, M, L, align=16)
+    overlap = world > 1 and n_seg // M > 4 * q0 and bool(os.environ.get("B200C_BENCH_OVERLAP"))
+    launches_per_step = 2 if overlap else 1
+
+    def fir_pass():
+        if not overlap:
+            sharding.exchange_halo(buf, K, rank, world)
+            _, cons, prod = fir.run(buf, out=out, out_capacity=out_cap)
+            return cons, prod
+        works = sharding.start_halo_exchange(buf, K, rank, world)
+        _, c1, p1 = fir.run(buf[in0:], out=out[out0:], out_capacity=out_cap - out0)
+        sharding.finish_halo_exchange(works)
+        _, c0, p0 = fir.run(buf[: in0 + K - 1], out=out[:out0], out_capacity=out0)
+        return c0 + c1, p0 + p1
 
     def step():
-        halo_exchange()
-        _, cons, prod = fir.run(buf, out=out, out_capacity=out_cap)
-        return cons, prod
+        return fir_pass()
 
     for _ in range(args.warmup):
         cons, prod = step()
@@ -434,10 +449,15 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
     for i in range(args.steps):
-        halo_exchange()
-        kev[i][0].record()
-        fir.run(buf, out=out, out_capacity=out_cap)
-        kev[i][1].record()
+        if overlap:
+            kev[i][0].record()
+            fir_pass()
+            kev[i][1].record()
+        else:
+            sharding.exchange_halo(buf, K, rank, world)
+            kev[i][0].record()
+            fir.run(buf, out=out, out_capacity=out_cap)
+            kev[i][1].record()
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -521,7 +541,7 @@ def main():
         "config": {"workload": f"{args.workload}: /comms/fir_filter {dt_name} {len(taps)} {tt} taps decim={M} interp={L}, "
                                f"2^{log2n} samples per GPU tone+noise, one stream split in contiguous segments with K-1 halo",
                    "samples_per_gpu": n_seg, "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per pass)"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:

@@ -26,6 +26,39 @@ def channel_range(num_channels: int, world: int, rank: int):
     return num_channels * rank // world, num_channels * (rank + 1) // world
 
 
+def start_halo_exchange(buf, K: int, rank: int, world: int):
+    """Asynchronous form of `exchange_halo`: starts the grouped P2P and returns its work handles;
+    `finish_halo_exchange` makes the current stream wait for them.  Between the two calls the caller
+    may launch everything that does not read buf[:K-1] (see `split_at_halo`)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or K <= 1:
+        return []
+    ops = []
+    n = buf.shape[0]
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, buf[n - (K - 1):].view(torch.uint8), rank + 1))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, buf[: K - 1].view(torch.uint8), rank - 1))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def finish_halo_exchange(works):
+    for w in works:
+        w.wait()
+
+
+def split_at_halo(K: int, decim: int, interp: int, align: int = 1):
+    """Blocks q < q0 of a segment's output read the neighbour's halo, blocks q >= q0 read only the
+    segment itself (its own first samples serve as their history): q0 = ceil((K-1) / M), rounded up
+    to a multiple of `align`.  Returns
+    (q0, first buffer element of the halo-free call, first output element of the halo-free call);
+    the head call takes buf[: q0*M + K-1] and writes out[: q0*L]."""
+    q0 = -(-(K - 1) // decim)
+    q0 = -(-q0 // align) * align      # align = 16 keeps both sub-buffers 16-byte aligned for any element size
+    return q0, q0 * decim, q0 * interp
+
+
 def exchange_halo(buf, K: int, rank: int, world: int):
     """`buf` is [K-1 halo | segment] on every rank.  Sends this rank's last K-1 samples to
     rank+1 and receives rank-1's into buf[:K-1]; rank 0 keeps its own halo (the stream's true

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, code, tcx, taps, M, L, x_full, K, q):
+def _worker(rank, world, port, code, tcx, taps, M, L, x_full, K, q, overlapped=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -37,17 +37,28 @@ def _worker(rank, world, port, code, tcx, taps, M, L, x_full, K, q):
         buf[K - 1:] = torch.from_numpy(x_full[K - 1 + start: K - 1 + stop])
         if rank == 0:
             buf[: K - 1] = torch.from_numpy(x_full[: K - 1])
-        sharding.exchange_halo(buf, K, rank, world)
-        y, cons, prod = oracle.fir(code, tcx, taps, M, L, buf.numpy())
+        if overlapped:
+            # what bench.py does at N > 1: start the P2P, compute everything that does not read the
+            # halo while it is in flight, then the q0 halo-dependent blocks
+            q0, in0, out0 = sharding.split_at_halo(K, M, L)
+            works = sharding.start_halo_exchange(buf, K, rank, world)
+            y1, c1, p1 = oracle.fir(code, tcx, taps, M, L, buf.numpy()[in0:])
+            sharding.finish_halo_exchange(works)
+            y0, c0, p0 = oracle.fir(code, tcx, taps, M, L, buf.numpy()[: in0 + K - 1])
+            assert p0 == out0
+            y, cons = np.concatenate([y0, y1]), c0 + c1
+        else:
+            sharding.exchange_halo(buf, K, rank, world)
+            y, cons, prod = oracle.fir(code, tcx, taps, M, L, buf.numpy())
         assert cons == stop - start
         q.put((rank, y))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world,overlapped", [(2, False), (3, False), (2, True)])
 @pytest.mark.parametrize("case", ["cf32_resampler", "ci16_fir"])
-def test_segments_with_halo_reproduce_single_stream(oracle, world, case):
+def test_segments_with_halo_reproduce_single_stream(oracle, world, overlapped, case):
     import torch.multiprocessing as mp
     rng = np.random.default_rng(5)
     if case == "cf32_resampler":
@@ -63,7 +74,7 @@ def test_segments_with_halo_reproduce_single_stream(oracle, world, case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, code, tcx, taps, M, L, x, K, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, code, tcx, taps, M, L, x, K, q, overlapped)) for r in range(world)]
     for p in procs:
         p.start()
     parts = dict(q.get(timeout=120) for _ in range(world))
