@@ -43,7 +43,7 @@ def is_complex(dtype_code: int) -> bool:
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
     lib = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "qformat.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "math_oracle.c", "qformat.h", "Makefile")]
     stale = force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
     ref = os.path.join(_HERE, "_ref", "libkissref.so")
     if stale or (not os.path.exists(ref) and os.path.exists("/root/reference/fft/kiss_fft.c")):
@@ -67,6 +67,9 @@ def lib():
         _lib.oracle_fir_phase_taps.argtypes = [i, i, vp, sz, sz, vp, vp]
         _lib.oracle_fft.argtypes = [i, sz, i, vp, vp, sz]
         _lib.oracle_fft_plan.argtypes = [i, i, vp, vp]
+        _lib.oracle_scale.argtypes = [i, ctypes.c_double, vp, vp, sz]
+        _lib.oracle_rotate.argtypes = [i, ctypes.c_double, vp, vp, sz]
+        _lib.oracle_probe.argtypes = [i, i, vp, sz, vp]
     return _lib
 
 
@@ -182,3 +185,34 @@ def fft_plan(nbins: int, fixed: bool):
     rem = (ctypes.c_int * 64)()
     n = lib().oracle_fft_plan(nbins, int(fixed), ctypes.addressof(radix), ctypes.addressof(rem))
     return list(radix[:n]), list(rem[:n])
+
+
+def scale(dtype_code: int, factor: float, x_raw: np.ndarray) -> np.ndarray:
+    """/comms/scale (math/Scale.cpp:15-23): out = fromQ(floatToQ(factor) * Q(in)), any shape of raw scalars."""
+    x = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code))
+    out = np.empty_like(x)
+    rc = lib().oracle_scale(dtype_code, ctypes.c_double(factor), x.ctypes.data, out.ctypes.data, x.size)
+    assert rc == 0
+    return out
+
+
+def rotate(dtype_code: int, phase: float, x_raw: np.ndarray) -> np.ndarray:
+    """/comms/rotate (math/Rotate.cpp:15-23): out = fromQ(floatToQ(polar(1, phase)) * Q(in)), raw [n, 2]."""
+    x = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code)).reshape(-1, 2)
+    out = np.empty_like(x)
+    rc = lib().oracle_rotate(dtype_code, ctypes.c_double(phase), x.ctypes.data, out.ctypes.data, x.shape[0])
+    assert rc == 0
+    return out
+
+
+PROBE_MODES = {"VALUE": 0, "RMS": 1, "MEAN": 2}
+
+
+def probe(dtype_code: int, mode: str, x_raw: np.ndarray) -> complex:
+    """/comms/signal_probe (utility/SignalProbe.cpp:140-160) over the whole of x_raw ([n, ncomp])."""
+    nc = 2 if is_complex(dtype_code) else 1
+    x = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code)).reshape(-1, nc)
+    v = (ctypes.c_double * 2)()
+    rc = lib().oracle_probe(dtype_code, PROBE_MODES[mode], x.ctypes.data, x.shape[0], ctypes.addressof(v))
+    assert rc == 0
+    return complex(v[0], v[1])
