@@ -52,6 +52,20 @@ int b200c_abi_version(void);
 int b200c_device_count(int *count);
 size_t b200c_dtype_size(int dtype);
 
+/* ------------------------------------------- HBM-resident neighbours --- */
+/* /comms/scale: arrayScale() with setFactor()'s floatToQ, math/Scale.cpp:15-23,41-45; every row
+ * of scaleFactory (:147-153).  `elems` elements of `dtype` (a complex element is one element;
+ * a vector dimension multiplies elems).  d_in == d_out is allowed. */
+int b200c_scale(int dtype, double factor, const void *d_in, void *d_out, size_t elems, int device, void *stream);
+/* /comms/rotate: arrayRotate() with setPhase()'s floatToQ(polar(1, phase)), math/Rotate.cpp:15-23,
+ * 71-75; complex types only (rotateFactory :145-157), else B200C_ERR_UNSUPPORTED. */
+int b200c_rotate(int dtype, double phase, const void *d_in, void *d_out, size_t elems, int device, void *stream);
+/* /comms/signal_probe work(), utility/SignalProbe.cpp:140-160 over one window of `elems` elements:
+ * mode 0 VALUE (last element), 1 RMS, 2 MEAN; value[0] = re, value[1] = im (0 for real types and
+ * RMS).  Synchronous: the result is on the host when the call returns. */
+enum b200c_probe_mode { B200C_PROBE_VALUE = 0, B200C_PROBE_RMS = 1, B200C_PROBE_MEAN = 2 };
+int b200c_probe(int dtype, int mode, const void *d_in, size_t elems, double *value, int device, void *stream);
+
 /* ------------------------------------------------------------------ /comms/fir_filter --- */
 typedef struct b200c_fir b200c_fir;
 

@@ -31,6 +31,9 @@ SYMBOLS = {
     "b200c_abi_version": (_i, []),
     "b200c_device_count": (_i, [_pi]),
     "b200c_dtype_size": (_sz, [_i]),
+    "b200c_scale": (_i, [_i, ctypes.c_double, _vp, _vp, _sz, _i, _vp]),
+    "b200c_rotate": (_i, [_i, ctypes.c_double, _vp, _vp, _sz, _i, _vp]),
+    "b200c_probe": (_i, [_i, _i, _vp, _sz, ctypes.POINTER(ctypes.c_double), _i, _vp]),
     "b200c_fir_create": (_i, [_pvp, _i, _i, _i]),
     "b200c_fir_destroy": (_i, [_vp]),
     "b200c_fir_set_taps": (_i, [_vp, _vp, _sz]),

@@ -246,3 +246,48 @@ class DeviceRing:
             self._h = ctypes.c_void_p()
 
     __del__ = close
+
+
+# ------------------------------------------------------- HBM-resident neighbours ---
+def _raw_cuda(x, code):
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch_scalar(code)
+    return x.numel() // ncomp(code)
+
+
+def scale(dtype, factor: float, d_in, out=None, stream=None):
+    """/comms/scale on a CUDA tensor of raw scalars ([n, ncomp]); returns the output tensor."""
+    import torch
+    code = dtype_code(dtype)
+    n = _raw_cuda(d_in, code)
+    if out is None:
+        out = torch.empty_like(d_in)
+    _abi.check(_abi.lib().b200c_scale(code, float(factor), ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(out.data_ptr()), n,
+                                      d_in.device.index or 0, _stream_ptr(stream, d_in.device)))
+    return out
+
+
+def rotate(dtype, phase: float, d_in, out=None, stream=None):
+    """/comms/rotate on a CUDA tensor [n, 2] of a complex type."""
+    import torch
+    code = dtype_code(dtype)
+    if not code & 1:
+        raise _abi.InvalidArgumentError(_abi.ERR_UNSUPPORTED, "rotateFactory(): unsupported type")
+    n = _raw_cuda(d_in, code)
+    if out is None:
+        out = torch.empty_like(d_in)
+    _abi.check(_abi.lib().b200c_rotate(code, float(phase), ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(out.data_ptr()), n,
+                                       d_in.device.index or 0, _stream_ptr(stream, d_in.device)))
+    return out
+
+
+PROBE_MODES = {"VALUE": 0, "RMS": 1, "MEAN": 2}
+
+
+def probe(dtype, mode: str, d_in, stream=None) -> complex:
+    """/comms/signal_probe over the whole tensor (one window); synchronous."""
+    code = dtype_code(dtype)
+    n = _raw_cuda(d_in, code)
+    v = (ctypes.c_double * 2)()
+    _abi.check(_abi.lib().b200c_probe(code, PROBE_MODES[mode], ctypes.c_void_p(d_in.data_ptr()), n, v, d_in.device.index or 0,
+                                      _stream_ptr(stream, d_in.device)))
+    return complex(v[0], v[1])
