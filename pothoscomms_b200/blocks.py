@@ -70,6 +70,10 @@ def lib():
         L.b200c_blk_num_out_labels.argtypes = [vp]
         L.b200c_blk_out_label.argtypes = [vp, sz, cp, sz, ctypes.POINTER(ull), ctypes.POINTER(sz), ctypes.POINTER(i),
                                           ctypes.POINTER(ctypes.c_double)]
+        L.b200c_blk_make_dtype.restype = vp
+        L.b200c_blk_make_dtype.argtypes = [cp, cp, sz, sz, ctypes.POINTER(i)]
+        L.b200c_blk_get_complex.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_double)]
+        L.b200c_blk_last_signal_value.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(sz)]
         L.b200c_blk_make_noargs.restype = vp
         L.b200c_blk_make_noargs.argtypes = [cp, ctypes.POINTER(i)]
         L.b200c_blk_call_double.argtypes = [vp, cp, ctypes.c_double]
@@ -95,12 +99,14 @@ def registry_has(path: str) -> bool:
     return bool(lib().b200c_blk_registry_has(path.encode()))
 
 
-_SIZE_SETTERS = {"setDecimation", "setInterpolation"}
+_SIZE_SETTERS = {"setDecimation", "setInterpolation", "setWindow"}
 _BOOL_SETTERS = {"setWaitTaps", "setInverse"}
-_STRING_SETTERS = {"setFrameStartId", "setFrameEndId"}
-_SIZE_GETTERS = {"getDecimation", "getInterpolation", "getNumBins"}
+_STRING_SETTERS = {"setFrameStartId", "setFrameEndId", "setLabelId", "setMode"}
+_DOUBLE_SETTERS = {"setFactor", "setPhase", "setRate"}
+_SIZE_GETTERS = {"getDecimation", "getInterpolation", "getNumBins", "getWindow"}
 _BOOL_GETTERS = {"getWaitTaps", "getInverse"}
-_STRING_GETTERS = {"getFrameStartId", "getFrameEndId"}
+_STRING_GETTERS = {"getFrameStartId", "getFrameEndId", "getLabelId", "getMode"}
+_DOUBLE_GETTERS = {"getFactor", "getPhase", "getRate"}
 
 
 class Block:
@@ -110,7 +116,9 @@ class Block:
         self.dtype = dtype_code(dtype) if dtype in _abi.DTYPE_CODES else -1
         self.dtype_name = dtype
         status = ctypes.c_int(0)
-        if len(args) == 1:   # /comms/fir_filter(dtype, tapsType)
+        if len(args) == 0:   # /comms/scale, /comms/rotate, /comms/signal_probe: factory (dtype)
+            self._h = lib().b200c_blk_make_dtype(path.encode(), dtype.encode(), in_bytes, out_bytes, ctypes.byref(status))
+        elif len(args) == 1:   # /comms/fir_filter(dtype, tapsType)
             self._h = lib().b200c_blk_make(path.encode(), dtype.encode(), str(args[0]).encode(), 0, 0, in_bytes, out_bytes,
                                            ctypes.byref(status))
         elif len(args) == 2:  # /comms/fft(dtype, numBins, inverse)
@@ -154,6 +162,17 @@ class Block:
         if name in _STRING_SETTERS:
             _check(L.b200c_blk_call_string(self._h, n, str(args[0]).encode()))
             return None
+        if name in _DOUBLE_SETTERS:
+            _check(L.b200c_blk_call_double(self._h, n, float(args[0])))
+            return None
+        if name in _DOUBLE_GETTERS:
+            v = ctypes.c_double(0)
+            _check(L.b200c_blk_get_double(self._h, n, ctypes.byref(v)))
+            return v.value
+        if name == "value":   # SignalProbe::value(): double or complex<double>
+            v = (ctypes.c_double * 2)()
+            _check(L.b200c_blk_get_complex(self._h, n, v))
+            return complex(v[0], v[1])
         if name in _SIZE_GETTERS:
             v = ctypes.c_size_t(0)
             _check(L.b200c_blk_get_size(self._h, n, ctypes.byref(v)))
@@ -170,6 +189,15 @@ class Block:
 
     def has_call(self, name: str) -> bool:
         return bool(lib().b200c_blk_has_call(self._h, name.encode()))
+
+    def has_signal(self, name: str) -> bool:
+        return bool(lib().b200c_blk_has_signal(self._h, name.encode()))
+
+    def last_signal_value(self, signal: str = "valueChanged"):
+        """(last payload of a value-carrying signal as complex, number of emissions)"""
+        v, count = (ctypes.c_double * 2)(), ctypes.c_size_t(0)
+        _check(lib().b200c_blk_last_signal_value(self._h, signal.encode(), v, ctypes.byref(count)))
+        return complex(v[0], v[1]), count.value
 
     def activate(self):
         _check(lib().b200c_blk_activate(self._h))

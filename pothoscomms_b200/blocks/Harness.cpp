@@ -22,11 +22,13 @@ public:
     {
         if (blk->numInputs() == 0 && blk->numOutputs() == 0) return;   // host-only block (designers): calls and signals only
         _inMgr = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(blk->getInputBufferManager("0", b200c_blocks::kHbmDomain));
-        _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
-        if (!_inMgr || !_outMgr) throw Exception("Harness()", "block does not provide device buffer managers");
+        _sink = blk->numOutputs() == 0;   // a consumer only (/comms/signal_probe): no output side
+        if (!_sink) _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
+        if (!_inMgr || (!_sink && !_outMgr)) throw Exception("Harness()", "block does not provide device buffer managers");
         BufferManagerArgs ia;
         ia.bufferSize = inBytes; ia.numBuffers = 1;
         _inMgr->init(ia);
+        if (_sink) return;
         BufferManagerArgs oa;
         oa.bufferSize = outBytes; oa.numBuffers = 2;
         _outMgr->init(oa);
@@ -57,6 +59,7 @@ public:
     void run()
     {
         InputPort *in = _blk->input(0);
+        if (_sink) { runSink(in); return; }
         OutputPort *out = _blk->output(0);
         const size_t isz = in->dtype().size(), osz = out->dtype().size();
         for (int guard = 0; guard < 1000000; guard++) {
@@ -115,8 +118,31 @@ public:
         }
     }
 
+    // a sink block: work() while the reserve is met and elements are consumed
+    void runSink(InputPort *in)
+    {
+        const size_t isz = in->dtype().size();
+        for (int guard = 0; guard < 1000000; guard++) {
+            const BufferChunk rd = _inMgr->readable();
+            in->_addr = rd.address;
+            in->_bytes = rd.length / isz * isz;
+            in->_labels.clear();
+            in->_pendingConsume = 0;
+            if (in->elements() < std::max<size_t>(in->_reserve, 1)) break;
+            _blk->work();
+            _workCalls++;
+            const size_t c = in->_pendingConsume;
+            if (c > in->elements()) throw Exception("Harness::run()", "block over-consumed");
+            if (c == 0) break;
+            _inMgr->push(c * isz);
+            _totalConsumed += c;
+            in->_totalConsumed = _totalConsumed;
+        }
+    }
+
     size_t collect(void *host, size_t maxElems)
     {
+        if (_sink) return 0;
         const size_t osz = _blk->output(0)->dtype().size();
         const size_t n = std::min(maxElems, _collected.size() / osz);
         std::memcpy(host, _collected.data(), n * osz);
@@ -126,7 +152,7 @@ public:
 
     Block *block() { return _blk.get(); }
     const std::vector<Label> &outLabels() const { return _outLabels; }
-    size_t pendingOutput() const { return _collected.size() / _blk->output(0)->dtype().size(); }
+    size_t pendingOutput() const { return _sink ? 0 : _collected.size() / _blk->output(0)->dtype().size(); }
     size_t reserve() const { return _blk->_inputs.at(0)._reserve; }
     unsigned long long totalConsumed() const { return _totalConsumed; }
     unsigned long long workCalls() const { return _workCalls; }
@@ -135,6 +161,7 @@ public:
 private:
     std::unique_ptr<Block> _blk;
     int _device;
+    bool _sink = false;
     std::shared_ptr<b200c_blocks::DeviceCircularBufferManager> _inMgr;
     BufferManager::Sptr _outMgr;
     std::vector<Label> _inLabels, _outLabels;
@@ -177,6 +204,42 @@ void *b200c_blk_make(const char *path, const char *dtype, const char *taps_type,
     });
     if (status) *status = rc;
     return h;
+}
+
+// factory (dtype) only: /comms/scale, /comms/rotate, /comms/signal_probe, /blocks/stream_probe
+void *b200c_blk_make_dtype(const char *path, const char *dtype, size_t in_bytes, size_t out_bytes, int *status)
+{
+    Harness *h = nullptr;
+    const int rc = guarded([&] {
+        Pothos::Block *blk = Pothos::BlockRegistry::make(path, Pothos::DType(dtype));
+        const char *env = std::getenv("B200C_DEVICE");
+        h = new Harness(blk, env ? std::atoi(env) : 0, in_bytes, out_bytes);
+    });
+    if (status) *status = rc;
+    return h;
+}
+// a call returning double or std::complex<double> (SignalProbe::value): out[0] = re, out[1] = im
+int b200c_blk_get_complex(void *h, const char *name, double *out)
+{
+    return guarded([&] {
+        const Object o = static_cast<Harness *>(h)->block()->call(name);
+        if (o.type() == typeid(std::complex<double>)) { const auto v = o.extract<std::complex<double>>(); out[0] = v.real(); out[1] = v.imag(); }
+        else { out[0] = o.convert<double>(); out[1] = 0.0; }
+    });
+}
+// last payload of a signal carrying one double or std::complex<double> ("valueChanged")
+int b200c_blk_last_signal_value(void *h, const char *signal, double *out, size_t *count)
+{
+    return guarded([&] {
+        Pothos::Block *b = static_cast<Harness *>(h)->block();
+        *count = b->signalCount(signal);
+        out[0] = out[1] = 0.0;
+        const auto *args = b->lastSignal(signal);
+        if (!args || args->empty()) return;
+        const Object &o = args->at(0);
+        if (o.type() == typeid(std::complex<double>)) { const auto v = o.extract<std::complex<double>>(); out[0] = v.real(); out[1] = v.imag(); }
+        else out[0] = o.convert<double>();
+    });
 }
 
 void b200c_blk_destroy(void *h) { delete static_cast<Harness *>(h); }

@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <string>
 #include <typeindex>
+#include <cctype>
 #include <typeinfo>
 #include <utility>
 #include <vector>
@@ -295,6 +296,21 @@ public:
 
 protected:
     void registerSignal(const std::string &name) { _signals[name] = true; }
+    // registerProbe("value"): slot "probeValue" that emits "valueTriggered" with the call's result
+    void registerProbe(const std::string &name)
+    {
+        std::string cap = name;
+        if (!cap.empty()) cap[0] = (char)std::toupper((unsigned char)cap[0]);
+        const std::string sig = name + "Triggered";
+        _signals[sig] = true;
+        _calls["probe" + cap] = [this, name, sig](const std::vector<Object> &) {
+            const std::vector<Object> args{this->call(name)};
+            _lastSignal[sig] = args;
+            _signalCounts[sig]++;
+            for (auto &c : _signalConns[sig]) c.first->call(c.second, args);
+            return Object();
+        };
+    }
     template <typename... A> void emitSignal(const std::string &name, const A &...a)
     {
         if (!_signals.count(name)) throw Exception("Block::emitSignal(" + name + ")", "no such registered signal");

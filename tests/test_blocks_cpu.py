@@ -33,3 +33,16 @@ def test_block_creation_fails_loudly_without_gpu():
         blocks.make("/comms/fir_filter", "complex_float32", "COMPLEX")
     with pytest.raises(blocks.PothosException, match="no CPU fallback"):
         blocks.make("/comms/fft", "complex_float32", 1024, False)
+
+
+def test_neighbour_blocks_registry_and_factory_errors():
+    """/comms/scale (math/Scale.cpp:155-156), /comms/rotate (math/Rotate.cpp:159-160), /comms/signal_probe and
+    its legacy path (utility/SignalProbe.cpp:188-192): registered; unsupported types rejected before any
+    device is touched."""
+    from pothoscomms_b200 import blocks
+    for path in ("/comms/scale", "/comms/rotate", "/comms/signal_probe", "/blocks/stream_probe"):
+        assert blocks.registry_has(path), path
+    with pytest.raises(blocks.InvalidArgumentException, match="unsupported type"):   # Rotate.cpp:157: complex only
+        blocks.make("/comms/rotate", "int16")
+    with pytest.raises(blocks.PothosException):
+        blocks.make("/comms/scale", "uint8")

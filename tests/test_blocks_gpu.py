@@ -323,3 +323,111 @@ def test_fir_designer(oracle, cuda_device, filter_type, band_type):
     for is_pass, freq in mask_points(band_type, rate, lower, upper):
         level = power[int(fft_size * ((freq + rate / 2) / rate))]
         assert (level > -30.0) if is_pass else (level < -80.0), (filter_type, band_type, freq, level)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int64", "int32", "int16", "int8"])
+def test_scale(oracle, cuda_device, dtype):
+    """math/TestScale.cpp:14-70 -- 13 points 10*i through /comms/scale for factors -1 ... 1; each output
+    within 1 of Type(input * factor) (:52), and equal to the oracle."""
+    from pothoscomms_b200 import blocks
+    code = oracle.DTYPE_CODES[dtype]
+    sc = oracle.scalar_np(code)
+    x = (10 * np.arange(13)).astype(sc).reshape(-1, 1)
+    for i in range(5):
+        factor = i / 2.0 - 1.0
+        b = blocks.make("/comms/scale", dtype)
+        assert all(b.has_call(c) for c in ("setFactor", "getFactor", "setLabelId", "getLabelId"))   # Scale.cpp:32-35
+        b.call("setFactor", factor)
+        assert b.call("getFactor") == factor
+        b.activate()
+        y = b.push_through(x)
+        assert y.shape == x.shape
+        expected = np.trunc(x.astype(np.float64) * factor) if "int" in dtype else x.astype(np.float64) * factor
+        assert np.all(np.abs(y.astype(np.float64) - expected) <= 1)
+        assert np.array_equal(y, oracle.scale(code, factor, x))
+
+
+def test_scale_label_changes_factor_mid_stream(oracle, cuda_device):
+    """math/Scale.cpp:86-108: a label with the configured id carries a new factor; it takes effect exactly
+    at the label's element."""
+    from pothoscomms_b200 import blocks
+    code = oracle.CI16
+    rng = np.random.default_rng(8)
+    x = rng.integers(-20000, 20000, size=(3000, 2)).astype(np.int16)
+    b = blocks.make("/comms/scale", "complex_int16")
+    b.call("setFactor", 0.5)
+    b.call("setLabelId", "gain")
+    assert b.call("getLabelId") == "gain"
+    b.activate()
+    b.post_label("gain", 1000, data=0.25)
+    b.post_label("other", 1500, data=9.0)             # a foreign id is ignored
+    y = b.push_through(x)
+    ref = np.concatenate([oracle.scale(code, 0.5, x[:1000]), oracle.scale(code, 0.25, x[1000:])])
+    assert np.array_equal(y, ref)
+    assert b.call("getFactor") == 0.25
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int64", "int32", "int16", "int8"])
+def test_rotate(oracle, cuda_device, dtype):
+    """math/TestRotate.cpp:14-71 -- (10 f, -20 f) through /comms/rotate at phases 0, pi/2, pi, 3pi/2"""
+    from pothoscomms_b200 import blocks
+    cdtype = "complex_" + dtype
+    code = oracle.DTYPE_CODES[cdtype]
+    sc = oracle.scalar_np(code)
+    f = np.arange(13)
+    x = np.stack([10 * f, -20 * f], axis=1).astype(sc)
+    for i in range(4):
+        phase = i * np.pi / 2
+        b = blocks.make("/comms/rotate", cdtype)
+        assert all(b.has_call(c) for c in ("setPhase", "getPhase", "setLabelId", "getLabelId"))    # Rotate.cpp:63-66
+        b.call("setPhase", phase)
+        b.activate()
+        y = b.push_through(x)
+        z = (x[:, 0].astype(np.float64) + 1j * x[:, 1].astype(np.float64)) * np.exp(1j * phase)
+        exp = np.stack([z.real, z.imag], axis=1)
+        if "int" in dtype:
+            exp = np.trunc(exp)
+        assert np.all(np.abs(y.astype(np.float64) - exp) <= 1)
+        assert np.array_equal(y, oracle.rotate(code, phase, x))
+
+
+def test_signal_probe_rms_at_the_end_of_the_fir_topology(oracle, cuda_device):
+    """filter/TestFIRFilter.cpp:44-78: waveform -> /comms/fir_filter -> /comms/signal_probe (RMS mode), checked
+    through the probe's "valueChanged" signal and value() call; here every block's samples stay in HBM."""
+    from pothoscomms_b200 import blocks
+    dtype = "complex_float32"
+    code = oracle.DTYPE_CODES[dtype]
+    amplitude, rate, freq, n = 1000.0, 1e6, 30e3, 4096
+    wave = amplitude * np.exp(2j * np.pi * freq / rate * np.arange(n))
+    x = oracle.to_raw(wave, code)
+    taps = sinc_complex_bandpass(101, (freq - 0.1 * rate) / rate, (freq + 0.1 * rate) / rate)
+    fir = blocks.make("/comms/fir_filter", dtype, "COMPLEX")
+    fir.call("setTaps", taps)
+    fir.activate()
+    y = fir.push_through(x)
+    probe = blocks.make("/comms/signal_probe", dtype)
+    assert all(probe.has_call(c) for c in "value setMode getMode setWindow getWindow setRate getRate probeValue".split())
+    assert probe.has_signal("valueChanged") and probe.has_signal("valueTriggered")
+    assert (probe.call("getMode"), probe.call("getWindow"), probe.call("getRate")) == ("VALUE", 1024, 0.0)   # SignalProbe.cpp:63-66
+    probe.call("setMode", "RMS")
+    probe.call("setWindow", 1024)
+    assert probe.reserve == 1024                       # setWindow sets the input reserve (:99)
+    probe.activate()
+    assert probe.input_domain == "b200c_hbm"
+    probe.feed(y[:3 * 1024 + 100])
+    probe.run()
+    value, count = probe.last_signal_value("valueChanged")
+    assert count == 3 and probe.total_consumed == 3 * 1024      # one emission per full window; the rest waits for the reserve
+    ref = oracle.probe(code, "RMS", y[2 * 1024: 3 * 1024]).real
+    assert abs(value.real - ref) <= 1e-9 * ref and value.imag == 0.0
+    assert probe.call("value") == value
+    assert value.real > 0.1 * amplitude                 # POTHOS_TEST_TRUE(rms > 0.1*waveAmplitude), :78
+    for mode in ("MEAN", "VALUE"):
+        p2 = blocks.make("/blocks/stream_probe", dtype)
+        p2.call("setMode", mode)
+        p2.call("setWindow", 512)
+        p2.activate()
+        p2.feed(y[:512])
+        p2.run()
+        got, c = p2.last_signal_value()
+        assert c == 1 and abs(got - oracle.probe(code, mode, y[:512])) <= 1e-6 * max(1.0, abs(got))
