@@ -163,25 +163,63 @@ template <int CLS> static int rotate_cls(double phase, const void *d_in, void *d
 }
 
 // ------------------------------------------------------------------------------ probe ---
-// acc[0] += sum of |x|^2 (RMS) or sum of re (MEAN), acc[1] += sum of im (MEAN), in double
-template <typename T, int NC, int MODE>
+// acc[0] += sum of |x|^2 (RMS) or sum of re (MEAN), acc[1] += sum of im (MEAN).  8- and 16-bit
+// integers are summed exactly in 64-bit integers per thread (a square pair is < 2^31), everything
+// else in double; 128-bit loads when the window is 16-byte aligned, four in flight per thread.
+template <typename T> struct ProbeAcc { typedef double type; };
+template <> struct ProbeAcc<int8_t> { typedef long long type; };
+template <> struct ProbeAcc<int16_t> { typedef long long type; };
+
+template <typename T, int NC, int MODE, typename A>
+__device__ __forceinline__ void probe_accumulate(const T *e, int count, A &a0, A &a1)
+{
+#pragma unroll
+    for (int k = 0; k < count; k += NC) {
+        if constexpr (MODE == 1) {
+            if constexpr (std::is_same<A, long long>::value) {
+                const int re = e[k], im = NC == 2 ? e[k + NC - 1] : 0;
+                a0 += (long long)(re * re + im * im);
+            } else {
+                const double re = (double)e[k], im = NC == 2 ? (double)e[k + NC - 1] : 0.0;
+                a0 += re * re + im * im;
+            }
+        } else {
+            a0 += (A)e[k];
+            if (NC == 2) a1 += (A)e[k + NC - 1];
+        }
+    }
+}
+
+template <typename T, int NC, int MODE, bool VEC>
 __global__ void __launch_bounds__(256) probe_kernel(const T *__restrict__ in, size_t n_elems, double *acc)
 {
-    double a0 = 0.0, a1 = 0.0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
-        const double re = (double)in[i * NC], im = NC == 2 ? (double)in[i * NC + 1] : 0.0;
-        if (MODE == 1) a0 += re * re + im * im;
-        else { a0 += re; a1 += im; }
+    typedef typename ProbeAcc<T>::type A;
+    A a0 = 0, a1 = 0;
+    const size_t n = n_elems * NC, stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (VEC) {
+        constexpr int V = 16 / (int)sizeof(T);               // scalars per vector: a whole number of elements
+        const size_t nv = n / V;
+        const uint4 *vin = reinterpret_cast<const uint4 *>(in);
+        for (size_t i = tid; i < nv; i += 4 * stride) {
+            uint4 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = i + j * stride < nv ? __ldcs(vin + i + j * stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) probe_accumulate<T, NC, MODE, A>(reinterpret_cast<const T *>(&u[j]), V, a0, a1);
+        }
+        for (size_t i = nv * V + tid * NC; i < n; i += stride * NC) probe_accumulate<T, NC, MODE, A>(in + i, NC, a0, a1);
+    } else {
+        for (size_t i = tid * NC; i < n; i += stride * NC) probe_accumulate<T, NC, MODE, A>(in + i, NC, a0, a1);
     }
+    double d0 = (double)a0, d1 = (double)a1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
     }
     __shared__ double s0[8], s1[8];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { s0[w] = a0; s1[w] = a1; }
+    if (l == 0) { s0[w] = d0; s1[w] = d1; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double t0 = 0.0, t1 = 0.0;
@@ -189,6 +227,13 @@ __global__ void __launch_bounds__(256) probe_kernel(const T *__restrict__ in, si
         atomicAdd(acc, t0);
         if (MODE == 2 && NC == 2) atomicAdd(acc + 1, t1);
     }
+}
+
+template <typename T, int NC, int MODE>
+static void launch_probe(const T *in, size_t n, double *d_acc, int grid, cudaStream_t s)
+{
+    if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) probe_kernel<T, NC, MODE, true><<<grid, 256, 0, s>>>(in, n, d_acc);
+    else probe_kernel<T, NC, MODE, false><<<grid, 256, 0, s>>>(in, n, d_acc);
 }
 
 template <typename T> static int probe_t(bool cx, int mode, const void *d_in, size_t n, double *value, int device, cudaStream_t s)
@@ -203,20 +248,25 @@ template <typename T> static int probe_t(bool cx, int mode, const void *d_in, si
     }
     int sms = 0, rc;
     if ((rc = sm_count_of(device, sms))) return rc;
-    double *d_acc = nullptr;
-    B200C_CUDA_TRY(cudaMalloc(&d_acc, 2 * sizeof(double)));
+    // per-thread, per-device scratch (two doubles on the device, two pinned on the host), allocated once:
+    // the actor calling work() is the only user, and a probe window is small, so call overhead matters
+    static thread_local double *scratch_d[16] = {nullptr}, *scratch_h[16] = {nullptr};
+    if (device >= 16) { set_error("b200c_probe: device index above 15"); return B200C_ERR_UNSUPPORTED; }
+    if (!scratch_d[device]) {
+        B200C_CUDA_TRY(cudaMalloc(&scratch_d[device], 2 * sizeof(double)));
+        B200C_CUDA_TRY(cudaMallocHost(&scratch_h[device], 2 * sizeof(double)));
+    }
+    double *d_acc = scratch_d[device], *h = scratch_h[device];
     cudaError_t e = cudaMemsetAsync(d_acc, 0, 2 * sizeof(double), s);
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)sms * 8));
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((n * nc * sizeof(T) / 16 + 1023) / 1024, (size_t)sms * 8));
     const T *in = static_cast<const T *>(d_in);
     if (e == cudaSuccess) {
-        if (mode == 1) { if (cx) probe_kernel<T, 2, 1><<<grid, 256, 0, s>>>(in, n, d_acc); else probe_kernel<T, 1, 1><<<grid, 256, 0, s>>>(in, n, d_acc); }
-        else { if (cx) probe_kernel<T, 2, 2><<<grid, 256, 0, s>>>(in, n, d_acc); else probe_kernel<T, 1, 2><<<grid, 256, 0, s>>>(in, n, d_acc); }
+        if (mode == 1) { if (cx) launch_probe<T, 2, 1>(in, n, d_acc, grid, s); else launch_probe<T, 1, 1>(in, n, d_acc, grid, s); }
+        else { if (cx) launch_probe<T, 2, 2>(in, n, d_acc, grid, s); else launch_probe<T, 1, 2>(in, n, d_acc, grid, s); }
         e = cudaGetLastError();
     }
-    double h[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_acc, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(d_acc);
     if (e != cudaSuccess) { set_error("b200c_probe failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return B200C_ERR_CUDA; }
     if (mode == 1) { value[0] = std::sqrt(h[0] / (double)n); value[1] = 0.0; }
     else { value[0] = h[0] / (double)n; value[1] = h[1] / (double)n; }
