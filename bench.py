@@ -46,6 +46,8 @@ WORKLOADS = {
     "resamp_short": ("complex_float32", "resamp_short", 2, 3, 28, 20.0),
     "real64": ("float32", "real64", 1, 1, 29, 8.0),
     "real64_i16": ("int16", "real64", 1, 1, 29, 4.0),
+    # the C3 resampler on the bit-exact fixed-point type (4 B in + 6 B out per input sample)
+    "c3_i16": ("complex_int16", "c3_i16", 2, 3, 28, 10.0),
 }
 
 

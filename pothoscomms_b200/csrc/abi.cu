@@ -108,6 +108,8 @@ struct b200c_fir {
     bool use_umma = false;
     FirUmma32Plan u32;          // tcgen05, 32 outputs per row (swizzled planes)
     bool use_u32 = false;
+    FirUmmaPPlan up;            // tcgen05 polyphase resampler (int16, L, M <= 4)
+    bool use_up = false;
 };
 
 struct b200c_fir_bank {
@@ -193,6 +195,13 @@ static int fir_refresh(b200c_fir *h)
             if (rc) return rc;
             h->use_umma = h->umma.ready;
         }
+        h->use_up = false;
+        if (!force_direct) {
+            rc = fir_ummap_configure(h->up, h->dtype, h->taps.data(), h->ntaps, h->taps_kind == B200C_TAPS_COMPLEX, h->M, h->L,
+                                     algo && std::strcmp(algo, "ummap") == 0);
+            if (rc) return rc;
+            h->use_up = h->up.ready;
+        }
         h->use_u32 = false;
         if (h->use_imma && !(algo && (std::strcmp(algo, "imma") == 0 || std::strcmp(algo, "umma") == 0))) {
             rc = fir_umma32_configure(h->u32, h->imma, h->taps.data(), algo && std::strcmp(algo, "umma32") == 0);
@@ -207,6 +216,7 @@ static int fir_refresh(b200c_fir *h)
 static int fir_dispatch(const b200c_fir *h, const void *d_in, size_t in_elems, void *d_out, size_t nblocks, cudaStream_t s)
 {
     if (h->use_os) return fir_os_launch(h->os, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
+    if (h->use_up) return fir_ummap_launch(h->up, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
     if (h->use_u32) return fir_umma32_launch(h->u32, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
     if (h->use_umma) return fir_umma_launch(h->umma, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
     if (h->use_imma) return fir_imma_launch(h->imma, d_in, in_elems, d_out, nblocks, h->di.sm_count, s);
@@ -279,6 +289,7 @@ int b200c_fir_destroy(b200c_fir *h)
         fir_imma_destroy(h->imma);
         fir_umma_destroy(h->umma);
         fir_umma32_destroy(h->u32);
+        fir_ummap_destroy(h->up);
         h->pipe.release();
     }
     delete h;
@@ -325,6 +336,7 @@ const char *b200c_fir_kernel(const b200c_fir *h)
 {
     if (!h) return "";
     if (h->use_os) return fir_os_kernel_name(h->os);
+    if (h->use_up) return "fir_ummap_kernel";
     if (h->use_u32) return "fir_umma32_kernel";
     if (h->use_umma) return "fir_umma_kernel";
     if (h->use_imma) return "fir_imma_kernel";

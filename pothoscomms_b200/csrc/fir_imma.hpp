@@ -59,4 +59,16 @@ void fir_umma32_destroy(FirUmma32Plan &p);
 int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
                       cudaStream_t stream);
 
+// tcgen05 polyphase resampler for int16 streams (fir_ummap.cu): L, M <= 4, 2-digit taps.
+struct FirUmmaPPlan {
+    bool ready = false;
+    int L = 1, M = 1, NB = 0, N = 0, dc = 1, nstage = 1;
+    void *d_bmat = nullptr;   // [M][dc][NB][N x 32 B] B tiles, N = 16 L dc 2
+    size_t capacity = 0;
+};
+int fir_ummap_configure(FirUmmaPPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L, bool force);
+void fir_ummap_destroy(FirUmmaPPlan &p);
+// nq = output blocks q (= consumed / M); outputs written = nq * L
+int fir_ummap_launch(const FirUmmaPPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count, cudaStream_t stream);
+
 } // namespace b200c

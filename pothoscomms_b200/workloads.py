@@ -59,6 +59,8 @@ def config_taps(name: str):
         return h / np.abs(h).sum(), "COMPLEX"
     if name == "c3":         # L=3, M=2, 255-tap RRC, real taps
         return root_raised_cosine(255, 3.0, 0.5), "REAL"
+    if name == "c3_i16":     # the same resampler scaled for fixed point: peak tap 0.33 (Q16 taps of two byte digits)
+        return 0.5 * root_raised_cosine(255, 3.0, 0.5), "REAL"
     if name == "c5":
         return complex_bandpass(1024, F0 / FS, 0.02), "COMPLEX"
     # short-tap streams (north_star: "the short-tap path stays on FFMA and is reported as an

@@ -575,3 +575,28 @@ def test_umma32_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
             assert f.kernel == "fir_umma32_kernel"
         assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
         _compare(oracle, code, y, y_ref, f"umma32 K={ntaps} n={n_new} zt={zero_tail}")
+
+
+@pytest.mark.parametrize("M,L", [(2, 1), (1, 2), (3, 1), (1, 3), (2, 3), (3, 2), (4, 3), (3, 4), (4, 4), (2, 2), (1, 4), (4, 1)])
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_ummap_polyphase_is_bit_exact(oracle, cuda_device, dt, taps_type, M, L):
+    """int16 resampling (interpolation, decimation <= 4) on tcgen05 (fir_ummap.cu): one Toeplitz GEMM per
+    input residue, all residues and components accumulating into shared tensor-memory regions.  Against
+    the oracle's loop nest (filter/FIRFilter.cpp:286-302) for tap counts that leave the last phases one
+    tap short, ragged lengths around the 2048-block tile, tiny inputs, the burst zero tail."""
+    code = getattr(oracle, dt)
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(9000 + 97 * M + L + cx)
+    for ntaps in (L * 13 + 1, 255):
+        taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps / L)
+        if cx:
+            taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps / L)
+        K = -(-ntaps // L)
+        for n_new, zero_tail in ((M, False), (M * 2047, False), (M * 2048, False), (M * 2049 + M - 1, False), (M * 9000 + 1, False),
+                                 (997, True), (1, True)):
+            x = _rand_input(oracle, code, K - 1 + n_new, rng, full_scale=True)
+            y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, M, L, x, zero_tail=zero_tail)
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
+            assert f.kernel == "fir_ummap_kernel", f.kernel
+            assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
+            _compare(oracle, code, y, y_ref, f"ummap {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}")
