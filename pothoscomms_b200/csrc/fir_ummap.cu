@@ -33,11 +33,12 @@ struct FirUmmaPArgs {
     long long ntiles;
     int L, M, NB, N;     // N = 16 * L * DC * 2
     int PL, PLa;         // plane bytes in use (2048 + 32 NB) / allocated (multiple of 128)
-    int R, nstage;       // landing ring depth; accumulator (and plane) stages: 1 or 2
+    int R, nstage;       // landing ring depth; accumulator stages: 1 or 2
+    int pstage;          // plane stages: 2 (staging overlaps the MMAs) unless shared memory is short
 };
 
 constexpr int kUPTile = 2048;      // blocks q per tile: 128 rows x 16
-constexpr int kUPEpiWarps = 8, kUPStageWarps = 4, kUPMaxRing = 6;
+constexpr int kUPEpiWarps = 8, kUPStageWarps = 8, kUPMaxRing = 6;
 constexpr int kUPThreads = 32 * (kUPEpiWarps + kUPStageWarps + 2);
 
 template <int DC>
@@ -51,8 +52,9 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     const unsigned ALLOC = (unsigned)(NS * COLS) <= 32 ? 32 : (NS * COLS) <= 64 ? 64 : (NS * COLS) <= 128 ? 128 : (NS * COLS) <= 256 ? 256 : 512;
     const size_t bm_bytes = (size_t)M * DC * NB * N * 32, stage_bytes = (size_t)M * NPL * PLa, raw_bytes = (size_t)PL * M * ESZ;
     unsigned char *bmat = smem_w;
-    unsigned char *planes = bmat + bm_bytes;                         // [NS][M][NPL][PLa]
-    unsigned char *raw = planes + NS * stage_bytes;                  // [R][PL * M * ESZ]
+    unsigned char *planes = bmat + bm_bytes;                         // [NP][M][NPL][PLa]
+    const int NP = a.pstage;
+    unsigned char *raw = planes + NP * stage_bytes;                  // [R][PL * M * ESZ]
     __shared__ __align__(8) unsigned long long raw_full[kUPMaxRing], raw_empty[kUPMaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
     __shared__ unsigned tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
     // the tile's window: buffer elements [q0 M, (q0 + PL) M)
     auto bulk_ok = [&](long long tile) { return al && (tile * kUPTile + PL) * M <= a.n_in; };
-    // stage / phase of the i-th tile of this CTA for an NS-deep ring
+    // accumulator stage / phase of the i-th tile of this CTA for an NS-deep ring; the planes are their
+    // own ring (2-deep when shared memory allows) so that staging tile i+1 overlaps the MMAs of tile i
     auto stage_of = [&](int i, int &s, unsigned &ph) { s = NS == 2 ? (i & 1) : 0; ph = (unsigned)(NS == 2 ? (i >> 1) : i) & 1; };
 
     if (warp == kUPEpiWarps + kUPStageWarps + 1) {
@@ -105,10 +108,12 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
             for (int i = 0; i < ntl; i++) {
                 int s; unsigned ph;
                 stage_of(i, s, ph);
-                mbar_wait(&planes_full[s], ph);
+                const int sp = NP == 2 ? (i & 1) : 0;
+                const unsigned php = (unsigned)(NP == 2 ? (i >> 1) : i) & 1;
+                mbar_wait(&planes_full[sp], php);
                 mbar_wait(&acc_empty[s], ph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned planes_s = smem_u32(planes + (size_t)s * stage_bytes);
+                const unsigned planes_s = smem_u32(planes + (size_t)sp * stage_bytes);
 #pragma unroll
                 for (int dl = 0; dl < 2; dl++) {                       // data limb: its own accumulator region
                     const unsigned d = tmem_base + (unsigned)(s * COLS + dl * N);
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
                             }
                         }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[s])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[sp])) : "memory");
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[s])) : "memory");
             }
         }
@@ -138,8 +143,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
         constexpr int NST = 32 * kUPStageWarps;
         const int nchunk = PL / 4;
         for (int i = 0, r = 0, rph = 0; i < ntl; i++) {
-            int s; unsigned ph;
-            stage_of(i, s, ph);
+            const int s = NP == 2 ? (i & 1) : 0;
+            const unsigned ph = (unsigned)(NP == 2 ? (i >> 1) : i) & 1;
             const long long tile = first + (long long)i * step;
             const long long e0 = tile * kUPTile * M;                  // first buffer element of the tile's window
             const bool landed = bulk_ok(tile);
@@ -302,8 +307,10 @@ int fir_ummap_configure(FirUmmaPPlan &p, int dtype, const double *taps, size_t n
     const int NB = (int)((15 + a_max + 1 + 31) / 32);
     const int PL = kUPTile + 32 * NB, PLa = (PL + 127) / 128 * 128;
     const int nstage = 4 * N <= 512 ? 2 : 1;
-    const size_t bm_bytes = (size_t)M * dc * NB * N * 32, fixed = bm_bytes + (size_t)nstage * M * dc * 2 * PLa + 1024;
-    if (fixed + 2 * (size_t)PL * M * dc * 2 > 210 * 1024) return B200C_OK;   // tables + planes + a 2-deep landing ring must fit
+    const size_t bm_bytes = (size_t)M * dc * NB * N * 32, stage = (size_t)M * dc * 2 * PLa, one = (size_t)PL * M * dc * 2;
+    // tables + planes (two stages if they fit) + a landing ring of at least two slots
+    const int pstage = bm_bytes + 2 * stage + 3 * one + 1024 <= 210 * 1024 ? 2 : 1;
+    if (bm_bytes + pstage * stage + 2 * one + 1024 > 210 * 1024) return B200C_OK;
     std::vector<uint8_t> bm(bm_bytes, 0);
     for (size_t ps = 0; ps < L; ps++) {
         const long long ii = (long long)((ps + 1) * M - 1), jp = ii % (long long)L, dp = ii / (long long)L;
@@ -341,7 +348,7 @@ int fir_ummap_configure(FirUmmaPPlan &p, int dtype, const double *taps, size_t n
         p.capacity = bm.size();
     }
     B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
-    p.L = (int)L; p.M = (int)M; p.NB = NB; p.N = N; p.dc = dc; p.nstage = nstage;
+    p.L = (int)L; p.M = (int)M; p.NB = NB; p.N = N; p.dc = dc; p.nstage = nstage; p.pstage = pstage;
     p.ready = true;
     return B200C_OK;
 }
@@ -363,7 +370,7 @@ static int launch_up(FirUmmaPArgs a, int sm_count, cudaStream_t stream)
         B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured[dev] = true;
     }
-    const size_t fixed = (size_t)a.M * DC * a.NB * a.N * 32 + (size_t)a.nstage * a.M * DC * 2 * a.PLa + 1024, one = (size_t)a.PL * a.M * DC * 2;
+    const size_t fixed = (size_t)a.M * DC * a.NB * a.N * 32 + (size_t)a.pstage * a.M * DC * 2 * a.PLa + 1024, one = (size_t)a.PL * a.M * DC * 2;
     a.R = (int)std::max<size_t>(2, std::min<size_t>(kUPMaxRing, (216 * 1024 - fixed) / one));
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);   // > half an SM: one CTA per SM (tensor memory)
     const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
@@ -380,7 +387,7 @@ int fir_ummap_launch(const FirUmmaPPlan &p, const void *d_in, size_t in_elems, v
     a.n_in = (long long)in_elems; a.nq = (long long)nq;
     a.ntiles = ((long long)nq + kUPTile - 1) / kUPTile;
     a.L = p.L; a.M = p.M; a.NB = p.NB; a.N = p.N;
-    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage;
+    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage; a.pstage = p.pstage;
     return p.dc == 1 ? launch_up<1>(a, sm_count, stream) : launch_up<2>(a, sm_count, stream);
 }
 
