@@ -13,8 +13,8 @@ B200C_FIR_ALGO=imma timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu -
 B200C_FIR_ALGO=umma timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --workload c2 > $O/r01d_bench_c2_umma16.log 2>&1; tail -1 $O/r01d_bench_c2_umma16.log
 B200C_FIR_ALGO=direct timeout 300 python bench.py --steps 5 --warmup 2 --no-cpu --no-e2e --workload c2 > $O/r01d_bench_c2_direct.log 2>&1; tail -1 $O/r01d_bench_c2_direct.log
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/r01d_bench_reference.log 2>&1; tail -1 $O/r01d_bench_reference.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/r01d_launches_headline.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $O/ncu_launches.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/r01d_launches_headline.csv \
+    python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > $O/ncu_launches.log 2>&1
 ./tools/ncu_cap.sh r01d_prof_umma32_c2 fir_umma32 c2
 ./tools/ncu_cap.sh r01d_prof_umma32_real64 fir_umma32 real64_i16
 ./tools/ncu_cap.sh r01d_prof_ummap_c3i16 fir_ummap c3_i16
