@@ -566,6 +566,87 @@ __global__ void __launch_bounds__(32 * NW, MINB) fir_osp_kernel(const FirOs32GAr
     }
 }
 
+// Grouped variant: G independent NW-warp groups per CTA (one CTA per SM) share ONE copy of the tap
+// spectra and twiddles in shared memory.  In fir_osp_kernel those are global loads through an L1
+// that 5 x 42 KB of shared memory had shrunk to 40 KB: 37 % hit rate, long-scoreboard stalls
+// (profiles/r01d_prof_osp_c3.txt).  Groups synchronise on their own named barriers.
+template <int NW, int G>
+__global__ void __launch_bounds__(32 * NW * G, 1) fir_ospg_kernel(const FirOs32GArgs a, const int M)
+{
+    extern __shared__ __align__(16) c2 smem_q[];
+    const int L = a.L, hop = a.hop;
+    const int pstride = osp_plane_stride(L);
+    c2 *Hs = smem_q;                                   // [L*M][1024]
+    c2 *tws = Hs + (size_t)L * M * 1024;               // [32][32]
+    const int group_elems = M * kOs32SmemElems + L * pstride;
+    const int g = (threadIdx.x >> 5) / NW, w = (threadIdx.x >> 5) % NW, t = threadIdx.x & 31, tg = threadIdx.x - g * 32 * NW;
+    c2 *S = tws + 1024 + (size_t)g * group_elems;      // [M][kOs32SmemElems]
+    c2 *P = S + M * kOs32SmemElems;                    // [L][pstride]
+    {
+        const c2 *__restrict__ Hg = static_cast<const c2 *>(a.H), *__restrict__ twg = static_cast<const c2 *>(a.tw);
+        for (int i = threadIdx.x; i < L * M * 1024; i += 32 * NW * G) Hs[i] = Hg[i];
+        for (int i = threadIdx.x; i < 1024; i += 32 * NW * G) tws[i] = twg[i];
+    }
+    __syncthreads();
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(32 * NW) : "memory"); };
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    const long long nblk = (a.nq + hop - 1) / hop;
+    const int dq = (32 * NW) / L, dr = (32 * NW) - dq * L;
+    for (long long blk = (long long)blockIdx.x * G + g; blk < nblk; blk += (long long)gridDim.x * G) {
+        const long long Q0 = blk * hop;
+        if (w < M) {
+            c2 *F = S + w * kOs32SmemElems;
+            const long long s0 = a.start0 + Q0 * M + w;
+            const bool inner = s0 >= 0 && s0 + 1023LL * M < a.n_in;
+            c2 v[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const long long ia = s0 + (long long)(32 * n1 + t) * M;
+                v[rev32(n1)] = (inner || (ia >= 0 && ia < a.n_in)) ? __ldg(in + ia) : 0ull;
+            }
+            fft1024_fwd<false>(v, F, tws, t);
+            __syncwarp();
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) F[32 * k2 + t] = v[k2];
+        }
+        group_sync();
+        if (w < L) {
+            c2 *plane = P + w * pstride;
+            const c2 *Hp = Hs + (size_t)w * M * 1024 + t;
+            c2 v[32];
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(S[32 * k2 + t], Hp[32 * k2]);
+            for (int e = 1; e < M; e++) {
+                const c2 *Se = S + e * kOs32SmemElems + t;
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) {
+                    float fx, fy, hx, hy;
+                    const c2 b = Se[32 * k2];
+                    upk(b, fx, fy); upk(Hp[e * 1024 + 32 * k2], hx, hy);
+                    v[k2] = fma2(b, pk(hx, hx), fma2(pk(-fy, fx), pk(hy, hy), v[k2]));
+                }
+            }
+            fft1024_inv(v, plane, tws, t);
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) plane[32 * n1 + t] = v[rev32(n1)];
+        }
+        group_sync();
+        {
+            const long long left = a.nq - Q0;
+            const int nu = left < hop ? (int)left : hop;
+            const int total = nu * L;
+            c2 *__restrict__ o = static_cast<c2 *>(a.out) + Q0 * L;
+            int u = tg / L, p = tg - u * L;
+            for (int j = tg; j < total; j += 32 * NW) {
+                __stcg(o + j, P[p * pstride + u]);
+                u += dq; p += dr;
+                if (p >= L) { p -= L; u++; }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- host ---
 // in-place forward DFT (e^{-2 pi i nk/N}), N a power of two, double precision (host, setTaps path)
 static void host_fft(std::vector<std::complex<double>> &x)
@@ -793,6 +874,20 @@ static void launch_osp(const FirOs32GArgs &a, int M, size_t smem, long long nblk
     kern<<<grid, 32 * NW, smem, stream>>>(a, M);
 }
 
+template <int NW, int G>
+static void launch_ospg(const FirOs32GArgs &a, int M, size_t smem, long long nblk, int sm_count, cudaStream_t stream)
+{
+    auto kern = fir_ospg_kernel<NW, G>;
+    static thread_local bool configured[16] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev < 16 && !configured[dev]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured[dev] = true;
+    }
+    const int grid = (int)std::min<long long>((nblk + G - 1) / G, (long long)sm_count);
+    kern<<<grid, 32 * NW * G, smem, stream>>>(a, M);
+}
+
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
                   cudaStream_t stream, const FirOsBatch *batch)
 {
@@ -807,7 +902,13 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
             const int nw = std::max(p.L, p.M);
             const size_t smem = sizeof(c2) * ((size_t)p.M * kOs32SmemElems + (size_t)p.L * osp_plane_stride(p.L));
             const long long nblk = ((long long)nq + p.hopq - 1) / p.hopq;
-            if (nw == 2) launch_osp<2, 7>(a, p.M, smem, nblk, sm_count, stream);
+            // grouped variant (tap spectra + twiddles once per SM in shared memory) when 4 / 3 groups fit
+            static const bool no_group = [] { const char *e = std::getenv("B200C_OSPG"); return e && std::atoi(e) == 0; }();
+            const size_t shared_tab = sizeof(c2) * ((size_t)p.L * p.M * 1024 + 1024), limit = 227 * 1024;
+            if (!no_group && nw == 3 && shared_tab + 4 * smem <= limit) launch_ospg<3, 4>(a, p.M, shared_tab + 4 * smem, nblk, sm_count, stream);
+            else if (!no_group && nw == 2 && shared_tab + 6 * smem <= limit) launch_ospg<2, 6>(a, p.M, shared_tab + 6 * smem, nblk, sm_count, stream);
+            else if (!no_group && nw == 4 && shared_tab + 3 * smem <= limit) launch_ospg<4, 3>(a, p.M, shared_tab + 3 * smem, nblk, sm_count, stream);
+            else if (nw == 2) launch_osp<2, 7>(a, p.M, smem, nblk, sm_count, stream);
             else if (nw == 3) launch_osp<3, 5>(a, p.M, smem, nblk, sm_count, stream);
             else launch_osp<4, 3>(a, p.M, smem, nblk, sm_count, stream);
             B200C_CUDA_TRY(cudaGetLastError());
