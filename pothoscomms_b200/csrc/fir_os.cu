@@ -160,23 +160,6 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
     }
 }
 
-// ---------------------------------------------------------------- 1024-point variant ---
-// Same algorithm on 1024 = 32 x 32: ONE WARP per transform, 32 points (64 registers) per
-// thread, exchanges through a per-warp shared-memory tile with __syncwarp() only.  Less
-// register state per thread => ~2.5x the resident warps of the 4096-point kernel, which is
-// what keeps the FMA pipe fed; the price is a shorter hop (1024 - (K-1)), so it is used for
-// the shorter tap counts (fir_os_launch).
-struct FirOs32Args {
-    const void *in;
-    void *out;
-    const void *hf;     // [nchan][1024] spectrum of the taps / 1024
-    const void *tw;     // [32][32] W1024^(j*t)
-    long long n_in, n_out;             // per channel
-    long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
-    int nchan;
-    int K;
-};
-
 #ifndef B200C_OS32_PARTIAL_TW
 #define B200C_OS32_PARTIAL_TW 0   // measured: no gain on B200 (headline 269 vs 272 Gsamples/s), kept for reference
 #endif
@@ -201,6 +184,23 @@ __device__ __forceinline__ void twiddle32(c2 (&v)[32], const c2 *__restrict__ tw
         if (b) v[r] = cmul_p<CONJ>(v[r], B[b]);
     }
 }
+
+// ---------------------------------------------------------------- 1024-point variant ---
+// Same algorithm on 1024 = 32 x 32: ONE WARP per transform, 32 points (64 registers) per
+// thread, exchanges through a per-warp shared-memory tile with __syncwarp() only.  Less
+// register state per thread => ~2.5x the resident warps of the 4096-point kernel, which is
+// what keeps the FMA pipe fed; the price is a shorter hop (1024 - (K-1)), so it is used for
+// the shorter tap counts (fir_os_launch).
+struct FirOs32Args {
+    const void *in;
+    void *out;
+    const void *hf;     // [nchan][1024] spectrum of the taps / 1024
+    const void *tw;     // [32][32] W1024^(j*t)
+    long long n_in, n_out;             // per channel
+    long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
+    int nchan;
+    int K;
+};
 
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
@@ -327,13 +327,16 @@ struct FirOs32GArgs {
 };
 
 // one 1024-point transform of the warp's 32 x 32 register tile through its shared-memory tile
-template <bool INV>
+template <bool INV, bool PT = false>
 __device__ __forceinline__ void fft1024_fwd(c2 (&v)[32], c2 *F, const c2 *__restrict__ tw, const int t)
 {
-    // in: v[rev32(n1)] = x[32 n1 + t]; out: v[k2] = X[t + 32 k2]
+    // in: v[rev32(n1)] = x[32 n1 + t]; out: v[k2] = X[t + 32 k2]   (PT: ten loaded twiddles instead of 31)
     dft32_dit<INV>(v);
+    if constexpr (PT) twiddle32<INV, false>(v, tw, t);
+    else {
 #pragma unroll
-    for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<INV>(v[k1], tw[k1 * 32 + t]);
+        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<INV>(v[k1], tw[k1 * 32 + t]);
+    }
     __syncwarp();
 #pragma unroll
     for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
@@ -342,12 +345,16 @@ __device__ __forceinline__ void fft1024_fwd(c2 (&v)[32], c2 *F, const c2 *__rest
     for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
     dft32_dit<INV>(v);
 }
+template <bool PT = false>
 __device__ __forceinline__ void fft1024_inv(c2 (&v)[32], c2 *F, const c2 *__restrict__ tw, const int t)
 {
     // in: v[k2] = X[t + 32 k2]; out: v[rev32(n1)] = x[32 n1 + t] (unnormalised inverse)
     dft32_dif<true>(v);
+    if constexpr (PT) twiddle32<true, true>(v, tw, t);
+    else {
 #pragma unroll
-    for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+        for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+    }
     __syncwarp();
 #pragma unroll
     for (int n2 = 0; n2 < 32; n2++) F[t * kOs32Stride + n2] = v[rev32(n2)];
@@ -570,6 +577,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fir_osp_kernel(const FirOs32GAr
 // spectra and twiddles in shared memory.  In fir_osp_kernel those are global loads through an L1
 // that 5 x 42 KB of shared memory had shrunk to 40 KB: 37 % hit rate, long-scoreboard stalls
 // (profiles/r01d_prof_osp_c3.txt).  Groups synchronise on their own named barriers.
+#ifndef B200C_OSPG_PARTIAL_TW
+#define B200C_OSPG_PARTIAL_TW 1
+#endif
+constexpr bool kOspgPartialTwiddles = B200C_OSPG_PARTIAL_TW != 0;
+
 template <int NW, int G>
 __global__ void __launch_bounds__(32 * NW * G, 1) fir_ospg_kernel(const FirOs32GArgs a, const int M)
 {
@@ -604,7 +616,7 @@ __global__ void __launch_bounds__(32 * NW * G, 1) fir_ospg_kernel(const FirOs32G
                 const long long ia = s0 + (long long)(32 * n1 + t) * M;
                 v[rev32(n1)] = (inner || (ia >= 0 && ia < a.n_in)) ? __ldg(in + ia) : 0ull;
             }
-            fft1024_fwd<false>(v, F, tws, t);
+            fft1024_fwd<false, kOspgPartialTwiddles>(v, F, tws, t);
             __syncwarp();
 #pragma unroll
             for (int k2 = 0; k2 < 32; k2++) F[32 * k2 + t] = v[k2];
@@ -626,7 +638,7 @@ __global__ void __launch_bounds__(32 * NW * G, 1) fir_ospg_kernel(const FirOs32G
                     v[k2] = fma2(b, pk(hx, hx), fma2(pk(-fy, fx), pk(hy, hy), v[k2]));
                 }
             }
-            fft1024_inv(v, plane, tws, t);
+            fft1024_inv<kOspgPartialTwiddles>(v, plane, tws, t);
             __syncwarp();
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) plane[32 * n1 + t] = v[rev32(n1)];
