@@ -48,6 +48,7 @@ struct FirOsPlan {
     bool general = false;     // polyphase / real-data kernel
     bool real = false;        // float32 data: two stream blocks per complex transform
     bool osp = false;         // general: the multi-warp resampler kernel (fir_osp_kernel) serves it
+    int ospg = 0;             // > 0: its grouped form (fir_ospg_kernel) with this many groups per CTA
     int N = 4096;             // transform length in use
     int K = 0;                // L = M = 1 kernels: taps; general: K = ceil(ntaps / L)
     int M = 1, L = 1;

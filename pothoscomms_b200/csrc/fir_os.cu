@@ -828,7 +828,17 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
         if (!force && per_phase < min_taps) return B200C_OK;
         if (ntaps < 2) return B200C_OK;
         p.osp = osp;
-        return configure_general(p, dtype == B200C_F32, taps, ntaps, complex_taps, M, L);
+        p.ospg = 0;
+        const int rc = configure_general(p, dtype == B200C_F32, taps, ntaps, complex_taps, M, L);
+        if (rc == B200C_OK && p.ready && p.osp) {
+            // grouped form: G groups + one copy of the tap spectra and twiddles must fit 227 KB
+            static const bool no_group = [] { const char *e = std::getenv("B200C_OSPG"); return e && std::atoi(e) == 0; }();
+            const int nw = (int)std::max(L, M), G = nw == 2 ? 6 : nw == 3 ? 4 : 3;
+            const size_t group = sizeof(c2) * ((size_t)M * kOs32SmemElems + (size_t)L * osp_plane_stride((int)L));
+            const size_t tables = sizeof(c2) * ((size_t)L * M * 1024 + 1024);
+            if (!no_group && tables + G * group <= 227 * 1024) p.ospg = G;
+        }
+        return rc;
     }
     return B200C_OK;
 }
@@ -845,7 +855,7 @@ void fir_os_destroy(FirOsPlan &p)
 
 const char *fir_os_kernel_name(const FirOsPlan &p)
 {
-    if (p.general) return p.osp ? "fir_osp_kernel" : "fir_os32g_kernel";
+    if (p.general) return p.osp ? (p.ospg ? "fir_ospg_kernel" : "fir_osp_kernel") : "fir_os32g_kernel";
     return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
 }
 
@@ -914,12 +924,11 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
             const int nw = std::max(p.L, p.M);
             const size_t smem = sizeof(c2) * ((size_t)p.M * kOs32SmemElems + (size_t)p.L * osp_plane_stride(p.L));
             const long long nblk = ((long long)nq + p.hopq - 1) / p.hopq;
-            // grouped variant (tap spectra + twiddles once per SM in shared memory) when 4 / 3 groups fit
-            static const bool no_group = [] { const char *e = std::getenv("B200C_OSPG"); return e && std::atoi(e) == 0; }();
-            const size_t shared_tab = sizeof(c2) * ((size_t)p.L * p.M * 1024 + 1024), limit = 227 * 1024;
-            if (!no_group && nw == 3 && shared_tab + 4 * smem <= limit) launch_ospg<3, 4>(a, p.M, shared_tab + 4 * smem, nblk, sm_count, stream);
-            else if (!no_group && nw == 2 && shared_tab + 6 * smem <= limit) launch_ospg<2, 6>(a, p.M, shared_tab + 6 * smem, nblk, sm_count, stream);
-            else if (!no_group && nw == 4 && shared_tab + 3 * smem <= limit) launch_ospg<4, 3>(a, p.M, shared_tab + 3 * smem, nblk, sm_count, stream);
+            // grouped variant (tap spectra + twiddles once per SM in shared memory) when its groups fit
+            const size_t shared_tab = sizeof(c2) * ((size_t)p.L * p.M * 1024 + 1024);
+            if (p.ospg && nw == 3) launch_ospg<3, 4>(a, p.M, shared_tab + 4 * smem, nblk, sm_count, stream);
+            else if (p.ospg && nw == 2) launch_ospg<2, 6>(a, p.M, shared_tab + 6 * smem, nblk, sm_count, stream);
+            else if (p.ospg && nw == 4) launch_ospg<4, 3>(a, p.M, shared_tab + 3 * smem, nblk, sm_count, stream);
             else if (nw == 2) launch_osp<2, 7>(a, p.M, smem, nblk, sm_count, stream);
             else if (nw == 3) launch_osp<3, 5>(a, p.M, smem, nblk, sm_count, stream);
             else launch_osp<4, 3>(a, p.M, smem, nblk, sm_count, stream);
