@@ -70,6 +70,7 @@ constexpr size_t kFirOs1kMaxTaps = 448;       // measured crossover of the 1024-
 // path): real float32 streams, and resamplers where the direct kernel still wins for short phases
 constexpr size_t kFirOsAutoMinTapsReal = 8;
 constexpr size_t kFirOsAutoMinTapsResamp = 24;
+constexpr size_t kFirOsAutoMinTapsOsp = 16;       // complex float32 resamplers served by fir_osp(g)_kernel
 constexpr long long kFirOsGenMaxSpan = 400;   // general kernel: keep hop >= ~60 % of the block
 constexpr size_t kFirOsGenMaxInterp = 64;
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
