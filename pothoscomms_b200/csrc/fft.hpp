@@ -49,6 +49,7 @@ struct FirOsPlan {
     bool real = false;        // float32 data: two stream blocks per complex transform
     bool osp = false;         // general: the multi-warp resampler kernel (fir_osp_kernel) serves it
     int ospg = 0;             // > 0: its grouped form (fir_ospg_kernel) with this many groups per CTA
+    bool real32 = false;      // float32 data, L = M = 1: fir_os32r_kernel (two blocks per transform)
     int N = 4096;             // transform length in use
     int K = 0;                // L = M = 1 kernels: taps; general: K = ceil(ntaps / L)
     int M = 1, L = 1;
@@ -62,7 +63,7 @@ struct FirOsPlan {
     void *d_H = nullptr;      // general: [L*M][1024] float2 tap-phase spectra / 1024
     size_t H_floats = 0;
     // output blocks q covered by one kernel block (host-buffer chunking aligns to this)
-    int hop() const { return general ? hopq * (real ? 2 : 1) : N - (K - 1); }
+    int hop() const { return general ? hopq * (real ? 2 : 1) : (N - (K - 1)) * (real32 ? 2 : 1); }
 };
 constexpr size_t kFirOsMaxTaps = 2049;
 constexpr size_t kFirOs1kMaxTaps = 448;       // measured crossover of the 1024- and 4096-point kernels

@@ -305,6 +305,114 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     }
 }
 
+// ------------------------------------------------------- real float32 data, L = M = 1 ---
+// float32 streams carry REAL taps only (filter/FIRFilter.cpp:373-376), so the filter is real and
+// linear: two consecutive stream blocks ride in one complex transform, z = x_A + i x_B gives
+// Re = y_A, Im = y_B.  Same warp-per-transform structure as fir_os32_kernel; the two blocks overlap in
+// the input (hop < 1024), so ONE bulk copy of hop + 1024 floats feeds both.
+struct FirOs32RArgs {
+    const float *in;
+    float *out;
+    const void *hf;     // [1024] spectrum of the taps / 1024
+    const void *tw;     // [32][32] W1024^(j*t)
+    long long n_in, n_out;
+    int K;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) fir_os32r_kernel(const FirOs32RArgs a)
+{
+    __shared__ __align__(16) c2 F[kOs32SmemElems];
+    __shared__ __align__(8) unsigned long long bar;
+    const float *Ff = reinterpret_cast<const float *>(F);
+    const int t = threadIdx.x;
+    const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
+    const int Km1 = a.K - 1, hop = 1024 - Km1;
+    const long long npair = (a.n_out + 2LL * hop - 1) / (2LL * hop);
+    // pair bp: block A = inputs [base, base + 1024), block B = [base + hop, base + hop + 1024), base = 2 hop bp
+    auto bulk_src = [&](long long bp, const float *&src, int &mis, unsigned &bytes) {
+        if (bp >= npair) return false;
+        const long long base = bp * 2LL * hop;
+        mis = (int)(((reinterpret_cast<unsigned long long>(a.in) >> 2) + base) & 3);
+        const int count = (mis + hop + 1024 + 3) & ~3;       // floats, a multiple of 16 bytes, <= 2052
+        src = a.in + (base - mis);
+        bytes = (unsigned)count * 4u;
+        return base - mis >= 0 && base - mis + count <= a.n_in;
+    };
+    if (t == 0) mbar_init(&bar, 1);
+    __syncwarp();
+    long long bp = blockIdx.x;
+    const float *src = nullptr;
+    int mis = 0, mis_next = 0;
+    unsigned bytes = 0;
+    bool pending = bulk_src(bp, src, mis, bytes);
+    if (pending && t == 0) bulk_load(F, src, bytes, &bar);
+    unsigned parity = 0;
+    while (bp < npair) {
+        const long long base = bp * 2LL * hop, nbp = bp + gridDim.x;
+        c2 v[32];
+        if (pending) {
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = pk(Ff[mis + 32 * n1 + t], Ff[mis + hop + 32 * n1 + t]);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const long long ga = base + 32 * n1 + t, gb = ga + hop;
+                v[rev32(n1)] = pk(ga < a.n_in ? __ldg(a.in + ga) : 0.f, gb < a.n_in ? __ldg(a.in + gb) : 0.f);
+            }
+        }
+        dft32_dit<false>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
+        dft32_dit<false>(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(v[k2], hf[32 * k2 + t]);
+        dft32_dif<true>(v);
+#pragma unroll
+        for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) F[t * kOs32Stride + n2] = v[rev32(n2)];
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
+        __syncwarp();                                        // the tile is free: fetch the next pair into it
+        pending = bulk_src(nbp, src, mis_next, bytes);
+        if (pending && t == 0) bulk_load(F, src, bytes, &bar);
+        dft32_dif<true>(v);
+        // circular results c[i], i = 32 n1 + t >= K-1: Re -> y[base + i - (K-1)], Im -> y[base + hop + i - (K-1)]
+        float *oa = a.out + (base - Km1), *ob = oa + hop;
+        if (base + 2LL * hop <= a.n_out) {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const int i = 32 * n1 + t;
+                float ya, yb;
+                upk(v[rev32(n1)], ya, yb);
+                if (i >= Km1) { __stcg(oa + i, ya); __stcg(ob + i, yb); }
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const int i = 32 * n1 + t;
+                float ya, yb;
+                upk(v[rev32(n1)], ya, yb);
+                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(oa + i, ya);
+                if (i >= Km1 && base + hop + i - Km1 < a.n_out) __stcg(ob + i, yb);
+            }
+        }
+        bp = nbp; mis = mis_next;
+    }
+}
+
 // ------------------------------------------------- polyphase / real-data generalisation ---
 // The reference's resampling nest (filter/FIRFilter.cpp:286-302) in polyphase form (fir.hpp):
 //   y[q L + p] = sum_e sum_a g_{p,e}[a] * x_e[q + a],   x_e[i] = x[i M + e],  a in [a_min, a_max]
@@ -790,7 +898,7 @@ static int configure_general(FirOsPlan &p, bool real_data, const double *taps, s
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
                      bool force)
 {
-    p.ready = false; p.general = false; p.real = false; p.osp = false;
+    p.ready = false; p.general = false; p.real = false; p.osp = false; p.real32 = false;
     if (dtype == B200C_CF32 && M == 1 && L == 1) {
         // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up
         if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
@@ -816,6 +924,21 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
             if ((rc = upload(&p.d_hf1k, hf))) return rc;
         }
         p.K = (int)ntaps;
+        p.ready = true;
+        return B200C_OK;
+    }
+    if (dtype == B200C_F32 && M == 1 && L == 1 && !complex_taps && ntaps >= 2 && ntaps <= kFirOs1kMaxTaps &&
+        !(std::getenv("B200C_OS32R") && std::atoi(std::getenv("B200C_OS32R")) == 0)) {
+        // real float32 stream: two blocks per complex 1024-point transform (fir_os32r_kernel)
+        std::vector<float> tb, hf;
+        int rc;
+        if (!p.d_tw1k) {
+            unit_root_table(tb, 1024, 32, 32, 1);
+            if ((rc = upload(&p.d_tw1k, tb))) return rc;
+        }
+        taps_spectrum(hf, 1024, taps, ntaps, false);
+        if ((rc = upload(&p.d_hf1k, hf))) return rc;
+        p.N = 1024; p.K = (int)ntaps; p.real32 = true;
         p.ready = true;
         return B200C_OK;
     }
@@ -856,6 +979,7 @@ void fir_os_destroy(FirOsPlan &p)
 const char *fir_os_kernel_name(const FirOsPlan &p)
 {
     if (p.general) return p.osp ? (p.ospg ? "fir_ospg_kernel" : "fir_osp_kernel") : "fir_os32g_kernel";
+    if (p.real32) return "fir_os32r_kernel";
     return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
 }
 
@@ -946,6 +1070,17 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         if (p.M == 1) return p.real ? OSG(1, true, 12, 10) : OSG(1, false, 12, 10);
         return p.real ? OSG(2, true, 10, 8) : OSG(2, false, 10, 8);
 #undef OSG
+    }
+    if (p.real32) {
+        if (batch) { set_error("filter bank: the batched launch serves complex float32 L = M = 1 only"); return B200C_ERR_UNSUPPORTED; }
+        FirOs32RArgs a;
+        a.in = static_cast<const float *>(d_in); a.out = static_cast<float *>(d_out); a.hf = p.d_hf1k; a.tw = p.d_tw1k;
+        a.n_in = (long long)in_elems; a.n_out = (long long)nq; a.K = p.K;
+        const long long npair = ((long long)nq + p.hop() - 1) / p.hop();
+        const int grid = (int)std::min<long long>(npair, (long long)sm_count * 12 * 4);
+        fir_os32r_kernel<12><<<grid, 32, 0, stream>>>(a);
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
     }
     const size_t n_out = nq;
     const long long nblk = (((long long)n_out + p.hop() - 1) / p.hop()) * nchan;

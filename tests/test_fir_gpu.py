@@ -392,7 +392,8 @@ def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type
             y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, zero_tail=zero_tail)
             with _with_algo("fft"):
                 y_os, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
-                assert f.kernel in (("fir_ospg_kernel", "fir_osp_kernel") if osp else ("fir_os32g_kernel",)), f.kernel
+                expect = ("fir_ospg_kernel", "fir_osp_kernel") if osp else ("fir_os32r_kernel",) if (dt, M, L) == ("F32", 1, 1) else ("fir_os32g_kernel",)
+                assert f.kernel in expect, f.kernel
             assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
             _compare(oracle, code, y_os, y_ref, f"os32g {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
             with _with_algo("direct"):
@@ -600,3 +601,40 @@ def test_ummap_polyphase_is_bit_exact(oracle, cuda_device, dt, taps_type, M, L):
             assert f.kernel == "fir_ummap_kernel", f.kernel
             assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
             _compare(oracle, code, y, y_ref, f"ummap {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}")
+
+
+@pytest.mark.parametrize("ntaps", [2, 5, 16, 64, 65, 255, 448])
+def test_real_float32_overlap_save_kernel(oracle, cuda_device, ntaps):
+    """float32 streams (REAL taps, L = M = 1) take fir_os32r_kernel: two stream blocks per complex
+    transform (z = x_A + i x_B).  Ragged lengths around the pair hop, odd block counts (a lone block A),
+    tiny inputs, the zero tail, unaligned base pointers; against the oracle and the direct kernel."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    rng = np.random.default_rng(ntaps * 5 + 1)
+    taps = rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    hop = 1024 - (ntaps - 1)
+    rms_hint = float(np.sqrt(np.sum(taps ** 2)))
+    for n_new, zero_tail in ((1, False), (hop, False), (hop + 1, False), (2 * hop, False), (2 * hop + 1, False), (7 * hop + 13, False),
+                             (200003, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, oracle.F32, ntaps - 1 + n_new, rng)
+        y_ref, c_ref, p_ref = oracle.fir(oracle.F32, False, taps, 1, 1, x, zero_tail=zero_tail)
+        y, cons, prod, f = _run_gpu(oracle.F32, "REAL", taps, 1, 1, x, zero_tail=zero_tail)
+        assert f.kernel == "fir_os32r_kernel", f.kernel
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, oracle.F32, y, y_ref, f"os32r K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
+    with _with_algo("direct"):
+        y_d, _, _, f = _run_gpu(oracle.F32, "REAL", taps, 1, 1, x, zero_tail=zero_tail)
+        assert f.kernel == "fir_tile_kernel"
+    _compare(oracle, oracle.F32, y_d, y_ref, "direct", rms_hint)
+    # base pointers shifted by 1..3 floats: the bulk copy re-aligns, guarded loads cover the edges
+    x = _rand_input(oracle, oracle.F32, 30000, rng)
+    y_ref, _, _ = oracle.fir(oracle.F32, False, taps, 1, 1, x)
+    f = FirFilter(oracle.F32, "REAL")
+    f.set_taps(taps)
+    xd = torch.from_numpy(x).cuda()
+    for off in (1, 2, 3):
+        shifted = torch.empty((x.shape[0] + off, 1), dtype=xd.dtype, device="cuda")
+        shifted[off:] = xd
+        y, _, prod = f.run(shifted[off:])
+        torch.cuda.synchronize()
+        _compare(oracle, oracle.F32, y.cpu().numpy()[:prod], y_ref, f"os32r unaligned {off}", rms_hint)
