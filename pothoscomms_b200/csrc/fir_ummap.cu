@@ -35,6 +35,7 @@ struct FirUmmaPArgs {
     int PL, PLa;         // plane bytes in use (2048 + 32 NB) / allocated (multiple of 128)
     int R, nstage;       // landing ring depth; accumulator stages: 1 or 2
     int pstage;          // plane stages: 2 (staging overlaps the MMAs) unless shared memory is short
+    long long *dbg;      // optional [grid][8] barrier-wait cycle counters of the roles (B200C_UMMA_DBG)
 };
 
 constexpr int kUPTile = 2048;      // blocks q per tile: 128 rows x 16
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     auto bulk_ok = [&](long long tile) { return al && (tile * kUPTile + PL) * M <= a.n_in; };
     // accumulator stage / phase of the i-th tile of this CTA for an NS-deep ring; the planes are their
     // own ring (2-deep when shared memory allows) so that staging tile i+1 overlaps the MMAs of tile i
+    long long w0 = 0, w1 = 0;
+    const long long t_begin = clock64();
     auto stage_of = [&](int i, int &s, unsigned &ph) { s = NS == 2 ? (i & 1) : 0; ph = (unsigned)(NS == 2 ? (i >> 1) : i) & 1; };
 
     if (warp == kUPEpiWarps + kUPStageWarps + 1) {
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
         if (lane == 0)
             for (int i = 0, r = 0, ph = 0; i < ntl; i++) {
                 const long long tile = first + (long long)i * step;
-                mbar_wait(&raw_empty[r], (unsigned)ph ^ 1);
+                timed_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
                 if (bulk_ok(tile))
                     bulk_load(raw + (size_t)r * raw_bytes, static_cast<const unsigned char *>(a.in) + (size_t)tile * kUPTile * M * ESZ,
                               (unsigned)raw_bytes, &raw_full[r]);
@@ -110,8 +113,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
                 stage_of(i, s, ph);
                 const int sp = NP == 2 ? (i & 1) : 0;
                 const unsigned php = (unsigned)(NP == 2 ? (i >> 1) : i) & 1;
-                mbar_wait(&planes_full[sp], php);
-                mbar_wait(&acc_empty[s], ph ^ 1);
+                timed_wait(&planes_full[sp], php, w0);
+                timed_wait(&acc_empty[s], ph ^ 1, w1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned planes_s = smem_u32(planes + (size_t)sp * stage_bytes);
 #pragma unroll
@@ -148,8 +151,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
             const long long tile = first + (long long)i * step;
             const long long e0 = tile * kUPTile * M;                  // first buffer element of the tile's window
             const bool landed = bulk_ok(tile);
-            mbar_wait(&raw_full[r], (unsigned)rph);
-            mbar_wait(&planes_empty[s], ph ^ 1);
+            timed_wait(&raw_full[r], (unsigned)rph, w0);
+            timed_wait(&planes_empty[s], ph ^ 1, w1);
             unsigned *pl = reinterpret_cast<unsigned *>(planes + (size_t)s * stage_bytes);
             const unsigned char *rw = raw + (size_t)r * raw_bytes;
             for (int c = st; c < nchunk; c += NST) {
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
             int s; unsigned ph;
             stage_of(i, s, ph);
             const long long tile = first + (long long)i * step, orow = (tile * kUPTile + 16LL * m) * L;
-            mbar_wait(&acc_full[s], ph);
+            timed_wait(&acc_full[s], ph, w0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int c = c0; c < c1; c++) {
@@ -275,6 +278,13 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
                 }
             }
         }
+    }
+    if (a.dbg && lane == 0) {
+        long long *d = a.dbg + (size_t)blockIdx.x * 8;
+        if (warp == 0) { d[0] = clock64() - t_begin; d[1] = ntl; d[7] = w0; }
+        if (warp == kUPEpiWarps) { d[5] = w0; d[6] = w1; }
+        if (warp == kUPEpiWarps + kUPStageWarps) { d[3] = w0; d[4] = w1; }
+        if (warp == kUPEpiWarps + kUPStageWarps + 1) d[2] = w0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -374,8 +384,23 @@ static int launch_up(FirUmmaPArgs a, int sm_count, cudaStream_t stream)
     a.R = (int)std::max<size_t>(2, std::min<size_t>(kUPMaxRing, (216 * 1024 - fixed) / one));
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);   // > half an SM: one CTA per SM (tensor memory)
     const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
+    static const bool dbg = std::getenv("B200C_UMMA_DBG") != nullptr;
+    if (dbg) {
+        B200C_CUDA_TRY(cudaMalloc(&a.dbg, (size_t)grid * 8 * sizeof(long long)));
+        B200C_CUDA_TRY(cudaMemset(a.dbg, 0, (size_t)grid * 8 * sizeof(long long)));
+    }
     kern<<<grid, kUPThreads, smem, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
+    if (dbg) {
+        std::vector<long long> h((size_t)grid * 8);
+        B200C_CUDA_TRY(cudaStreamSynchronize(stream));
+        B200C_CUDA_TRY(cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.dbg);
+        double s8[8] = {0};
+        for (int g = 0; g < grid; g++) for (int k = 0; k < 8; k++) s8[k] += (double)h[(size_t)g * 8 + k] / grid;
+        std::fprintf(stderr, "ummap: cycles/tile %.0f | issuer wait raw_empty %.0f | mma wait planes_full %.0f acc_empty %.0f | stager wait raw_full %.0f planes_empty %.0f | epilogue wait acc_full %.0f (tiles/CTA %.1f, R %d, N %d, NB %d, acc stages %d, plane stages %d)\n",
+                     s8[0] / s8[1], s8[2] / s8[1], s8[3] / s8[1], s8[4] / s8[1], s8[5] / s8[1], s8[6] / s8[1], s8[7] / s8[1], s8[1], a.R, a.N, a.NB, a.nstage, a.pstage);
+    }
     return B200C_OK;
 }
 
@@ -387,7 +412,7 @@ int fir_ummap_launch(const FirUmmaPPlan &p, const void *d_in, size_t in_elems, v
     a.n_in = (long long)in_elems; a.nq = (long long)nq;
     a.ntiles = ((long long)nq + kUPTile - 1) / kUPTile;
     a.L = p.L; a.M = p.M; a.NB = p.NB; a.N = p.N;
-    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage; a.pstage = p.pstage;
+    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage; a.pstage = p.pstage; a.dbg = nullptr;
     return p.dc == 1 ? launch_up<1>(a, sm_count, stream) : launch_up<2>(a, sm_count, stream);
 }
 
