@@ -65,6 +65,15 @@ int b200c_rotate(int dtype, double phase, const void *d_in, void *d_out, size_t 
  * RMS).  Synchronous: the result is on the host when the call returns. */
 enum b200c_probe_mode { B200C_PROBE_VALUE = 0, B200C_PROBE_RMS = 1, B200C_PROBE_MEAN = 2 };
 int b200c_probe(int dtype, int mode, const void *d_in, size_t elems, double *value, int device, void *stream);
+/* The work() loops of /comms/waveform_source and /comms/noise_source (fast mode):
+ *   out[i] = table[(index + i*step) & (table_elems - 1)],  i < elems
+ * waveform/WaveformSource.cpp:98-108 (step = _step, the caller then advances _index by elems*step)
+ * and waveform/NoiseSource.cpp:108-117 (step = 1, 4096 entries).  d_table: table_elems elements of
+ * `dtype` in DEVICE memory, filled by the block layer as updateTable() does (WaveformSource.cpp:184-260,
+ * NoiseSource.cpp:188-226); table_elems must be a power of two (the reference's mask) else
+ * B200C_ERR_INVALID.  Every row of the two factories (all twelve types).  Asynchronous on `stream`. */
+int b200c_table_source(int dtype, const void *d_table, size_t table_elems, uint64_t index, uint64_t step, void *d_out,
+                       size_t elems, int device, void *stream);
 
 /* ------------------------------------------------------------------ /comms/fir_filter --- */
 typedef struct b200c_fir b200c_fir;

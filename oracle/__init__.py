@@ -43,7 +43,7 @@ def is_complex(dtype_code: int) -> bool:
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
     lib = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "math_oracle.c", "qformat.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "math_oracle.c", "source_oracle.cpp", "qformat.h", "Makefile")]
     stale = force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
     ref = os.path.join(_HERE, "_ref", "libkissref.so")
     if stale or (not os.path.exists(ref) and os.path.exists("/root/reference/fft/kiss_fft.c")):
@@ -70,6 +70,11 @@ def lib():
         _lib.oracle_scale.argtypes = [i, ctypes.c_double, vp, vp, sz]
         _lib.oracle_rotate.argtypes = [i, ctypes.c_double, vp, vp, sz]
         _lib.oracle_probe.argtypes = [i, i, vp, sz, vp]
+        d, u64 = ctypes.c_double, ctypes.c_uint64
+        _lib.oracle_waveform_table.argtypes = [i, ctypes.c_char_p, d, d, d, d, d, d, d, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(u64)]
+        _lib.oracle_table_walk.argtypes = [i, vp, sz, u64, u64, vp, sz]
+        _lib.oracle_table_walk.restype = None
+        _lib.oracle_noise_stream.argtypes = [i, ctypes.c_char_p, d, d, d, d, d, d, ctypes.c_uint32, vp, vp, sz, vp, vp]
     return _lib
 
 
@@ -216,3 +221,44 @@ def probe(dtype_code: int, mode: str, x_raw: np.ndarray) -> complex:
     rc = lib().oracle_probe(dtype_code, PROBE_MODES[mode], x.ctypes.data, x.shape[0], ctypes.addressof(v))
     assert rc == 0
     return complex(v[0], v[1])
+
+
+# ------------------------------------------------- stream sources ---
+def waveform_table(dtype_code: int, wave: str, freq: float, rate: float, res: float = 0.0, ampl: complex = 1.0,
+                   offset: complex = 0.0):
+    """WaveformSource::updateTable() (waveform/WaveformSource.cpp:184-260): (raw table [entries, ncomp], step).
+    Raises ValueError where the reference throws InvalidArgumentException."""
+    ampl, offset = complex(ampl), complex(offset)
+    nc = 2 if is_complex(dtype_code) else 1
+    table = np.zeros((1 << 20, nc), dtype=scalar_np(dtype_code))
+    entries, step = ctypes.c_size_t(0), ctypes.c_uint64(0)
+    rc = lib().oracle_waveform_table(dtype_code, wave.encode(), freq, rate, res, ampl.real, ampl.imag, offset.real, offset.imag,
+                                     table.ctypes.data, table.shape[0], ctypes.byref(entries), ctypes.byref(step))
+    if rc:
+        raise ValueError(f"WaveformSource::updateTable(): invalid setting ({wave}, freq={freq}, rate={rate})")
+    return table[: entries.value].copy(), step.value
+
+
+def table_walk(dtype_code: int, table_raw: np.ndarray, index: int, step: int, n: int) -> np.ndarray:
+    """WaveformSource::work() (waveform/WaveformSource.cpp:98-108): out[i] = table[(index + i*step) & mask]."""
+    t = np.ascontiguousarray(table_raw)
+    out = np.empty((n, t.shape[1]), dtype=t.dtype)
+    lib().oracle_table_walk(dtype_code, t.ctypes.data, t.shape[0], index & (2**64 - 1), step & (2**64 - 1), out.ctypes.data, n)
+    return out
+
+
+def noise_stream(dtype_code: int, wave: str, mean: float, b: float, seed: int, work_elems, refill_before=None,
+                 ampl: complex = 1.0, offset: complex = 0.0):
+    """A NoiseSource (waveform/NoiseSource.cpp) seeded with `seed`: activate(), then one work() per entry of
+    work_elems (a setter call first where refill_before[w] is set).  Returns (stream [sum, ncomp], table [4096, ncomp])."""
+    ampl, offset = complex(ampl), complex(offset)
+    nc = 2 if is_complex(dtype_code) else 1
+    we = np.ascontiguousarray(work_elems, dtype=np.uintp)
+    rb = np.ascontiguousarray(refill_before if refill_before is not None else np.zeros(we.size), dtype=np.int32)
+    out = np.empty((int(we.sum()), nc), dtype=scalar_np(dtype_code))
+    table = np.empty((4096, nc), dtype=scalar_np(dtype_code))
+    rc = lib().oracle_noise_stream(dtype_code, wave.encode(), mean, b, ampl.real, ampl.imag, offset.real, offset.imag, seed,
+                                   we.ctypes.data, rb.ctypes.data, we.size, out.ctypes.data, table.ctypes.data)
+    if rc:
+        raise ValueError(f"NoiseSource::setWaveform({wave}): unknown waveform setting")
+    return out, table

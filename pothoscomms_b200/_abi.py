@@ -34,6 +34,7 @@ SYMBOLS = {
     "b200c_scale": (_i, [_i, ctypes.c_double, _vp, _vp, _sz, _i, _vp]),
     "b200c_rotate": (_i, [_i, ctypes.c_double, _vp, _vp, _sz, _i, _vp]),
     "b200c_probe": (_i, [_i, _i, _vp, _sz, ctypes.POINTER(ctypes.c_double), _i, _vp]),
+    "b200c_table_source": (_i, [_i, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64, _vp, _sz, _i, _vp]),
     "b200c_fir_create": (_i, [_pvp, _i, _i, _i]),
     "b200c_fir_destroy": (_i, [_vp]),
     "b200c_fir_set_taps": (_i, [_vp, _vp, _sz]),

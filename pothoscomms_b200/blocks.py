@@ -82,6 +82,8 @@ def lib():
         L.b200c_blk_connect_signal.argtypes = [vp, cp, vp, cp]
         L.b200c_blk_last_signal.argtypes = [vp, cp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(i), ctypes.POINTER(sz)]
         L.b200c_blk_has_signal.argtypes = [vp, cp]
+        L.b200c_blk_call_complex.argtypes = [vp, cp, ctypes.c_double, ctypes.c_double]
+        L.b200c_blk_run_source.argtypes = [vp, sz, sz]
         _lib = L
     return _lib
 
@@ -101,12 +103,14 @@ def registry_has(path: str) -> bool:
 
 _SIZE_SETTERS = {"setDecimation", "setInterpolation", "setWindow"}
 _BOOL_SETTERS = {"setWaitTaps", "setInverse"}
-_STRING_SETTERS = {"setFrameStartId", "setFrameEndId", "setLabelId", "setMode"}
-_DOUBLE_SETTERS = {"setFactor", "setPhase", "setRate"}
+_STRING_SETTERS = {"setFrameStartId", "setFrameEndId", "setLabelId", "setMode", "setWaveform"}
+_DOUBLE_SETTERS = {"setFactor", "setPhase", "setRate", "setFrequency", "setSampleRate", "setResolution", "setMean", "setB"}
+_COMPLEX_SETTERS = {"setOffset", "setAmplitude"}
+_COMPLEX_GETTERS = {"value", "getOffset", "getAmplitude"}
 _SIZE_GETTERS = {"getDecimation", "getInterpolation", "getNumBins", "getWindow"}
 _BOOL_GETTERS = {"getWaitTaps", "getInverse"}
-_STRING_GETTERS = {"getFrameStartId", "getFrameEndId", "getLabelId", "getMode"}
-_DOUBLE_GETTERS = {"getFactor", "getPhase", "getRate"}
+_STRING_GETTERS = {"getFrameStartId", "getFrameEndId", "getLabelId", "getMode", "getWaveform"}
+_DOUBLE_GETTERS = {"getFactor", "getPhase", "getRate", "getFrequency", "getSampleRate", "getResolution", "getMean", "getB"}
 
 
 class Block:
@@ -116,7 +120,7 @@ class Block:
         self.dtype = dtype_code(dtype) if dtype in _abi.DTYPE_CODES else -1
         self.dtype_name = dtype
         status = ctypes.c_int(0)
-        if len(args) == 0:   # /comms/scale, /comms/rotate, /comms/signal_probe: factory (dtype)
+        if len(args) == 0:   # /comms/scale, /comms/rotate, /comms/signal_probe, the two sources: factory (dtype)
             self._h = lib().b200c_blk_make_dtype(path.encode(), dtype.encode(), in_bytes, out_bytes, ctypes.byref(status))
         elif len(args) == 1:   # /comms/fir_filter(dtype, tapsType)
             self._h = lib().b200c_blk_make(path.encode(), dtype.encode(), str(args[0]).encode(), 0, 0, in_bytes, out_bytes,
@@ -169,7 +173,11 @@ class Block:
             v = ctypes.c_double(0)
             _check(L.b200c_blk_get_double(self._h, n, ctypes.byref(v)))
             return v.value
-        if name == "value":   # SignalProbe::value(): double or complex<double>
+        if name in _COMPLEX_SETTERS:
+            z = complex(args[0])
+            _check(L.b200c_blk_call_complex(self._h, n, z.real, z.imag))
+            return None
+        if name in _COMPLEX_GETTERS:   # SignalProbe::value(): double or complex<double>; getOffset / getAmplitude
             v = (ctypes.c_double * 2)()
             _check(L.b200c_blk_get_complex(self._h, n, v))
             return complex(v[0], v[1])
@@ -220,6 +228,12 @@ class Block:
 
     def run(self):
         _check(lib().b200c_blk_run(self._h))
+
+    def run_source(self, nwork: int = 1, elems: int = 0) -> np.ndarray:
+        """A source block: `nwork` work() calls, each offered room for `elems` elements (0 = the whole output
+        buffer); returns everything produced."""
+        _check(lib().b200c_blk_run_source(self._h, nwork, elems))
+        return self.collect()
 
     def collect(self) -> np.ndarray:
         nc = ncomp(self.dtype)

@@ -21,6 +21,14 @@ public:
     Harness(Block *blk, int device, size_t inBytes, size_t outBytes) : _blk(blk), _device(device)
     {
         if (blk->numInputs() == 0 && blk->numOutputs() == 0) return;   // host-only block (designers): calls and signals only
+        if (blk->numInputs() == 0) {   // a source (/comms/waveform_source, /comms/noise_source): output side only
+            _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
+            if (!_outMgr) throw Exception("Harness()", "block does not provide device buffer managers");
+            BufferManagerArgs oa;
+            oa.bufferSize = outBytes; oa.numBuffers = 2;
+            _outMgr->init(oa);
+            return;
+        }
         _inMgr = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(blk->getInputBufferManager("0", b200c_blocks::kHbmDomain));
         _sink = blk->numOutputs() == 0;   // a consumer only (/comms/signal_probe): no output side
         if (!_sink) _outMgr = blk->getOutputBufferManager("0", b200c_blocks::kHbmDomain);
@@ -115,6 +123,32 @@ public:
                 _totalProduced += p;
             }
             if (c == 0 && p == 0) break;
+        }
+    }
+
+    // a source block: `nwork` calls of work(), each offered room for `elems` elements (0 = the whole slab)
+    void runSource(size_t nwork, size_t elems)
+    {
+        OutputPort *out = _blk->output(0);
+        const size_t osz = out->dtype().size();
+        for (size_t k = 0; k < nwork; k++) {
+            if (_outMgr->empty()) throw Exception("Harness::runSource()", "no output buffer");
+            out->_addr = _outMgr->front().address;
+            out->_bytes = _outMgr->front().length / osz * osz;
+            if (elems && elems * osz < out->_bytes) out->_bytes = elems * osz;
+            out->_pendingProduce = 0;
+            _blk->work();
+            _workCalls++;
+            const size_t p = out->_pendingProduce;
+            if (p > out->elements()) throw Exception("Harness::runSource()", "block over-produced");
+            if (!p) continue;
+            const size_t at = _collected.size();
+            _collected.resize(at + p * osz);
+            b200c_blocks::throwOnError(b200c_copy_d2h(_collected.data() + at, out->buffer().as<const void *>(), p * osz, _device, nullptr), "Harness::runSource()");
+            b200c_blocks::throwOnError(b200c_stream_sync(_device, nullptr), "Harness::runSource()");
+            _outMgr->pop(p * osz);
+            _outMgr->push(p * osz);
+            _totalProduced += p;
         }
     }
 
@@ -298,6 +332,11 @@ void *b200c_blk_make_noargs(const char *path, int *status)
     if (status) *status = rc;
     return h;
 }
+int b200c_blk_call_complex(void *h, const char *name, double re, double im)
+{
+    return guarded([&] { static_cast<Harness *>(h)->block()->call(name, std::complex<double>(re, im)); });
+}
+int b200c_blk_run_source(void *h, size_t nwork, size_t elems) { return guarded([&] { static_cast<Harness *>(h)->runSource(nwork, elems); }); }
 int b200c_blk_call_double(void *h, const char *name, double v) { return guarded([&] { static_cast<Harness *>(h)->block()->call(name, v); }); }
 int b200c_blk_get_double(void *h, const char *name, double *out)
 {

@@ -291,3 +291,17 @@ def probe(dtype, mode: str, d_in, stream=None) -> complex:
     _abi.check(_abi.lib().b200c_probe(code, PROBE_MODES[mode], ctypes.c_void_p(d_in.data_ptr()), n, v, d_in.device.index or 0,
                                       _stream_ptr(stream, d_in.device)))
     return complex(v[0], v[1])
+
+
+def table_source(dtype, d_table, index: int, step: int, elems: int, out=None, stream=None):
+    """The work() loop of /comms/waveform_source / /comms/noise_source: out[i] = table[(index + i*step) & mask]
+    from a CUDA table tensor of raw scalars ([entries, ncomp], entries a power of two)."""
+    import torch
+    code = dtype_code(dtype)
+    entries = _raw_cuda(d_table, code)
+    if out is None:
+        out = torch.empty((elems, ncomp(code)), dtype=d_table.dtype, device=d_table.device)
+    _abi.check(_abi.lib().b200c_table_source(code, ctypes.c_void_p(d_table.data_ptr()), entries, index & (2**64 - 1),
+                                             step & (2**64 - 1), ctypes.c_void_p(out.data_ptr()), elems,
+                                             d_table.device.index or 0, _stream_ptr(stream, d_table.device)))
+    return out

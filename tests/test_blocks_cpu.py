@@ -46,3 +46,32 @@ def test_neighbour_blocks_registry_and_factory_errors():
         blocks.make("/comms/rotate", "int16")
     with pytest.raises(blocks.PothosException):
         blocks.make("/comms/scale", "uint8")
+
+
+def test_source_blocks_registry_and_factory_errors():
+    """/comms/waveform_source + /blocks/waveform_source (waveform/WaveformSource.cpp:289-293) and
+    /comms/noise_source + /blocks/noise_source (waveform/NoiseSource.cpp:285-289): registered; a type outside the
+    twelve factory rows is rejected before any device is touched."""
+    from pothoscomms_b200 import blocks
+    for path in ("/comms/waveform_source", "/blocks/waveform_source", "/comms/noise_source", "/blocks/noise_source"):
+        assert blocks.registry_has(path), path
+    with pytest.raises(blocks.InvalidArgumentException):
+        blocks.make("/comms/waveform_source", "uint8")
+    with pytest.raises(blocks.InvalidArgumentException):
+        blocks.make("/comms/noise_source", "uint8")
+
+
+def test_table_source_argument_errors_and_loud_failure():
+    import ctypes
+    import torch
+    from pothoscomms_b200 import _abi
+    lib = _abi.lib()
+    buf = (ctypes.c_char * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.b200c_table_source(77, p, 4096, 0, 1, p, 4, 0, None) == _abi.ERR_UNSUPPORTED
+    assert lib.b200c_table_source(_abi.CF32, p, 4095, 0, 1, p, 4, 0, None) == _abi.ERR_INVALID     # mask needs a power of two
+    assert lib.b200c_table_source(_abi.CF32, p, 0, 0, 1, p, 4, 0, None) == _abi.ERR_INVALID
+    assert lib.b200c_table_source(_abi.CF32, p, 4096, 0, 1, p, 0, 0, None) == _abi.OK              # nothing to produce
+    if not torch.cuda.is_available():
+        assert lib.b200c_table_source(_abi.CF32, p, 4, 0, 1, p, 4, 0, None) == _abi.ERR_CUDA
+        assert b"no CPU fallback" in lib.b200c_last_error()

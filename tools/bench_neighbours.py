@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Stream-rate check of the HBM-resident neighbours (b200c_scale / b200c_rotate / b200c_probe):
+"""Stream-rate check of the HBM-resident neighbours (b200c_scale / b200c_rotate / b200c_probe / b200c_table_source):
 one JSON line per (op, dtype) with Msamples/s and the fraction of the measured HBM copy peak.
 Inputs (2^28 elements) are far larger than L2; CUDA-event timing over 10 launches after 3 warm-ups."""
 import json
@@ -21,14 +21,20 @@ def main():
         peak = 6650.0
     n = 1 << 28
     for op, dt in (("scale", "complex_float32"), ("scale", "complex_int16"), ("scale", "int16"), ("rotate", "complex_float32"),
-                   ("rotate", "complex_int16"), ("probe_rms", "complex_float32"), ("probe_rms", "complex_int16")):
+                   ("rotate", "complex_int16"), ("probe_rms", "complex_float32"), ("probe_rms", "complex_int16"),
+                   ("source", "complex_float32"), ("source", "complex_int16"), ("source_big_table", "complex_float32")):
         code = dtype_code(dt)
         nc, ts = ncomp(code), torch_scalar(code)
         x = (torch.randn((n, nc), device="cuda") * 1000).to(ts)
         out = torch.empty_like(x)
         esz = x.element_size() * nc
+        # a source walks a 4096-entry table (staged in shared memory) or a 2^20-entry one (gathered through L2)
+        table = x[: (1 << 20) if op == "source_big_table" else 4096].clone()
 
         def run():
+            if op.startswith("source"):
+                handles.table_source(code, table, 12345, 123, n, out=out)
+                return
             if op == "scale":
                 handles.scale(code, 0.37, x, out=out)
             elif op == "rotate":
@@ -52,7 +58,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-        bytes_per = esz * (1 if op.startswith("probe") else 2)
+        bytes_per = esz * (1 if op.startswith("probe") or op.startswith("source") else 2)
         gbs = n * bytes_per / (ms * 1e-3) / 1e9
         print(json.dumps({"op": op, "dtype": dt, "elements": n, "ms": ms, "Msamples_per_s": n / (ms * 1e-3) / 1e6,
                           "algorithmic_bytes_per_element": bytes_per, "GBps": gbs, "hbm_peak": peak, "frac": gbs / peak}))
