@@ -62,7 +62,7 @@ int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems,
 // tcgen05 polyphase resampler for int16 streams (fir_ummap.cu): L, M <= 4, 2-digit taps.
 struct FirUmmaPPlan {
     bool ready = false;
-    int L = 1, M = 1, NB = 0, N = 0, dc = 1, nstage = 1, pstage = 1;
+    int L = 1, M = 1, NB = 0, N = 0, dc = 1, nstage = 1, pstage = 1, npass = 1;
     void *d_bmat = nullptr;   // [M][dc][NB][N x 32 B] B tiles, N = 16 L dc 2
     size_t capacity = 0;
 };

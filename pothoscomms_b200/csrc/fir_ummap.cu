@@ -11,7 +11,10 @@
 //   N = 16 u x L slots x (components x 2 digits),  regions: lo / hi data limb,
 //   MMAs per tile of 2048 blocks q: 2 limbs x components x M residues x NB k-blocks.
 // A GEMM row's columns are 16 L CONSECUTIVE outputs, so the epilogue stores them as they come.
-// Two accumulator stages when 4 N <= 512 TMEM columns (L <= 2 complex), one otherwise.
+// Two accumulator stages when 4 N <= 512 TMEM columns, one otherwise (L >= 3 complex).  A tile can also be
+// computed as two column passes of N / 2 (the first / last eight output blocks of every row, the same A
+// planes against half of each B tile), each pass its own unit of a two-stage MMA -> epilogue pipeline;
+// measured slower (the MMA count doubles and an MMA costs about the same at half the width), so opt-in.
 // Warp-specialised like fir_umma32_kernel: bulk-copy issuer -> stagers -> MMA issuer -> epilogue.
 #include <algorithm>
 #include <cmath>
@@ -34,6 +37,7 @@ struct FirUmmaPArgs {
     int L, M, NB, N;     // N = 16 * L * DC * 2
     int PL, PLa;         // plane bytes in use (2048 + 32 NB) / allocated (multiple of 128)
     int R, nstage;       // landing ring depth; accumulator stages: 1 or 2
+    int npass;           // column passes per tile: 1, or 2 halves of N / 2 columns
     int pstage;          // plane stages: 2 (staging overlaps the MMAs) unless shared memory is short
     long long *dbg;      // optional [grid][8] barrier-wait cycle counters of the roles (B200C_UMMA_DBG)
 };
@@ -49,11 +53,14 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     constexpr int NQ = DC * 2, NPL = DC * 2, ESZ = DC * 2;
     constexpr int CH = 16 / NQ;                    // outputs per 16-column epilogue chunk
     const int L = a.L, M = a.M, NB = a.NB, N = a.N, PL = a.PL, PLa = a.PLa, R = a.R, NS = a.nstage;
-    const int COLS = 2 * N;                        // lo and hi regions of one stage
+    const int NPASS = a.npass, Nh = N / NPASS;     // columns of one pass
+    const int COLS = 2 * Nh;                       // lo and hi regions of one stage
     const unsigned ALLOC = (unsigned)(NS * COLS) <= 32 ? 32 : (NS * COLS) <= 64 ? 64 : (NS * COLS) <= 128 ? 128 : (NS * COLS) <= 256 ? 256 : 512;
     const size_t bm_bytes = (size_t)M * DC * NB * N * 32, stage_bytes = (size_t)M * NPL * PLa, raw_bytes = (size_t)PL * M * ESZ;
+    const int nmma_pass = 2 * M * DC * NB, nmma = NPASS * nmma_pass;  // MMAs of one column pass / of one tile
     unsigned char *bmat = smem_w;
-    unsigned char *planes = bmat + bm_bytes;                         // [NP][M][NPL][PLa]
+    uint4 *mma_tab = reinterpret_cast<uint4 *>(bmat + bm_bytes);     // [nmma] issue list of one tile (see the MMA issuer)
+    unsigned char *planes = reinterpret_cast<unsigned char *>(mma_tab) + (((size_t)nmma * 16 + 127) & ~(size_t)127);   // [NP][M][NPL][PLa]
     const int NP = a.pstage;
     unsigned char *raw = planes + NP * stage_bytes;                  // [R][PL * M * ESZ]
     __shared__ __align__(8) unsigned long long raw_full[kUPMaxRing], raw_empty[kUPMaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
@@ -62,6 +69,27 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
 
     for (size_t i = tid; i < bm_bytes / 16; i += kUPThreads)
         reinterpret_cast<uint4 *>(bmat)[i] = __ldg(static_cast<const uint4 *>(a.bmat) + i);
+    // The MMAs of a tile are the same list for every tile up to the plane stage (A start address) and the
+    // accumulator stage (D column): one 16-byte entry per MMA, in issue order (pass, limb, residue, component,
+    // k-block) -- the issuing thread then spends one shared-memory load and two adds per MMA instead of
+    // rebuilding descriptors (which, not the tensor core, set the pace: ~350 cycles per operand plane).
+    //   .x/.y = B descriptor, .z = A start-address offset from the plane stage (16-byte units),
+    //   .w = D column offset within the stage | hi limb << 16 | first MMA of its accumulator << 17
+    {
+        const unsigned long long b_base = umma_smem_desc(smem_u32(bmat), 128, 256, 0);
+        const unsigned long long kBStep = (unsigned long long)((N * 32) >> 4);
+        for (int j = tid; j < nmma; j += kUPThreads) {
+            int t = j;
+            const int b = t % NB; t /= NB;
+            const int dc = t % DC; t /= DC;
+            const int e = t % M; t /= M;
+            const int dl = t & 1, h = t >> 1;
+            const unsigned long long bd = b_base + (unsigned long long)((e * DC + dc) * NB + b) * kBStep + (unsigned long long)(h * ((Nh * 32) >> 4));
+            const unsigned a_off = (unsigned)((((e * NPL) + 2 * dc + dl) * PLa + 32 * b) >> 4);
+            const unsigned meta = (unsigned)(dl * Nh) | ((unsigned)dl << 16) | ((e == 0 && dc == 0 && b == 0) ? 1u << 17 : 0u);
+            mma_tab[j] = make_uint4((unsigned)bd, (unsigned)(bd >> 32), a_off, meta);
+        }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) {
         for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * kUPStageWarps); }
@@ -87,7 +115,8 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     // own ring (2-deep when shared memory allows) so that staging tile i+1 overlaps the MMAs of tile i
     long long w0 = 0, w1 = 0;
     const long long t_begin = clock64();
-    auto stage_of = [&](int i, int &s, unsigned &ph) { s = NS == 2 ? (i & 1) : 0; ph = (unsigned)(NS == 2 ? (i >> 1) : i) & 1; };
+    // (the unit of that ring is a column pass: u = tile index * NPASS + pass)
+    auto stage_of = [&](int u, int &s, unsigned &ph) { s = NS == 2 ? (u & 1) : 0; ph = (unsigned)(NS == 2 ? (u >> 1) : u) & 1; };
 
     if (warp == kUPEpiWarps + kUPStageWarps + 1) {
         // ================================================================ bulk-copy issuer
@@ -105,38 +134,35 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
     } else if (warp == kUPEpiWarps + kUPStageWarps) {
         // ====================================================================== MMA issuer
         if (lane == 0) {
-            const unsigned idesc_lo = umma_idesc_i8(false, N), idesc_hi = umma_idesc_i8(true, N);
-            const unsigned long long b_base = umma_smem_desc(smem_u32(bmat), 128, 256, 0);
-            const unsigned long long kBStep = (unsigned long long)((N * 32) >> 4);
+            const unsigned idesc_lo = umma_idesc_i8(false, Nh), idesc_hi = umma_idesc_i8(true, Nh);
+            // A: plane (e, dc, dl): row m = plane[16 m + 32 b ..] (SBO 128, LBO 16), start address = stage + table offset
+            const unsigned long long a_stage0 = umma_smem_desc(smem_u32(planes), 16, 128, 0);
+            const unsigned long long a_stage1 = umma_smem_desc(smem_u32(planes + stage_bytes), 16, 128, 0);
             for (int i = 0; i < ntl; i++) {
-                int s; unsigned ph;
-                stage_of(i, s, ph);
                 const int sp = NP == 2 ? (i & 1) : 0;
                 const unsigned php = (unsigned)(NP == 2 ? (i >> 1) : i) & 1;
                 timed_wait(&planes_full[sp], php, w0);
-                timed_wait(&acc_empty[s], ph ^ 1, w1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned planes_s = smem_u32(planes + (size_t)sp * stage_bytes);
-#pragma unroll
-                for (int dl = 0; dl < 2; dl++) {                       // data limb: its own accumulator region
-                    const unsigned d = tmem_base + (unsigned)(s * COLS + dl * N);
-                    const unsigned idesc = dl ? idesc_hi : idesc_lo;
-                    bool acc = false;
-                    for (int e = 0; e < M; e++)
-#pragma unroll
-                        for (int dc = 0; dc < DC; dc++) {
-                            // A: plane (e, dc, dl): row m = plane[16 m + 32 b ..] (SBO 128, LBO 16); B: tile (e, dc, b)
-                            unsigned long long ad = umma_smem_desc(planes_s + (unsigned)(((e * NPL) + 2 * dc + dl) * PLa), 16, 128, 0);
-                            unsigned long long bd = b_base + (unsigned long long)((e * DC + dc) * NB) * kBStep;
-                            for (int b = 0; b < NB; b++) {
-                                if (acc) umma_i8_acc(d, ad, bd, idesc); else umma_i8_first(d, ad, bd, idesc);
-                                acc = true;
-                                ad += 2; bd += kBStep;                 // + 32 bytes of window, next B tile
-                            }
-                        }
+                const unsigned long long a_stage = sp ? a_stage1 : a_stage0;
+                const uint4 *tab = mma_tab;
+                for (int h = 0; h < NPASS; h++) {                          // column pass: columns [h Nh, (h + 1) Nh) of every B tile
+                    int s; unsigned ph;
+                    stage_of(i * NPASS + h, s, ph);
+                    timed_wait(&acc_empty[s], ph ^ 1, w1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned d_stage = tmem_base + (unsigned)(s * COLS);
+                    uint4 cur = tab[0];
+#pragma unroll 4
+                    for (int k = 0; k < nmma_pass; k++) {
+                        const uint4 nxt = tab[k + 1 < nmma_pass ? k + 1 : k];   // loaded ahead of the MMA it follows
+                        const unsigned long long bd = ((unsigned long long)cur.y << 32) | cur.x;
+                        umma_i8(d_stage + (cur.w & 0xffffu), a_stage + cur.z, bd, (cur.w & 0x10000u) ? idesc_hi : idesc_lo, !(cur.w & 0x20000u));
+                        cur = nxt;
+                    }
+                    tab += nmma_pass;
+                    if (h == NPASS - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[sp])) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[s])) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[sp])) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[s])) : "memory");
             }
         }
     } else if (warp >= kUPEpiWarps) {
@@ -162,8 +188,16 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
                 const int nwords = 4 * M / EPW;
                 if (landed) {
                     const unsigned *src = reinterpret_cast<const unsigned *>(rw) + (size_t)c * nwords;
+                    if ((nwords & 3) == 0) {   // 128-bit loads: word loads at this 4 nwords-byte lane stride are 8-way bank conflicts
 #pragma unroll
-                    for (int j = 0; j < 16; j++) x[j] = j < nwords ? src[j] : 0u;
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 v = 4 * j < nwords ? reinterpret_cast<const uint4 *>(src)[j] : make_uint4(0, 0, 0, 0);
+                            x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) x[j] = j < nwords ? src[j] : 0u;
+                    }
                 } else {
                     const long long g0 = e0 + 4LL * c * M;
                     if constexpr (DC == 2) {
@@ -227,24 +261,26 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
         // outputs of the row's 16 L:  y = lo_d0 + ((lo_d1 + hi_d0) << 8) + (hi_d1 << 16) mod 2^32, bits [16, 32)
         const int m = 32 * (warp & 3) + lane, half = warp >> 2;
         const unsigned lane_addr = tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
-        const int nch = N / 16, c0 = half * (nch / 2), c1 = c0 + nch / 2;
+        const int nch = Nh / 16, c0 = half * (nch / 2), c1 = c0 + nch / 2;
         const long long n_out = a.nq * L;
-        for (int i = 0; i < ntl; i++) {
+        for (int u = 0; u < ntl * NPASS; u++) {
             int s; unsigned ph;
-            stage_of(i, s, ph);
-            const long long tile = first + (long long)i * step, orow = (tile * kUPTile + 16LL * m) * L;
+            stage_of(u, s, ph);
+            const int i = u / NPASS, h = u - i * NPASS;
+            // pass h holds output blocks [8 h, 8 h + 8) of the row when NPASS == 2: CH * nch outputs further on
+            const long long tile = first + (long long)i * step, orow = (tile * kUPTile + 16LL * m) * L + (long long)h * CH * nch;
             timed_wait(&acc_full[s], ph, w0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c = c0; c < c1; c++) {
-                unsigned lo[16], hi[16];
+            // chunk c + 1 is loaded from tensor memory while chunk c is combined and stored (two register sets)
+            auto load = [&](int c, unsigned (&lo)[16], unsigned (&hi)[16]) {
                 tmem_ld16(lane_addr + (unsigned)(s * COLS + 16 * c), lo);
-                tmem_ld16(lane_addr + (unsigned)(s * COLS + N + 16 * c), hi);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == c1 - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[s]);
-                }
+                tmem_ld16(lane_addr + (unsigned)(s * COLS + Nh + 16 * c), hi);
+            };
+            auto landed_all = [&] {   // every tensor-memory read of this unit is done: the stage can be overwritten
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&acc_empty[s]);
+            };
+            auto emit = [&](int c, const unsigned (&lo)[16], const unsigned (&hi)[16]) {
                 unsigned res[CH];
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
@@ -275,6 +311,19 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
                         for (int k = 0; k < CH; k++)
                             if (o + k < n_out) out16[o + k] = (unsigned short)res[k];
                     }
+                }
+            };
+            unsigned loA[16], hiA[16], loB[16], hiB[16];
+            load(c0, loA, hiA);
+#pragma unroll 1
+            for (int c = c0; c < c1; c += 2) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 1 < c1) load(c + 1, loB, hiB); else landed_all();
+                emit(c, loA, hiA);
+                if (c + 1 < c1) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c + 2 < c1) load(c + 2, loA, hiA); else landed_all();
+                    emit(c + 1, loB, hiB);
                 }
             }
         }
@@ -316,12 +365,19 @@ int fir_ummap_configure(FirUmmaPPlan &p, int dtype, const double *taps, size_t n
     const long long a_max = t_max / (long long)M;
     const int NB = (int)((15 + a_max + 1 + 31) / 32);
     const int PL = kUPTile + 32 * NB, PLa = (PL + 127) / 128 * 128;
-    const int nstage = 4 * N <= 512 ? 2 : 1;
-    const size_t bm_bytes = (size_t)M * dc * NB * N * 32, stage = (size_t)M * dc * 2 * PLa, one = (size_t)PL * M * dc * 2;
+    // Two accumulator stages of (lo, hi) regions fit the 512 tensor-memory columns when 4 N <= 512.  Beyond
+    // (L >= 3 complex) the tile keeps ONE stage: splitting it into two column passes of N / 2 (opt-in,
+    // B200C_UMMAP_NPASS=2) does overlap MMAs and epilogue but doubles the MMA count, and an MMA costs
+    // ~105 + 125 per new operand plane cycles almost independently of N: measured 199 against 256 Gsamples/s.
+    static const bool two_pass = [] { const char *e = std::getenv("B200C_UMMAP_NPASS"); return e && std::atoi(e) == 2; }();
+    const int npass = (4 * N > 512 && two_pass) ? 2 : 1;
+    const int nstage = 4 * (N / npass) <= 512 ? 2 : 1;
+    const size_t tab_bytes = ((size_t)npass * 2 * M * dc * NB * 16 + 127) & ~(size_t)127;            // the MMA issue list
+    const size_t bm_bytes = (size_t)M * dc * NB * N * 32 + tab_bytes, stage = (size_t)M * dc * 2 * PLa, one = (size_t)PL * M * dc * 2;
     // tables + planes (two stages if they fit) + a landing ring of at least two slots
     const int pstage = bm_bytes + 2 * stage + 3 * one + 1024 <= 210 * 1024 ? 2 : 1;
     if (bm_bytes + pstage * stage + 2 * one + 1024 > 210 * 1024) return B200C_OK;
-    std::vector<uint8_t> bm(bm_bytes, 0);
+    std::vector<uint8_t> bm(bm_bytes - tab_bytes, 0);
     for (size_t ps = 0; ps < L; ps++) {
         const long long ii = (long long)((ps + 1) * M - 1), jp = ii % (long long)L, dp = ii / (long long)L;
         for (long long k = 0; jp + k * (long long)L < (long long)ntaps; k++) {
@@ -358,7 +414,7 @@ int fir_ummap_configure(FirUmmaPPlan &p, int dtype, const double *taps, size_t n
         p.capacity = bm.size();
     }
     B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
-    p.L = (int)L; p.M = (int)M; p.NB = NB; p.N = N; p.dc = dc; p.nstage = nstage; p.pstage = pstage;
+    p.L = (int)L; p.M = (int)M; p.NB = NB; p.N = N; p.dc = dc; p.nstage = nstage; p.pstage = pstage; p.npass = npass;
     p.ready = true;
     return B200C_OK;
 }
@@ -380,7 +436,8 @@ static int launch_up(FirUmmaPArgs a, int sm_count, cudaStream_t stream)
         B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured[dev] = true;
     }
-    const size_t fixed = (size_t)a.M * DC * a.NB * a.N * 32 + (size_t)a.pstage * a.M * DC * 2 * a.PLa + 1024, one = (size_t)a.PL * a.M * DC * 2;
+    const size_t tab_bytes = ((size_t)a.npass * 2 * a.M * DC * a.NB * 16 + 127) & ~(size_t)127;
+    const size_t fixed = (size_t)a.M * DC * a.NB * a.N * 32 + tab_bytes + (size_t)a.pstage * a.M * DC * 2 * a.PLa + 1024, one = (size_t)a.PL * a.M * DC * 2;
     a.R = (int)std::max<size_t>(2, std::min<size_t>(kUPMaxRing, (216 * 1024 - fixed) / one));
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);   // > half an SM: one CTA per SM (tensor memory)
     const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
@@ -398,8 +455,8 @@ static int launch_up(FirUmmaPArgs a, int sm_count, cudaStream_t stream)
         cudaFree(a.dbg);
         double s8[8] = {0};
         for (int g = 0; g < grid; g++) for (int k = 0; k < 8; k++) s8[k] += (double)h[(size_t)g * 8 + k] / grid;
-        std::fprintf(stderr, "ummap: cycles/tile %.0f | issuer wait raw_empty %.0f | mma wait planes_full %.0f acc_empty %.0f | stager wait raw_full %.0f planes_empty %.0f | epilogue wait acc_full %.0f (tiles/CTA %.1f, R %d, N %d, NB %d, acc stages %d, plane stages %d)\n",
-                     s8[0] / s8[1], s8[2] / s8[1], s8[3] / s8[1], s8[4] / s8[1], s8[5] / s8[1], s8[6] / s8[1], s8[7] / s8[1], s8[1], a.R, a.N, a.NB, a.nstage, a.pstage);
+        std::fprintf(stderr, "ummap: cycles/tile %.0f | issuer wait raw_empty %.0f | mma wait planes_full %.0f acc_empty %.0f | stager wait raw_full %.0f planes_empty %.0f | epilogue wait acc_full %.0f (tiles/CTA %.1f, R %d, N %d, NB %d, acc stages %d, plane stages %d, column passes %d)\n",
+                     s8[0] / s8[1], s8[2] / s8[1], s8[3] / s8[1], s8[4] / s8[1], s8[5] / s8[1], s8[6] / s8[1], s8[7] / s8[1], s8[1], a.R, a.N, a.NB, a.nstage, a.pstage, a.npass);
     }
     return B200C_OK;
 }
@@ -412,7 +469,7 @@ int fir_ummap_launch(const FirUmmaPPlan &p, const void *d_in, size_t in_elems, v
     a.n_in = (long long)in_elems; a.nq = (long long)nq;
     a.ntiles = ((long long)nq + kUPTile - 1) / kUPTile;
     a.L = p.L; a.M = p.M; a.NB = p.NB; a.N = p.N;
-    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage; a.pstage = p.pstage; a.dbg = nullptr;
+    a.PL = kUPTile + 32 * p.NB; a.PLa = (a.PL + 127) / 128 * 128; a.R = 2; a.nstage = p.nstage; a.pstage = p.pstage; a.npass = p.npass; a.dbg = nullptr;
     return p.dc == 1 ? launch_up<1>(a, sm_count, stream) : launch_up<2>(a, sm_count, stream);
 }
 
