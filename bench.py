@@ -28,7 +28,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "FIR Msamples/s (cf32, 256 taps)"
+def _baseline_metric() -> str:
+    """BASELINE.json's metric string, verbatim (the file travels with the repo)."""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "FIR Msamples/s (cf32, 256 taps) at 1/2/4/8 B200; % HBM roofline; vs host CPU"
+
+
+METRIC = _baseline_metric()
 UNIT = "Msamples/s"
 
 WORKLOADS = {
@@ -119,6 +128,16 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def workload_config(wl_name: str) -> dict:
+    """The `config` object of a FIR workload: the same for the GPU arm and the reference arm."""
+    from pothoscomms_b200 import workloads as wl
+    dt_name, taps_name, M, L, log2n, _ = WORKLOADS[wl_name]
+    taps, tt = wl.config_taps(taps_name)
+    return {"workload": f"{wl_name}: /comms/fir_filter {dt_name} {len(taps)} {tt} taps decim={M} interp={L}, "
+                        f"2^{log2n} samples per GPU tone+noise, one stream split in contiguous segments with K-1 halo",
+            "samples_per_gpu": 1 << log2n, "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per pass)"}
+
+
 def cpu_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -157,24 +176,28 @@ def reference_arm(args):
     if rank != 0:
         return 0
     threads = cpu_threads()
-    for _ in range(min(args.warmup, 1)):
-        run_cpu_sample(args.workload, threads, log2_per_thread=18)
+    # W warm-up steps, then exactly K timed steps; a step is a bounded sample of the workload (2^19 samples per
+    # host thread: ~0.2 s at the measured 50-60 Msamples/s) so that any K the driver picks ends within minutes
+    log2_step = 19
+    for _ in range(args.warmup):
+        run_cpu_sample(args.workload, threads, log2_per_thread=log2_step)
     total_s, total_n = 0.0, 0
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, args.steps)
     for _ in range(steps):
-        _, cons, dt = run_cpu_sample(args.workload, threads, log2_per_thread=20)
+        _, cons, dt = run_cpu_sample(args.workload, threads, log2_per_thread=log2_step)
         total_s += dt
         total_n += cons
     value = total_n / total_s / 1e6
-    dt_name, taps_name, M, L, _, _ = WORKLOADS[args.workload]
+    dt_name = WORKLOADS[args.workload][0]
+    config = workload_config(args.workload)
+    config["sample"] = f"{threads} host threads x 2^{log2_step} samples per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": total_s / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: /comms/fir_filter {dt_name} 256 COMPLEX taps decim={M} interp={L}",
-                   "sample": f"{threads} threads x 2^20 samples per step"},
+        "warmup": args.warmup, "ms_per_step": total_s / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if "float" in dt_name else dt_name, "data": "synthetic",
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{threads} x 2^20 samples per step, {steps} steps"},
+                         "sample": f"{threads} threads x 2^{log2_step} samples per step, {steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -532,17 +555,16 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = cpu_threads()
-        v, cons_cpu, secs = run_cpu_sample(args.workload, threads, log2_per_thread=21)
+        # ~10-20 core-seconds of CPU work: 2^22 samples per thread, best of two passes
+        v, cons_cpu, secs = run_cpu_sample(args.workload, threads, log2_per_thread=22, repeats=2)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{threads} threads x 2^21 samples of the same workload ({secs:.1f} s)"}
+               "sample": f"{threads} threads x 2^22 samples of the same workload ({secs:.1f} s wall per pass, best of 2)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if code in (0, 1) else dt_name, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: /comms/fir_filter {dt_name} {len(taps)} {tt} taps decim={M} interp={L}, "
-                               f"2^{log2n} samples per GPU tone+noise, one stream split in contiguous segments with K-1 halo",
-                   "samples_per_gpu": n_seg, "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per pass)"},
+        "config": workload_config(args.workload),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
     }
     print(json.dumps(line))
