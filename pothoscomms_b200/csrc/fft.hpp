@@ -50,6 +50,11 @@ struct FirOsPlan {
     bool osp = false;         // general: the multi-warp resampler kernel (fir_osp_kernel) serves it
     int ospg = 0;             // > 0: its grouped form (fir_ospg_kernel) with this many groups per CTA
     bool real32 = false;      // float32 data, L = M = 1: fir_os32r_kernel (two blocks per transform)
+    bool x32 = false;         // complex float32, L = 3, M = 2: fir_os32x_kernel (one 1024-point forward, one 1536-point inverse)
+    int m0 = 0;               // x32: first alias-free output of a block (hop = 1536 - m0 outputs)
+    long long p0 = 0;         // x32: input element at which block 0's window starts
+    void *d_hx = nullptr;     // x32: [3072] float2 folded tap spectrum H'
+    void *d_tw3 = nullptr;    // x32: [48][32] float2 exp(+2 pi i n2 t / 1536)
     int N = 4096;             // transform length in use
     int K = 0;                // L = M = 1 kernels: taps; general: K = ceil(ntaps / L)
     int M = 1, L = 1;
@@ -63,7 +68,7 @@ struct FirOsPlan {
     void *d_H = nullptr;      // general: [L*M][1024] float2 tap-phase spectra / 1024
     size_t H_floats = 0;
     // output blocks q covered by one kernel block (host-buffer chunking aligns to this)
-    int hop() const { return general ? hopq * (real ? 2 : 1) : (N - (K - 1)) * (real32 ? 2 : 1); }
+    int hop() const { return x32 ? (1536 - m0) / 3 : general ? hopq * (real ? 2 : 1) : (N - (K - 1)) * (real32 ? 2 : 1); }
 };
 constexpr size_t kFirOsMaxTaps = 2049;
 constexpr size_t kFirOs1kMaxTaps = 448;       // measured crossover of the 1024- and 4096-point kernels

@@ -305,6 +305,185 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     }
 }
 
+// ------------------------------------- spectral resampler, interpolation 3 / decimation 2 ---
+// The polyphase nest (filter/FIRFilter.cpp:286-302) for L = 3, M = 2 as ONE forward and ONE inverse
+// transform per block instead of M + L transforms of 1024 points: with u the zero-stuffed input
+// (u[3 n] = x[n]) and v = h * u at the high rate, the reference's outputs are y[m] = v[2 m + 1 + 3 (K - 1)].
+// On a block of 1024 inputs, DFT_3072(u)[k] = X[k mod 1024] (X = DFT_1024 of the block), V = X . H, and
+// keeping every second sample of v (phase 1) folds the spectrum:
+//   W[kk] = X[kk mod 1024] H'[kk] + X[(kk + 512) mod 1024] H'[kk + 1536],  kk < 1536,
+//   H'[k] = DFT_3072(h)[k] exp(2 pi i k / 3072) / 3072,            w[m'] = sum_kk W[kk] exp(2 pi i kk m' / 1536).
+// Outputs m' >= m0 = ceil((ntaps - 2) / 2) (rounded up to a multiple of 3) are alias free: a block yields
+// 1536 - m0 outputs from (1536 - m0) 2 / 3 new inputs (C3: 1407 from 938).
+// One warp per block, as fir_os32_kernel.  After the forward transform thread t holds X[t + 32 k2]; every
+// bin of W it needs is then one of ITS registers (both X indices are congruent to kk mod 32), so the fold
+// is register arithmetic: thread t forms W[t + 32 c], c < 48.  1536 = 32 x 48: the thread transforms its
+// 48 bins (three 16-point transforms, constant twiddles, sixteen 3-point butterflies), twiddles by
+// exp(2 pi i t n2 / 1536), and after ONE exchange the 48 rows n2 are 32-point transforms over t: lane n2
+// takes row n2, lanes 0..15 also row 32 + n2 (the second round runs half empty: 1.5 rows per lane).
+// Row n2 gives w[48 n1 + n2]: for every n1 the warp stores 32 (16) consecutive outputs.
+B200C_HD constexpr float cos48(int e)
+{
+    constexpr float t[48] = {
+        1.0f, 0.9914448857307434f, 0.9659258127212524f, 0.9238795042037964f, 0.8660253882408142f, 0.7933533191680908f,
+        0.7071067690849304f, 0.6087614297866821f, 0.5f, 0.3826834261417389f, 0.258819043636322f, 0.13052618503570557f, 0.0f,
+        -0.13052618503570557f, -0.258819043636322f, -0.3826834261417389f, -0.5f, -0.6087614297866821f, -0.7071067690849304f,
+        -0.7933533191680908f, -0.8660253882408142f, -0.9238795042037964f, -0.9659258127212524f, -0.9914448857307434f, -1.0f,
+        -0.9914448857307434f, -0.9659258127212524f, -0.9238795042037964f, -0.8660253882408142f, -0.7933533191680908f,
+        -0.7071067690849304f, -0.6087614297866821f, -0.5f, -0.3826834261417389f, -0.258819043636322f, -0.13052618503570557f, 0.0f,
+        0.13052618503570557f, 0.258819043636322f, 0.3826834261417389f, 0.5f, 0.6087614297866821f, 0.7071067690849304f,
+        0.7933533191680908f, 0.8660253882408142f, 0.9238795042037964f, 0.9659258127212524f, 0.9914448857307434f};
+    return t[e % 48];
+}
+B200C_HD constexpr float sin48(int e) { return cos48(e + 36); }   // sin(x) = cos(x - pi/2)
+
+// 16-point DFT in place, decimation in frequency: input n in x[n], output k in x[rev16(k)]
+B200C_HD constexpr int rev16(int k) { return 4 * (k & 3) + (k >> 2); }
+template <bool INV> B200C_HD void dft16_dif(c2 (&x)[16])
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        dft4_p<INV>(x[k], x[k + 4], x[k + 8], x[k + 12]);
+        x[k + 4] = mul_w64<INV>(x[k + 4], 4 * k);      // W16^k
+        x[k + 8] = mul_w64<INV>(x[k + 8], 8 * k);
+        x[k + 12] = mul_w64<INV>(x[k + 12], 12 * k);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) dft4_p<INV>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+}
+
+// acc + f * w
+B200C_HD c2 cmul_acc(c2 f, c2 w, c2 acc)
+{
+    float fx, fy, wx, wy;
+    upk(f, fx, fy); upk(w, wx, wy);
+    return fma2(f, pk(wx, wx), fma2(pk(-fy, fx), pk(wy, wy), acc));
+}
+
+struct FirOsX32Args {
+    const void *in;
+    void *out;
+    const void *hx;     // [3072] H'
+    const void *tw;     // [32][32] W1024^(j t)
+    const void *tw3;    // [48][32] exp(+2 pi i n2 t / 1536)
+    long long n_in, n_out;
+    long long p0;       // input element at which block 0's window starts (<= 0: zeros in front)
+    int m0;             // first alias-free output of a block
+};
+constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
+
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args a)
+{
+    __shared__ __align__(16) c2 F[kX32SmemElems];
+    __shared__ __align__(8) unsigned long long bar;
+    const int t = threadIdx.x;
+    const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
+    const c2 *__restrict__ hx = static_cast<const c2 *>(a.hx);
+    const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
+    c2 *__restrict__ out = static_cast<c2 *>(a.out);
+    const int m0 = a.m0, hop_out = 1536 - m0, hop_in = hop_out / 3 * 2;
+    const long long nblk = (a.n_out + hop_out - 1) / hop_out;
+    constexpr int kBulk = 1026;
+    auto bulk_src = [&](long long blk, const c2 *&src) {
+        if (blk >= nblk) return false;
+        const long long P = a.p0 + blk * hop_in;
+        const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + (unsigned long long)P) & 1);
+        src = in + (P - mis);
+        return P - mis >= 0 && P - mis + kBulk <= a.n_in;
+    };
+    if (t == 0) mbar_init(&bar, 1);
+    __syncwarp();
+    long long blk = blockIdx.x;
+    const c2 *src = nullptr;
+    bool pending = bulk_src(blk, src);
+    if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+    unsigned parity = 0;
+    for (; blk < nblk; blk += gridDim.x) {
+        const long long P = a.p0 + blk * hop_in;
+        c2 v[32];
+        if (pending) {
+            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + (unsigned long long)P) & 1);
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = F[mis + 32 * n1 + t];
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const long long g = P + 32 * n1 + t;
+                v[rev32(n1)] = (g >= 0 && g < a.n_in) ? __ldcg(in + g) : 0ull;
+            }
+        }
+        // forward 1024 = 32 x 32 (as fir_os32_kernel): thread t ends with X[t + 32 k2] in v[k2]
+        dft32_dit<false>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
+        dft32_dit<false>(v);
+        // replicate x taps, fold: W[t + 32 c] in s[c % 3][c / 3]
+        c2 s[3][16];
+#pragma unroll
+        for (int c = 0; c < 48; c++) {
+            const c2 w = cmul_p<false>(v[c & 31], hx[32 * c + t]);
+            s[c % 3][c / 3] = cmul_acc(v[(c + 16) & 31], hx[1536 + 32 * c + t], w);
+        }
+        // 48-point inverse transform of the thread's bins: c = 3 c2 + c1, n2 = 16 v1 + v2
+#pragma unroll
+        for (int c1 = 0; c1 < 3; c1++) dft16_dif<true>(s[c1]);
+        __syncwarp();
+#pragma unroll
+        for (int v2 = 0; v2 < 16; v2++) {
+            const int r = rev16(v2);
+            const c2 a0 = s[0][r];
+            const c2 a1 = v2 ? cmul_s(s[1][r], cos48(v2), sin48(v2)) : s[1][r];             // exp(+2 pi i v2 / 48)
+            const c2 a2 = v2 ? cmul_s(s[2][r], cos48(2 * v2), sin48(2 * v2)) : s[2][r];
+            const c2 t1 = add2(a1, a2);
+            const c2 t2 = fma2(t1, pk(-0.5f, -0.5f), a0);
+            const c2 t3 = rot_p<true>(mul2(sub2(a1, a2), pk(0.8660254037844386f, 0.8660254037844386f)));   // +i sin(2 pi / 3) (a1 - a2)
+            const c2 y0 = add2(a0, t1), y1 = add2(t2, t3), y2 = sub2(t2, t3);
+            // step twiddle exp(2 pi i t n2 / 1536), then row n2 of the exchange tile
+            F[v2 * kOs32Stride + t] = v2 ? cmul_p<false>(y0, tw3[v2 * 32 + t]) : y0;
+            F[(16 + v2) * kOs32Stride + t] = cmul_p<false>(y1, tw3[(16 + v2) * 32 + t]);
+            F[(32 + v2) * kOs32Stride + t] = cmul_p<false>(y2, tw3[(32 + v2) * 32 + t]);
+        }
+        __syncwarp();
+        const long long mbase = blk * hop_out - m0;          // global output index of w[0]
+        const bool whole = (blk + 1) * (long long)hop_out <= a.n_out;
+        // round 1: lane t transforms row n2 = t -> w[48 n1 + t]
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[t * kOs32Stride + k1];
+        dft32_dit<true>(v);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+            const int mp = 48 * n1 + t;
+            if (mp >= m0 && (whole || mbase + mp < a.n_out)) __stcg(out + mbase + mp, v[n1]);
+        }
+        // round 2: lanes 0..15 transform rows 32 + t -> w[48 n1 + 32 + t]
+        if (t < 16) {
+#pragma unroll
+            for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[(32 + t) * kOs32Stride + k1];
+        }
+        __syncwarp();                                        // the tile is free: fetch the next block into it
+        pending = bulk_src(blk + gridDim.x, src);
+        if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+        if (t < 16) {
+            dft32_dit<true>(v);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                const int mp = 48 * n1 + 32 + t;
+                if (mp >= m0 && (whole || mbase + mp < a.n_out)) __stcg(out + mbase + mp, v[n1]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------- real float32 data, L = M = 1 ---
 // float32 streams carry REAL taps only (filter/FIRFilter.cpp:373-376), so the filter is real and
 // linear: two consecutive stream blocks ride in one complex transform, z = x_A + i x_B gives
@@ -898,7 +1077,46 @@ static int configure_general(FirOsPlan &p, bool real_data, const double *taps, s
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
                      bool force)
 {
-    p.ready = false; p.general = false; p.real = false; p.osp = false; p.real32 = false;
+    p.ready = false; p.general = false; p.real = false; p.osp = false; p.real32 = false; p.x32 = false;
+    // complex float32, interpolation 3 / decimation 2: one forward + one inverse transform per block
+    // (fir_os32x_kernel); its rate does not depend on the tap count while the hop stays above ~60 % of the block
+    const bool no_x32 = [] { const char *e = std::getenv("B200C_OSX"); return e && std::atoi(e) == 0; }();   // read per configure: tests compare both
+    if (dtype == B200C_CF32 && L == 3 && M == 2 && !no_x32 && ntaps >= 2 && ntaps <= 1200 &&
+        (force || (ntaps + L - 1) / L >= kFirOsAutoMinTapsOsp)) {
+        const long long K = (long long)((ntaps + L - 1) / L);            // filter/FIRFilter.cpp:335
+        int m0 = (int)((ntaps - 2 + 1) / 2);                             // ceil((ntaps - 2) / 2): v[i] is alias free from i = ntaps - 1
+        m0 = (m0 + 2) / 3 * 3;                                           // whole output blocks q per transform block
+        const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
+        std::vector<float> hx(2 * 3072), tb(2 * 48 * 32);
+        for (int k = 0; k < 3072; k++) {
+            // H'[k] = (1/3072) exp(2 pi i k (M - 1) / 3072) sum_t h[t] exp(-2 pi i k t / 3072), in double
+            std::complex<double> acc(0.0, 0.0);
+            for (size_t tt = 0; tt < ntaps; tt++) {
+                const std::complex<double> h = complex_taps ? std::complex<double>(taps[2 * tt], taps[2 * tt + 1]) : std::complex<double>(taps[tt], 0.0);
+                const long long e = ((long long)k * (long long)tt) % 3072;
+                acc += h * std::polar(1.0, -two_pi * (double)e / 3072.0);
+            }
+            acc *= std::polar(1.0 / 3072.0, two_pi * (double)k / 3072.0);
+            hx[2 * k] = (float)acc.real();
+            hx[2 * k + 1] = (float)acc.imag();
+        }
+        for (int n2 = 0; n2 < 48; n2++)
+            for (int t = 0; t < 32; t++) {
+                tb[2 * (n2 * 32 + t)] = (float)std::cos(two_pi * (double)(n2 * t) / 1536.0);
+                tb[2 * (n2 * 32 + t) + 1] = (float)std::sin(two_pi * (double)(n2 * t) / 1536.0);
+            }
+        int rc;
+        if ((rc = upload(&p.d_hx, hx))) return rc;
+        if ((rc = upload(&p.d_tw3, tb))) return rc;
+        if (!p.d_tw1k) {
+            unit_root_table(tb, 1024, 32, 32, 1);
+            if ((rc = upload(&p.d_tw1k, tb))) return rc;
+        }
+        p.N = 1024; p.K = (int)K; p.M = 2; p.L = 3; p.m0 = m0; p.p0 = (K - 1) - 2 * (long long)(m0 / 3);
+        p.x32 = true;
+        p.ready = true;
+        return B200C_OK;
+    }
     if (dtype == B200C_CF32 && M == 1 && L == 1) {
         // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up
         if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
@@ -968,7 +1186,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
 
 void fir_os_destroy(FirOsPlan &p)
 {
-    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k, &p.d_H}) {
+    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k, &p.d_H, &p.d_hx, &p.d_tw3}) {
         if (*d) cudaFree(*d);
         *d = nullptr;
     }
@@ -978,6 +1196,7 @@ void fir_os_destroy(FirOsPlan &p)
 
 const char *fir_os_kernel_name(const FirOsPlan &p)
 {
+    if (p.x32) return "fir_os32x_kernel";
     if (p.general) return p.osp ? (p.ospg ? "fir_ospg_kernel" : "fir_osp_kernel") : "fir_os32g_kernel";
     if (p.real32) return "fir_os32r_kernel";
     return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
@@ -1039,6 +1258,23 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
 {
     if (nq == 0) return B200C_OK;
     const int nchan = batch ? batch->nchan : 1;
+    if (p.x32) {
+        if (batch) { set_error("filter bank: the batched launch serves complex float32 L = M = 1 only"); return B200C_ERR_UNSUPPORTED; }
+        FirOsX32Args a;
+        a.in = d_in; a.out = d_out; a.hx = p.d_hx; a.tw = p.d_tw1k; a.tw3 = p.d_tw3;
+        a.n_in = (long long)in_elems; a.n_out = (long long)nq * 3; a.p0 = p.p0; a.m0 = p.m0;
+        const long long nblk = (a.n_out + (1536 - p.m0) - 1) / (1536 - p.m0);
+        static const int minb = [] { const char *e = std::getenv("B200C_OSX_MINB"); return e ? std::atoi(e) : 12; }();
+        const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
+        switch (minb) {
+        case 8: fir_os32x_kernel<8><<<grid, 32, 0, stream>>>(a); break;
+        case 9: fir_os32x_kernel<9><<<grid, 32, 0, stream>>>(a); break;
+        case 10: fir_os32x_kernel<10><<<grid, 32, 0, stream>>>(a); break;
+        default: fir_os32x_kernel<12><<<grid, 32, 0, stream>>>(a); break;
+        }
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
     if (p.general) {
         if (batch) { set_error("filter bank: the batched launch serves complex float32 L = M = 1 only"); return B200C_ERR_UNSUPPORTED; }
         FirOs32GArgs a;

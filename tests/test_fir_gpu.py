@@ -392,7 +392,8 @@ def test_overlap_save_polyphase_and_real_data(oracle, cuda_device, dt, taps_type
             y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, zero_tail=zero_tail)
             with _with_algo("fft"):
                 y_os, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
-                expect = ("fir_ospg_kernel", "fir_osp_kernel") if osp else ("fir_os32r_kernel",) if (dt, M, L) == ("F32", 1, 1) else ("fir_os32g_kernel",)
+                expect = ("fir_os32x_kernel",) if (dt, M, L) == ("CF32", 2, 3) else ("fir_ospg_kernel", "fir_osp_kernel") if osp else \
+                    ("fir_os32r_kernel",) if (dt, M, L) == ("F32", 1, 1) else ("fir_os32g_kernel",)
                 assert f.kernel in expect, f.kernel
             assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
             _compare(oracle, code, y_os, y_ref, f"os32g {dt}/{taps_type} M={M} L={L} K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
@@ -638,3 +639,76 @@ def test_real_float32_overlap_save_kernel(oracle, cuda_device, ntaps):
         y, _, prod = f.run(shifted[off:])
         torch.cuda.synchronize()
         _compare(oracle, oracle.F32, y.cpu().numpy()[:prod], y_ref, f"os32r unaligned {off}", rms_hint)
+
+
+def _with_env(name, value):
+    import contextlib
+    import os
+
+    @contextlib.contextmanager
+    def cm():
+        old = os.environ.get(name)
+        os.environ[name] = value
+        try:
+            yield
+        finally:
+            if old is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = old
+    return cm()
+
+
+@pytest.mark.parametrize("ntaps", [2, 7, 40, 48, 100, 255, 301, 700, 1200])
+@pytest.mark.parametrize("taps_type", ["REAL", "COMPLEX"])
+def test_spectral_resampler_interp3_decim2(oracle, cuda_device, ntaps, taps_type):
+    """complex float32, interpolation 3 / decimation 2 (BASELINE config C3) takes fir_os32x_kernel: one 1024-point
+    forward and one 1536-point inverse transform per block (spectrum replicated, multiplied, folded).  Ragged
+    lengths around the block hop, tiny inputs, the burst zero tail, unaligned base pointers, an output capacity
+    that ends mid-block; against the oracle and against the grouped polyphase kernel it replaces."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    code, M, L = oracle.CF32, 2, 3
+    rng = np.random.default_rng(31 * ntaps + (taps_type == "COMPLEX"))
+    taps = rng.standard_normal(ntaps) / np.sqrt(ntaps / L)
+    if taps_type == "COMPLEX":
+        taps = taps + 1j * rng.standard_normal(ntaps) / np.sqrt(ntaps / L)
+    K = -(-ntaps // L)
+    m0 = (-(-(ntaps - 2) // 2) + 2) // 3 * 3
+    hop_in = (1536 - m0) // 3 * 2
+    rms_hint = float(np.sqrt(np.sum(np.abs(taps) ** 2) / L))
+    for n_new, zero_tail in ((M, False), (hop_in - 2, False), (hop_in, False), (hop_in + 2, False), (3 * hop_in + 2, False),
+                             (M * 2049, False), (M * 25000 + 1, False), (997, True), (1, True)):
+        x = _rand_input(oracle, code, K - 1 + n_new, rng)
+        y_ref, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, zero_tail=zero_tail)
+        with _with_algo("fft"):
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
+        assert f.kernel == "fir_os32x_kernel", f.kernel
+        assert (cons, prod) == (c_ref, p_ref), (ntaps, n_new, zero_tail)
+        _compare(oracle, code, y, y_ref, f"os32x {taps_type} K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
+    # the kernel it replaced, on the same stream
+    if K >= 16:
+        with _with_env("B200C_OSX", "0"):
+            y_g, _, _, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail)
+            assert f.kernel in ("fir_ospg_kernel", "fir_osp_kernel"), f.kernel
+        _compare(oracle, code, y_g, y_ref, "ospg", rms_hint)
+    # unaligned base pointers (the bulk copy re-aligns by one element) and a capacity that ends inside a block
+    x = _rand_input(oracle, code, 30001, rng)
+    y_ref, _, _ = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x)
+    with _with_algo("fft"):
+        f = FirFilter(code, taps_type)
+        f.set_taps(taps)
+        f.set_rates(M, L)
+    xd = torch.from_numpy(x).cuda()
+    for off in (1, 2, 3):
+        shifted = torch.empty((x.shape[0] + off, 2), dtype=xd.dtype, device="cuda")
+        shifted[off:] = xd
+        y, _, prod = f.run(shifted[off:])
+        torch.cuda.synchronize()
+        _compare(oracle, code, y.cpu().numpy()[:prod], y_ref, f"os32x unaligned {off}", rms_hint)
+    cap = 3 * 1000 + 3
+    y_ref_c, c_ref, p_ref = oracle.fir(code, taps_type == "COMPLEX", taps, M, L, x, out_capacity=cap)
+    y, cons, prod = f.run(xd, out_capacity=cap)
+    torch.cuda.synchronize()
+    assert (cons, prod) == (c_ref, p_ref)
+    _compare(oracle, code, y.cpu().numpy()[:prod], y_ref_c, "os32x capacity", rms_hint)
