@@ -427,12 +427,19 @@ __global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args 
 #pragma unroll
         for (int n2 = 0; n2 < 32; n2++) v[rev32(n2)] = F[t * kOs32Stride + n2];
         dft32_dit<false>(v);
-        // replicate x taps, fold: W[t + 32 c] in s[c % 3][c / 3]
+        // replicate x taps, fold: W[t + 32 c] in s[c % 3][c / 3].  Bins c, c + 16, c + 32 (c < 16) are the three
+        // combinations of the SAME two inputs X[c], X[c + 16], which retire with them: at most 48 values stay
+        // live, which leaves registers for the tap-spectrum loads to run ahead.
         c2 s[3][16];
 #pragma unroll
-        for (int c = 0; c < 48; c++) {
-            const c2 w = cmul_p<false>(v[c & 31], hx[32 * c + t]);
-            s[c % 3][c / 3] = cmul_acc(v[(c + 16) & 31], hx[1536 + 32 * c + t], w);
+        for (int c = 0; c < 16; c++) {
+            const c2 xa = v[c], xb = v[c + 16];
+            const c2 h0 = hx[32 * c + t], g0 = hx[1536 + 32 * c + t];
+            const c2 h1 = hx[32 * (c + 16) + t], g1 = hx[1536 + 32 * (c + 16) + t];
+            const c2 h2 = hx[32 * (c + 32) + t], g2 = hx[1536 + 32 * (c + 32) + t];
+            s[c % 3][c / 3] = cmul_acc(xb, g0, cmul_p<false>(xa, h0));
+            s[(c + 16) % 3][(c + 16) / 3] = cmul_acc(xa, g1, cmul_p<false>(xb, h1));
+            s[(c + 32) % 3][(c + 32) / 3] = cmul_acc(xb, g2, cmul_p<false>(xa, h2));
         }
         // 48-point inverse transform of the thread's bins: c = 3 c2 + c1, n2 = 16 v1 + v2
 #pragma unroll
@@ -456,14 +463,21 @@ __global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args 
         __syncwarp();
         const long long mbase = blk * hop_out - m0;          // global output index of w[0]
         const bool whole = (blk + 1) * (long long)hop_out <= a.n_out;
+        c2 *const o = out + mbase + t;                       // w[48 n1 + t] goes to o[48 n1]
+        const int d0 = t - m0;                               // w[m'] is kept when m' >= m0
+        const int left = whole ? 0x7fffffff : (int)(a.n_out - mbase) - t;   // ... and inside the output: 48 n1 (+ 32) < left
         // round 1: lane t transforms row n2 = t -> w[48 n1 + t]
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[t * kOs32Stride + k1];
         dft32_dit<true>(v);
+        if (whole) {
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) {
-            const int mp = 48 * n1 + t;
-            if (mp >= m0 && (whole || mbase + mp < a.n_out)) __stcg(out + mbase + mp, v[n1]);
+            for (int n1 = 0; n1 < 32; n1++)
+                if (d0 + 48 * n1 >= 0) __stcg(o + 48 * n1, v[n1]);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++)
+                if (d0 + 48 * n1 >= 0 && 48 * n1 < left) __stcg(o + 48 * n1, v[n1]);
         }
         // round 2: lanes 0..15 transform rows 32 + t -> w[48 n1 + 32 + t]
         if (t < 16) {
@@ -475,10 +489,14 @@ __global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args 
         if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
         if (t < 16) {
             dft32_dit<true>(v);
+            if (whole) {
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const int mp = 48 * n1 + 32 + t;
-                if (mp >= m0 && (whole || mbase + mp < a.n_out)) __stcg(out + mbase + mp, v[n1]);
+                for (int n1 = 0; n1 < 32; n1++)
+                    if (d0 + 48 * n1 + 32 >= 0) __stcg(o + 48 * n1 + 32, v[n1]);
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++)
+                    if (d0 + 48 * n1 + 32 >= 0 && 48 * n1 + 32 < left) __stcg(o + 48 * n1 + 32, v[n1]);
             }
         }
     }
@@ -1270,6 +1288,7 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         case 8: fir_os32x_kernel<8><<<grid, 32, 0, stream>>>(a); break;
         case 9: fir_os32x_kernel<9><<<grid, 32, 0, stream>>>(a); break;
         case 10: fir_os32x_kernel<10><<<grid, 32, 0, stream>>>(a); break;
+        case 14: fir_os32x_kernel<14><<<grid, 32, 0, stream>>>(a); break;
         default: fir_os32x_kernel<12><<<grid, 32, 0, stream>>>(a); break;
         }
         B200C_CUDA_TRY(cudaGetLastError());
