@@ -372,15 +372,28 @@ struct FirOsX32Args {
 };
 constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
 
-template <int MINB>
-__global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args a)
+// WARPS == 1: one warp per CTA, MINB CTAs per SM, tables read through L1.  WARPS > 1: one persistent CTA per SM
+// whose warps share ONE copy of the tables (tap spectrum 24 KB, step twiddles 12 KB + 8 KB) in shared memory.
+constexpr int kX32TabElems = 3072 + 1536 + 1024;
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOsX32Args a)
 {
-    __shared__ __align__(16) c2 F[kX32SmemElems];
-    __shared__ __align__(8) unsigned long long bar;
-    const int t = threadIdx.x;
+    extern __shared__ __align__(16) c2 x32_smem[];
+    __shared__ __align__(8) unsigned long long bars[WARPS];
+    const int t = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
     const c2 *__restrict__ hx = static_cast<const c2 *>(a.hx);
+    c2 *F = x32_smem + wp * kX32SmemElems;
+    if constexpr (WARPS > 1) {
+        c2 *tab = x32_smem + WARPS * kX32SmemElems;
+        for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
+        for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
+        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
+        __syncthreads();
+        hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
+    }
+    unsigned long long &bar = bars[wp];
     const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
     c2 *__restrict__ out = static_cast<c2 *>(a.out);
     const int m0 = a.m0, hop_out = 1536 - m0, hop_in = hop_out / 3 * 2;
@@ -395,12 +408,13 @@ __global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args 
     };
     if (t == 0) mbar_init(&bar, 1);
     __syncwarp();
-    long long blk = blockIdx.x;
+    long long blk = (long long)blockIdx.x * WARPS + wp;
+    const long long bstep = (long long)gridDim.x * WARPS;
     const c2 *src = nullptr;
     bool pending = bulk_src(blk, src);
     if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
     unsigned parity = 0;
-    for (; blk < nblk; blk += gridDim.x) {
+    for (; blk < nblk; blk += bstep) {
         const long long P = a.p0 + blk * hop_in;
         c2 v[32];
         if (pending) {
@@ -485,7 +499,7 @@ __global__ void __launch_bounds__(32, MINB) fir_os32x_kernel(const FirOsX32Args 
             for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[(32 + t) * kOs32Stride + k1];
         }
         __syncwarp();                                        // the tile is free: fetch the next block into it
-        pending = bulk_src(blk + gridDim.x, src);
+        pending = bulk_src(blk + bstep, src);
         if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
         if (t < 16) {
             dft32_dit<true>(v);
@@ -1282,14 +1296,29 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hx = p.d_hx; a.tw = p.d_tw1k; a.tw3 = p.d_tw3;
         a.n_in = (long long)in_elems; a.n_out = (long long)nq * 3; a.p0 = p.p0; a.m0 = p.m0;
         const long long nblk = (a.n_out + (1536 - p.m0) - 1) / (1536 - p.m0);
-        static const int minb = [] { const char *e = std::getenv("B200C_OSX_MINB"); return e ? std::atoi(e) : 12; }();
-        const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
-        switch (minb) {
-        case 8: fir_os32x_kernel<8><<<grid, 32, 0, stream>>>(a); break;
-        case 9: fir_os32x_kernel<9><<<grid, 32, 0, stream>>>(a); break;
-        case 10: fir_os32x_kernel<10><<<grid, 32, 0, stream>>>(a); break;
-        case 14: fir_os32x_kernel<14><<<grid, 32, 0, stream>>>(a); break;
-        default: fir_os32x_kernel<12><<<grid, 32, 0, stream>>>(a); break;
+        // B200C_OSX_MINB: 8 / 10 / 12 one-warp CTAs per SM (tables through L1); 112 (default): one persistent 12-warp
+        // CTA per SM with the tables in shared memory
+        static const int minb = [] { const char *e = std::getenv("B200C_OSX_MINB"); return e ? std::atoi(e) : 112; }();
+        const size_t tile = sizeof(c2) * kX32SmemElems;
+        if (minb >= 100) {
+            auto kern = fir_os32x_kernel<12, 1>;
+            const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = true;
+            }
+            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
+            kern<<<grid, 32 * 12, smem, stream>>>(a);
+        } else {
+            const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
+            switch (minb) {
+            case 8: fir_os32x_kernel<1, 8><<<grid, 32, tile, stream>>>(a); break;
+            case 10: fir_os32x_kernel<1, 10><<<grid, 32, tile, stream>>>(a); break;
+            default: fir_os32x_kernel<1, 12><<<grid, 32, tile, stream>>>(a); break;
+            }
         }
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
