@@ -375,7 +375,7 @@ constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
 // WARPS == 1: one warp per CTA, MINB CTAs per SM, tables read through L1.  WARPS > 1: one persistent CTA per SM
 // whose warps share ONE copy of the tables (tap spectrum 24 KB, step twiddles 12 KB + 8 KB) in shared memory.
 constexpr int kX32TabElems = 3072 + 1536 + 1024;
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool PT = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOsX32Args a)
 {
     extern __shared__ __align__(16) c2 x32_smem[];
@@ -432,8 +432,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
         }
         // forward 1024 = 32 x 32 (as fir_os32_kernel): thread t ends with X[t + 32 k2] in v[k2]
         dft32_dit<false>(v);
+        if constexpr (PT) twiddle32<false, false>(v, tw, t);   // ten loaded + 21 computed twiddles
+        else {
 #pragma unroll
-        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+            for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
+        }
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) F[k1 * kOs32Stride + t] = v[k1];
@@ -459,6 +462,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
         for (int c1 = 0; c1 < 3; c1++) dft16_dif<true>(s[c1]);
         __syncwarp();
+        // step twiddles exp(2 pi i t n2 / 1536), n2 = 16 v1 + v2: PT loads the 15 + 2 factors and multiplies
+        c2 twb1 = 0, twb2 = 0;
+        if constexpr (PT) { twb1 = tw3[16 * 32 + t]; twb2 = tw3[32 * 32 + t]; }
 #pragma unroll
         for (int v2 = 0; v2 < 16; v2++) {
             const int r = rev16(v2);
@@ -470,9 +476,16 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
             const c2 t3 = rot_p<true>(mul2(sub2(a1, a2), pk(0.8660254037844386f, 0.8660254037844386f)));   // +i sin(2 pi / 3) (a1 - a2)
             const c2 y0 = add2(a0, t1), y1 = add2(t2, t3), y2 = sub2(t2, t3);
             // step twiddle exp(2 pi i t n2 / 1536), then row n2 of the exchange tile
-            F[v2 * kOs32Stride + t] = v2 ? cmul_p<false>(y0, tw3[v2 * 32 + t]) : y0;
-            F[(16 + v2) * kOs32Stride + t] = cmul_p<false>(y1, tw3[(16 + v2) * 32 + t]);
-            F[(32 + v2) * kOs32Stride + t] = cmul_p<false>(y2, tw3[(32 + v2) * 32 + t]);
+            if constexpr (PT) {
+                const c2 wa = v2 ? tw3[v2 * 32 + t] : pk(1.f, 0.f);
+                F[v2 * kOs32Stride + t] = v2 ? cmul_p<false>(y0, wa) : y0;
+                F[(16 + v2) * kOs32Stride + t] = cmul_p<false>(y1, v2 ? cmul_p<false>(wa, twb1) : twb1);
+                F[(32 + v2) * kOs32Stride + t] = cmul_p<false>(y2, v2 ? cmul_p<false>(wa, twb2) : twb2);
+            } else {
+                F[v2 * kOs32Stride + t] = v2 ? cmul_p<false>(y0, tw3[v2 * 32 + t]) : y0;
+                F[(16 + v2) * kOs32Stride + t] = cmul_p<false>(y1, tw3[(16 + v2) * 32 + t]);
+                F[(32 + v2) * kOs32Stride + t] = cmul_p<false>(y2, tw3[(32 + v2) * 32 + t]);
+            }
         }
         __syncwarp();
         const long long mbase = blk * hop_out - m0;          // global output index of w[0]
@@ -1300,14 +1313,17 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         // CTA per SM with the tables in shared memory
         static const int minb = [] { const char *e = std::getenv("B200C_OSX_MINB"); return e ? std::atoi(e) : 112; }();
         const size_t tile = sizeof(c2) * kX32SmemElems;
+        // partial twiddles (10 + 17 loaded, the rest multiplied up): C3 207.8 -> 211.2 Gsamples/s; B200C_OSX_PT=0 loads all
+        static const bool pt = [] { const char *e = std::getenv("B200C_OSX_PT"); return !e || std::atoi(e) != 0; }();
         if (minb >= 100) {
-            auto kern = fir_os32x_kernel<12, 1>;
+            auto kern = pt ? fir_os32x_kernel<12, 1, true> : fir_os32x_kernel<12, 1, false>;
             const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
             static thread_local bool configured[16] = {false};
             int dev = 0;
             B200C_CUDA_TRY(cudaGetDevice(&dev));
             if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured[dev] = true;
             }
             const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
