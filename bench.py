@@ -540,7 +540,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                 "kernel": fir.kernel, "kernel_ms": kernel_ms,
-                "note": ("fused overlap-save (fast convolution): one pass over HBM, 16 B per sample whatever the tap count"
+                "note": ("spectral resampler (one 1024-point forward + one 1536-point inverse transform per block): one pass over "
+                         "HBM, 8 B in + 12 B out per input sample whatever the tap count"
+                         if fir.kernel == "fir_os32x_kernel" else
+                         "fused overlap-save (fast convolution): one pass over HBM, 16 B per sample whatever the tap count"
                          if fir.kernel.startswith("fir_os") else
                          "bit-exact int16 as byte-limb Toeplitz GEMMs on the int8 tensor cores (tcgen05 kind::i8, accumulators "
                          "in tensor memory); the HBM figure is reported next to it, the kernel is shared-memory/tensor bound"
