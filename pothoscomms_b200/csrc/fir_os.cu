@@ -202,15 +202,26 @@ struct FirOs32Args {
     int K;
 };
 
-template <int WARPS, int MINB>
+// TABS: one persistent CTA per SM whose warps share ONE copy of the tap spectrum and the twiddles in (dynamic) shared
+// memory -- single-channel streams only (a filter bank has one spectrum per channel)
+template <int WARPS, int MINB, bool TABS = false, bool PT = kOs32PartialTwiddles>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
 {
-    __shared__ __align__(16) c2 Fs[WARPS][kOs32SmemElems];
+    extern __shared__ __align__(16) c2 os32_dyn[];
+    __shared__ __align__(16) c2 Fs[TABS ? 1 : WARPS][TABS ? 1 : kOs32SmemElems];
     __shared__ __align__(8) unsigned long long bars[WARPS];
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
-    c2 *F = Fs[w];
+    c2 *F = TABS ? os32_dyn + w * kOs32SmemElems : Fs[TABS ? 0 : w];
     unsigned long long *bar = &bars[w];
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
+    const c2 *__restrict__ hf_tab = nullptr;
+    if constexpr (TABS) {
+        c2 *tab = os32_dyn + WARPS * kOs32SmemElems;
+        const c2 *__restrict__ hf0 = static_cast<const c2 *>(a.hf);
+        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
+        __syncthreads();
+        hf_tab = tab; tw = tab + 1024;
+    }
     const int Km1 = a.K - 1;
     const int hop = 1024 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
         long long nch = ch + dch, nblkpos = blk + dblk;      // this warp's next task
         if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
         const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
-        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 1024;
+        const c2 *__restrict__ hf = TABS ? hf_tab : static_cast<const c2 *>(a.hf) + ch * 1024;
         c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
         c2 v[32];
         if (pending) {
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
             }
         }
         dft32_dit<false>(v);
-        if constexpr (kOs32PartialTwiddles) twiddle32<false, false>(v, tw, t);
+        if constexpr (PT) twiddle32<false, false>(v, tw, t);
         else {
 #pragma unroll
             for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
 #pragma unroll
         for (int k2 = 0; k2 < 32; k2++) v[k2] = cmul_p<false>(v[k2], hf[32 * k2 + t]);
         dft32_dif<true>(v);
-        if constexpr (kOs32PartialTwiddles) twiddle32<true, true>(v, tw, t);
+        if constexpr (PT) twiddle32<true, true>(v, tw, t);
         else {
 #pragma unroll
             for (int n2 = 1; n2 < 32; n2++) v[rev32(n2)] = cmul_p<true>(v[rev32(n2)], tw[n2 * 32 + t]);
@@ -543,15 +554,25 @@ struct FirOs32RArgs {
     int K;
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(32, MINB) fir_os32r_kernel(const FirOs32RArgs a)
+// WARPS == 1: one warp per CTA, MINB CTAs per SM, tables through L1.  WARPS > 1: one persistent CTA per SM whose warps
+// share one copy of the tap spectrum and the twiddles in shared memory (as fir_os32_kernel's TABS form).
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32r_kernel(const FirOs32RArgs a)
 {
-    __shared__ __align__(16) c2 F[kOs32SmemElems];
-    __shared__ __align__(8) unsigned long long bar;
+    extern __shared__ __align__(16) c2 os32r_dyn[];
+    __shared__ __align__(8) unsigned long long bars[WARPS];
+    const int t = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    c2 *F = os32r_dyn + wp * kOs32SmemElems;
+    unsigned long long &bar = bars[wp];
     const float *Ff = reinterpret_cast<const float *>(F);
-    const int t = threadIdx.x;
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
+    if constexpr (WARPS > 1) {
+        c2 *tab = os32r_dyn + WARPS * kOs32SmemElems;
+        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf[i]; tab[1024 + i] = tw[i]; }
+        __syncthreads();
+        hf = tab; tw = tab + 1024;
+    }
     const int Km1 = a.K - 1, hop = 1024 - Km1;
     const long long npair = (a.n_out + 2LL * hop - 1) / (2LL * hop);
     // pair bp: block A = inputs [base, base + 1024), block B = [base + hop, base + hop + 1024), base = 2 hop bp
@@ -566,7 +587,7 @@ __global__ void __launch_bounds__(32, MINB) fir_os32r_kernel(const FirOs32RArgs 
     };
     if (t == 0) mbar_init(&bar, 1);
     __syncwarp();
-    long long bp = blockIdx.x;
+    long long bp = (long long)blockIdx.x * WARPS + wp;
     const float *src = nullptr;
     int mis = 0, mis_next = 0;
     unsigned bytes = 0;
@@ -574,7 +595,7 @@ __global__ void __launch_bounds__(32, MINB) fir_os32r_kernel(const FirOs32RArgs 
     if (pending && t == 0) bulk_load(F, src, bytes, &bar);
     unsigned parity = 0;
     while (bp < npair) {
-        const long long base = bp * 2LL * hop, nbp = bp + gridDim.x;
+        const long long base = bp * 2LL * hop, nbp = bp + (long long)gridDim.x * WARPS;
         c2 v[32];
         if (pending) {
             mbar_wait(&bar, parity);
@@ -1377,8 +1398,24 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = static_cast<const float *>(d_in); a.out = static_cast<float *>(d_out); a.hf = p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)nq; a.K = p.K;
         const long long npair = ((long long)nq + p.hop() - 1) / p.hop();
-        const int grid = (int)std::min<long long>(npair, (long long)sm_count * 12 * 4);
-        fir_os32r_kernel<12><<<grid, 32, 0, stream>>>(a);
+        // one persistent 12-warp CTA per SM with the tables in shared memory (B200C_OS32R_CFG=112: 12 one-warp CTAs)
+        static const int rcfg = [] { const char *e = std::getenv("B200C_OS32R_CFG"); return e ? std::atoi(e) : 1012; }();
+        const size_t tile = sizeof(c2) * kOs32SmemElems;
+        if (rcfg >= 1000) {
+            const size_t smem = 12 * tile + sizeof(c2) * 2048;
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = true;
+            }
+            const int grid = (int)std::min<long long>((npair + 11) / 12, (long long)sm_count);
+            fir_os32r_kernel<12, 1><<<grid, 32 * 12, smem, stream>>>(a);
+        } else {
+            const int grid = (int)std::min<long long>(npair, (long long)sm_count * 12 * 4);
+            fir_os32r_kernel<1, 12><<<grid, 32, tile, stream>>>(a);
+        }
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
@@ -1389,12 +1426,30 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
         a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
-        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 112; }();
+        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 1012; }();
 #define OS32_LAUNCH(W, MB)                                                                                        \
     {                                                                                                             \
         const int grid = (int)std::min<long long>((nblk + (W) - 1) / (W), (long long)sm_count * (MB) * 4);        \
         fir_os32_kernel<W, MB><<<grid, 32 * (W), 0, stream>>>(a);                                                  \
     }
+        // 1012 / 1112: one persistent 12-warp CTA per SM, tap spectrum + twiddles in shared memory (single stream only),
+        // all twiddles loaded / partial twiddles
+        if (cfg >= 1000 && nchan == 1) {
+            const size_t smem = sizeof(c2) * (12 * (size_t)kOs32SmemElems + 2048);
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = true;
+            }
+            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
+            if (cfg >= 1100) fir_os32_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
+            else fir_os32_kernel<12, 1, true, false><<<grid, 32 * 12, smem, stream>>>(a);
+            B200C_CUDA_TRY(cudaGetLastError());
+            return B200C_OK;
+        }
         switch (cfg) {   // (warps per CTA)(CTAs per SM)
         case 42: OS32_LAUNCH(4, 2) break;
         case 25: OS32_LAUNCH(2, 5) break;
