@@ -204,7 +204,10 @@ struct FirOs32Args {
 
 // TABS: one persistent CTA per SM whose warps share ONE copy of the tap spectrum and the twiddles in (dynamic) shared
 // memory -- single-channel streams only (a filter bank has one spectrum per channel)
-template <int WARPS, int MINB, bool TABS = false, bool PT = kOs32PartialTwiddles>
+// EARLY (TABS form): every warp also owns a landing buffer, so the bulk copy of its NEXT block is issued as soon as the
+// current block sits in registers and has the whole block's compute time to arrive (instead of the last register pass).
+constexpr int kOs32Landing = 1032;   // c2 elements per landing buffer (1026 used)
+template <int WARPS, int MINB, bool TABS = false, bool PT = kOs32PartialTwiddles, bool EARLY = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs32Args a)
 {
     extern __shared__ __align__(16) c2 os32_dyn[];
@@ -215,6 +218,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     unsigned long long *bar = &bars[w];
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ hf_tab = nullptr;
+    c2 *Lb = F;                                               // where the bulk copy lands
+    if constexpr (TABS && EARLY) Lb = os32_dyn + WARPS * kOs32SmemElems + 2048 + w * kOs32Landing;
     if constexpr (TABS) {
         c2 *tab = os32_dyn + WARPS * kOs32SmemElems;
         const c2 *__restrict__ hf0 = static_cast<const c2 *>(a.hf);
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     __syncwarp();
     const c2 *src = nullptr;
     bool pending = bulk_src(ch, blk, src);
-    if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), bar);
+    if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
     while (ch < a.nchan) {
         const long long base = blk * hop;
@@ -259,13 +264,18 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
             mbar_wait(bar, parity);
             parity ^= 1;
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = F[mis + 32 * n1 + t];
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = Lb[mis + 32 * n1 + t];
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) {
                 const long long g = base + 32 * n1 + t;
                 v[rev32(n1)] = g < a.n_in ? __ldcg(in + g) : 0ull;
             }
+        }
+        if constexpr (TABS && EARLY) {
+            __syncwarp();                                    // the landing buffer is in registers: fetch the next block now
+            pending = bulk_src(nch, nblkpos, src);
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
         }
         dft32_dit<false>(v);
         if constexpr (PT) twiddle32<false, false>(v, tw, t);
@@ -294,9 +304,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
-        __syncwarp();                                        // the tile is free: fetch the next block into it
-        pending = bulk_src(nch, nblkpos, src);
-        if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), bar);
+        if constexpr (!(TABS && EARLY)) {
+            __syncwarp();                                    // the tile is free: fetch the next block into it
+            pending = bulk_src(nch, nblkpos, src);
+            if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), bar);
+        }
         dft32_dif<true>(v);
         c2 *o = out + (base - Km1);
         if (base + hop <= a.n_out) {
@@ -556,15 +568,17 @@ struct FirOs32RArgs {
 
 // WARPS == 1: one warp per CTA, MINB CTAs per SM, tables through L1.  WARPS > 1: one persistent CTA per SM whose warps
 // share one copy of the tap spectrum and the twiddles in shared memory (as fir_os32_kernel's TABS form).
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool EARLY = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32r_kernel(const FirOs32RArgs a)
 {
     extern __shared__ __align__(16) c2 os32r_dyn[];
     __shared__ __align__(8) unsigned long long bars[WARPS];
     const int t = threadIdx.x & 31, wp = threadIdx.x >> 5;
     c2 *F = os32r_dyn + wp * kOs32SmemElems;
+    // EARLY (WARPS > 1): a landing buffer per warp, the next pair is fetched while this one is computed
+    c2 *Lb = (WARPS > 1 && EARLY) ? os32r_dyn + WARPS * kOs32SmemElems + 2048 + wp * kOs32Landing : F;
     unsigned long long &bar = bars[wp];
-    const float *Ff = reinterpret_cast<const float *>(F);
+    const float *Ff = reinterpret_cast<const float *>(Lb);
     const c2 *__restrict__ tw = static_cast<const c2 *>(a.tw);
     const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf);
     if constexpr (WARPS > 1) {
@@ -592,7 +606,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32r_kernel(const FirOs
     int mis = 0, mis_next = 0;
     unsigned bytes = 0;
     bool pending = bulk_src(bp, src, mis, bytes);
-    if (pending && t == 0) bulk_load(F, src, bytes, &bar);
+    if (pending && t == 0) bulk_load(Lb, src, bytes, &bar);
     unsigned parity = 0;
     while (bp < npair) {
         const long long base = bp * 2LL * hop, nbp = bp + (long long)gridDim.x * WARPS;
@@ -608,6 +622,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32r_kernel(const FirOs
                 const long long ga = base + 32 * n1 + t, gb = ga + hop;
                 v[rev32(n1)] = pk(ga < a.n_in ? __ldg(a.in + ga) : 0.f, gb < a.n_in ? __ldg(a.in + gb) : 0.f);
             }
+        }
+        if constexpr (WARPS > 1 && EARLY) {
+            __syncwarp();                                    // the landing buffer is in registers: fetch the next pair now
+            pending = bulk_src(nbp, src, mis_next, bytes);
+            if (pending && t == 0) bulk_load(Lb, src, bytes, &bar);
         }
         dft32_dit<false>(v);
 #pragma unroll
@@ -630,9 +649,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32r_kernel(const FirOs
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) v[k1] = F[k1 * kOs32Stride + t];
-        __syncwarp();                                        // the tile is free: fetch the next pair into it
-        pending = bulk_src(nbp, src, mis_next, bytes);
-        if (pending && t == 0) bulk_load(F, src, bytes, &bar);
+        if constexpr (!(WARPS > 1 && EARLY)) {
+            __syncwarp();                                    // the tile is free: fetch the next pair into it
+            pending = bulk_src(nbp, src, mis_next, bytes);
+            if (pending && t == 0) bulk_load(F, src, bytes, &bar);
+        }
         dft32_dif<true>(v);
         // circular results c[i], i = 32 n1 + t >= K-1: Re -> y[base + i - (K-1)], Im -> y[base + hop + i - (K-1)]
         float *oa = a.out + (base - Km1), *ob = oa + hop;
@@ -1399,19 +1420,22 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.n_in = (long long)in_elems; a.n_out = (long long)nq; a.K = p.K;
         const long long npair = ((long long)nq + p.hop() - 1) / p.hop();
         // one persistent 12-warp CTA per SM with the tables in shared memory (B200C_OS32R_CFG=112: 12 one-warp CTAs)
-        static const int rcfg = [] { const char *e = std::getenv("B200C_OS32R_CFG"); return e ? std::atoi(e) : 1012; }();
+        // 2012 (default): the same with a landing buffer per warp (the next pair is fetched a whole pair ahead)
+        static const int rcfg = [] { const char *e = std::getenv("B200C_OS32R_CFG"); return e ? std::atoi(e) : 2012; }();
         const size_t tile = sizeof(c2) * kOs32SmemElems;
         if (rcfg >= 1000) {
-            const size_t smem = 12 * tile + sizeof(c2) * 2048;
+            const size_t smem = 12 * tile + sizeof(c2) * 2048, smem_early = smem + sizeof(c2) * 12 * kOs32Landing;
             static thread_local bool configured[16] = {false};
             int dev = 0;
             B200C_CUDA_TRY(cudaGetDevice(&dev));
             if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
                 configured[dev] = true;
             }
             const int grid = (int)std::min<long long>((npair + 11) / 12, (long long)sm_count);
-            fir_os32r_kernel<12, 1><<<grid, 32 * 12, smem, stream>>>(a);
+            if (rcfg >= 2000) fir_os32r_kernel<12, 1, true><<<grid, 32 * 12, smem_early, stream>>>(a);
+            else fir_os32r_kernel<12, 1, false><<<grid, 32 * 12, smem, stream>>>(a);
         } else {
             const int grid = (int)std::min<long long>(npair, (long long)sm_count * 12 * 4);
             fir_os32r_kernel<1, 12><<<grid, 32, tile, stream>>>(a);
@@ -1426,7 +1450,7 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
         a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
-        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 1012; }();
+        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 2012; }();
 #define OS32_LAUNCH(W, MB)                                                                                        \
     {                                                                                                             \
         const int grid = (int)std::min<long long>((nblk + (W) - 1) / (W), (long long)sm_count * (MB) * 4);        \
@@ -1435,17 +1459,20 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         // 1012 / 1112: one persistent 12-warp CTA per SM, tap spectrum + twiddles in shared memory (single stream only),
         // all twiddles loaded / partial twiddles
         if (cfg >= 1000 && nchan == 1) {
-            const size_t smem = sizeof(c2) * (12 * (size_t)kOs32SmemElems + 2048);
+            // 2012: the same with a landing buffer per warp (the next block is fetched a whole block ahead)
+            const size_t smem = sizeof(c2) * (12 * (size_t)kOs32SmemElems + 2048), smem_early = smem + sizeof(c2) * 12 * kOs32Landing;
             static thread_local bool configured[16] = {false};
             int dev = 0;
             B200C_CUDA_TRY(cudaGetDevice(&dev));
             if (dev < 16 && !configured[dev]) {
                 B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
                 configured[dev] = true;
             }
             const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
-            if (cfg >= 1100) fir_os32_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
+            if (cfg >= 2000) fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
+            else if (cfg >= 1100) fir_os32_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
             else fir_os32_kernel<12, 1, true, false><<<grid, 32 * 12, smem, stream>>>(a);
             B200C_CUDA_TRY(cudaGetLastError());
             return B200C_OK;
