@@ -138,6 +138,17 @@ def workload_config(wl_name: str) -> dict:
             "samples_per_gpu": 1 << log2n, "l2_policy": "inputs larger than L2 (2 GiB in + 2 GiB out per pass)"}
 
 
+def workload_traffic(wl_name: str, samples: int):
+    """DRAM bytes one launch moves (ncu dram__bytes_read + write per sample, profiles/traffic.json, x the samples of
+    a launch), or None when no capture of that workload's kernel is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(wl_name)
+        return t["bytes_per_sample"] * samples if t else None
+    except Exception:
+        return None
+
+
 def cpu_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -275,7 +286,8 @@ def bench_fft(args):
         "config": {"workload": f"{args.workload}: /comms/fft {dt_name} 4096-point batched forward then inverse over 2^{log2n} samples",
                    "l2_policy": "inputs larger than L2"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "kernel": "fft"},
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": workload_traffic(args.workload, total), "peak_kind": peak_kind,
+                     "kernel": "fft"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
     }
     print(json.dumps(line))
@@ -530,13 +542,7 @@ def main():
     peaks, peak_kind = measured_peaks()
     algo_bytes = bytes_per_sample * n_seg
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(args.workload)
-            traffic = t["bytes_per_sample"] * n_seg if t else None
-    except Exception:
-        pass
+    traffic = workload_traffic(args.workload, n_seg)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                 "kernel": fir.kernel, "kernel_ms": kernel_ms,
