@@ -46,6 +46,19 @@ fir("complex_float32", "REAL", 255, 4, 3, 30001)
 fir("float32", "REAL", 64, 1, 1, 30001)
 fir("float32", "REAL", 600, 1, 1, 30001)
 fir("float32", "REAL", 101, 2, 1, 30001)
+# the same kernels in their one-warp-CTA forms, and the grouped polyphase kernel the spectral resampler replaced
+for var, val in (("B200C_OS32_CFG", "112"), ("B200C_OS32_CFG", "1012"), ("B200C_OS32R_CFG", "112"), ("B200C_OSX_MINB", "12"), ("B200C_OSX", "0")):
+    print("spawn", var, val)   # these knobs are read once per process: one child process per setting
+    import subprocess
+    child = ("import os, sys; sys.path.insert(0, %r); os.environ[%r] = %r; import numpy as np, torch; from pothoscomms_b200 import FirFilter; "
+             "f = FirFilter('complex_float32', 'REAL'); f.set_taps(np.hanning(255) / 40); f.set_rates(2, 3); "
+             "y, c, p = f.run(torch.randn((30001, 2), device='cuda')); torch.cuda.synchronize(); print(f.kernel, c, p); "
+             "g = FirFilter('complex_float32', 'COMPLEX'); g.set_taps(np.hanning(256) / 40); y, c, p = g.run(torch.randn((30001, 2), device='cuda')); "
+             "h = FirFilter('float32', 'REAL'); h.set_taps(np.hanning(64) / 10); y, c, p = h.run(torch.randn((30001, 1), device='cuda')); "
+             "torch.cuda.synchronize(); print(g.kernel, h.kernel)") % (ROOT, var, val)
+    subprocess.run([sys.executable, "-c", child], check=True)
+t = (torch.randn((4096, 2), device="cuda")).float()
+print(handles.table_source("complex_float32", t, 12345, 123, 100003).shape, handles.table_source("complex_float32", t, 5, 1, 7).shape)
 x = (torch.randn((4 * 4096, 2), device="cuda")).float()
 Fft("complex_float32", 4096, False).run(x)
 xi = (torch.randn((10001, 2), device="cuda") * 1000).to(torch.int16)
