@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Small invocations of every kernel family for `compute-sanitizer --tool memcheck python tools/sanitize_small.py`."""
+"""Small invocations of every kernel family for
+`compute-sanitizer --tool memcheck --target-processes all python tools/sanitize_small.py` (the launch-shape knobs are
+read once per process, so their other settings run in child processes)."""
 import os
 import sys
 
