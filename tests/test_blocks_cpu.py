@@ -61,6 +61,16 @@ def test_source_blocks_registry_and_factory_errors():
         blocks.make("/comms/noise_source", "uint8")
 
 
+def test_source_blocks_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pothoscomms_b200 import blocks
+    for path in ("/comms/waveform_source", "/comms/noise_source"):
+        with pytest.raises(blocks.PothosException, match="no CPU fallback"):
+            blocks.make(path, "complex_float32")
+
+
 def test_table_source_argument_errors_and_loud_failure():
     import ctypes
     import torch
