@@ -126,3 +126,26 @@ def test_noise_pool_statistics_and_stream_structure(oracle, wave, mean, b):
 def test_noise_unknown_wave(oracle):
     with pytest.raises(ValueError):
         oracle.noise_stream(oracle.F32, "PINK", 0.0, 1.0, 1, [4])
+
+
+def test_source_oracle_regression_fixtures(oracle):
+    """tests/golden/source_*.npz (made by tests/golden/make_source_golden.py): the oracle must keep producing them."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_source_golden", os.path.join(here, "make_source_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    wave = np.load(os.path.join(here, "source_waveform.npz"))
+    for name, dt, kind, freq, rate, res, ampl, off in g.WAVE_CASES:
+        code = getattr(oracle, dt)
+        table, step = oracle.waveform_table(code, kind, freq, rate, res=res, ampl=ampl, offset=off)
+        assert [table.shape[0], step] == [int(v) for v in wave[name + "_entries_step"]], name
+        assert np.array_equal(table[:64], wave[name + "_table_head"]), name
+        assert np.array_equal(oracle.table_walk(code, table, 12345, step, 3000), wave[name + "_stream"]), name
+    noise = np.load(os.path.join(here, "source_noise.npz"))
+    for name, dt, kind, mean, b, ampl, off in g.NOISE_CASES:
+        code = getattr(oracle, dt)
+        stream, pool = oracle.noise_stream(code, kind, mean, b, g.NOISE_SEED, g.NOISE_WORK, refill_before=[0, 0, 1], ampl=ampl, offset=off)
+        assert np.array_equal(pool[:256], noise[name + "_pool"]), name
+        assert np.array_equal(np.concatenate([stream[:256], stream[-300:]]), noise[name + "_stream"]), name
