@@ -4,9 +4,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this package.  The product (``pothoscomms_b200``) never
 does; it fails loudly if its CUDA library is missing instead of falling back to this.
 
-* ``fir(...)``      : C restatement of filter/FIRFilter.cpp:278-302,327-354 (``liboracle.so``).
-                      The FIR block cannot be compiled here (PothosCore absent) => kind "port";
-                      Q-format rounding is PARITY UNPINNED (see qformat.h).
+* ``fir(...)``      : C restatement of filter/FIRFilter.cpp:278-302,327-354 (``liboracle.so``), pinned
+                      bit-for-bit against ``ref_fir`` (tests/test_oracle_fir.py).
+* ``ref_fir(...)``, ``ref_fir_stream(...)`` : the REFERENCE's own filter/FIRFilter.cpp, compiled unmodified
+                      from /root/reference into ``oracle/_ref/libfirref.so`` against the repo's Pothos API
+                      subset and a RECALLED Pothos/Util/QFormat.hpp (the one external header; its rounding
+                      is the only thing still unpinned, see oracle/ref_include/Pothos/Util/QFormat.hpp).
 * ``fft(...)``      : C restatement of fft/kissfft.hh + fft/kiss_fft.c (``liboracle.so``), pinned
                       bit-for-bit against ``ref_fft``.
 * ``ref_fft(...)``  : the REFERENCE's own kiss_fft sources compiled from /root/reference into
@@ -45,13 +48,19 @@ def build(force: bool = False) -> None:
     lib = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("fir_oracle.c", "fft_oracle.c", "math_oracle.c", "source_oracle.cpp", "qformat.h", "Makefile")]
     stale = force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs)
-    ref = os.path.join(_HERE, "_ref", "libkissref.so")
-    if stale or (not os.path.exists(ref) and os.path.exists("/root/reference/fft/kiss_fft.c")):
+    have_checkout = os.path.exists("/root/reference/fft/kiss_fft.c")
+    refs = [os.path.join(_HERE, "_ref", n) for n in ("libkissref.so", "libfirref.so")]
+    ref_srcs = [os.path.join(_HERE, f) for f in ("ref_fir_wrap.cpp", "ref_wrap.cpp", "ref_include/Pothos/Util/QFormat.hpp")]
+    ref_stale = have_checkout and any(not os.path.exists(r) or any(os.path.getmtime(s) > os.path.getmtime(r) for s in ref_srcs)
+                                      for r in refs)
+    if stale or ref_stale:
         subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True, capture_output=True)
 
 
 _lib = None
 _ref = None
+_firref = None
+DTYPE_NAMES = {v: k for k, v in DTYPE_CODES.items()}
 
 
 def lib():
@@ -92,6 +101,95 @@ def ref():
         _ref.ref_fft.argtypes = [i, sz, i, vp, vp, sz]
         _ref.ref_fft_mt.argtypes = [i, i, sz, i, vp, vp, sz]
     return _ref
+
+
+def have_ref_fir() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libfirref.so"))
+
+
+def firref():
+    """The reference's own filter/FIRFilter.cpp, compiled (oracle/_ref/libfirref.so)."""
+    global _firref
+    if _firref is None:
+        build()
+        _firref = ctypes.CDLL(os.path.join(_HERE, "_ref", "libfirref.so"))
+        sz, vp, i, cp = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p
+        _firref.firref_last_error.restype = cp
+        _firref.firref_stream.argtypes = [cp, cp, vp, sz, sz, sz, vp, sz, vp, sz, sz, sz, i, vp, vp, vp]
+        _firref.firref_work.argtypes = [cp, cp, vp, sz, sz, sz, vp, sz, vp, sz, vp, vp]
+        _firref.firref_work_mt.argtypes = [i, cp, cp, vp, sz, sz, sz, vp, sz, vp, sz, vp, vp]
+        _firref.firref_input_require.argtypes = [cp, cp, vp, sz, sz, sz]
+        _firref.firref_input_require.restype = ctypes.c_long
+    return _firref
+
+
+class ReferenceError_(ValueError):
+    """An exception thrown by the reference block (factory or setter), text preserved."""
+
+
+def _ref_fir_args(dtype_code, taps_complex, taps, x_raw):
+    t = _as_taps(taps, taps_complex)
+    ntaps = t.size // (2 if taps_complex else 1)
+    ncomp = 2 if is_complex(dtype_code) else 1
+    x_raw = np.ascontiguousarray(x_raw, dtype=scalar_np(dtype_code)).reshape(-1, ncomp)
+    return t, ntaps, ncomp, x_raw, DTYPE_NAMES[dtype_code].encode(), (b"COMPLEX" if taps_complex else b"REAL")
+
+
+def ref_fir(dtype_code: int, taps_complex: bool, taps, decim: int, interp: int, x_raw: np.ndarray,
+            out_capacity: int | None = None, threads: int = 1):
+    """ONE work() call of the reference block on the window ``x_raw`` (K-1 history then new data):
+    same contract as ``fir(..., zero_tail=False)``.  threads > 1: that many block instances, each on
+    its own equal share of x_raw ([threads, seg, ncomp]) -- the CPU baseline driver."""
+    t, ntaps, ncomp, x_raw, dn, tn = _ref_fir_args(dtype_code, taps_complex, taps, x_raw)
+    cons, prod = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    if threads > 1:
+        seg = x_raw.shape[0] // threads
+        cap = (seg // decim + 1) * interp
+        out = np.zeros((threads, cap, ncomp), dtype=x_raw.dtype)
+        rc = firref().firref_work_mt(threads, dn, tn, t.ctypes.data, ntaps, decim, interp, x_raw.ctypes.data, seg,
+                                     out.ctypes.data, cap, ctypes.addressof(cons), ctypes.addressof(prod))
+        if rc:
+            raise ReferenceError_(firref().firref_last_error().decode())
+        return out, cons.value, prod.value
+    n_in = x_raw.shape[0]
+    if out_capacity is None:
+        out_capacity = (n_in // max(decim, 1) + 1) * interp
+    out = np.zeros((max(out_capacity, 1), ncomp), dtype=x_raw.dtype)
+    rc = firref().firref_work(dn, tn, t.ctypes.data, ntaps, decim, interp, x_raw.ctypes.data, n_in, out.ctypes.data,
+                              out_capacity, ctypes.addressof(cons), ctypes.addressof(prod))
+    if rc:
+        raise ReferenceError_(firref().firref_last_error().decode())
+    return out[: prod.value], cons.value, prod.value
+
+
+def ref_fir_stream(dtype_code: int, taps_complex: bool, taps, decim: int, interp: int, x_raw: np.ndarray,
+                   in_chunk: int = 0, out_chunk: int = 0, frame_end: bool = False, out_capacity: int | None = None):
+    """Stream ``x_raw`` through one reference block instance the way feeder -> fir_filter -> collector does
+    (filter/TestFIRFilter.cpp:19-53): ``in_chunk`` elements arrive per round, ``out_chunk`` output elements are
+    offered per work(); ``frame_end`` labels the last element as the end of a burst (flush path :263-272).
+    Returns (out_raw, consumed, produced, work_calls)."""
+    t, ntaps, ncomp, x_raw, dn, tn = _ref_fir_args(dtype_code, taps_complex, taps, x_raw)
+    n_in = x_raw.shape[0]
+    if out_capacity is None:
+        out_capacity = (n_in // decim + 2) * interp
+    out = np.zeros((max(out_capacity, 1), ncomp), dtype=x_raw.dtype)
+    cons, prod, calls = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    rc = firref().firref_stream(dn, tn, t.ctypes.data, ntaps, decim, interp, x_raw.ctypes.data, n_in, out.ctypes.data,
+                                out_capacity, in_chunk, out_chunk, int(frame_end), ctypes.addressof(cons),
+                                ctypes.addressof(prod), ctypes.addressof(calls))
+    if rc:
+        raise ReferenceError_(firref().firref_last_error().decode())
+    return out[: prod.value], cons.value, prod.value, calls.value
+
+
+def ref_fir_input_require(dtype_code: int, taps_complex: bool, taps, decim: int, interp: int) -> int:
+    """_inputRequire = M + K - 1 of the reference block (filter/FIRFilter.cpp:353), read back through the
+    reserve it sets when starved (:248-252)."""
+    t, ntaps, _, _, dn, tn = _ref_fir_args(dtype_code, taps_complex, taps, np.zeros((1, 2 if is_complex(dtype_code) else 1)))
+    r = firref().firref_input_require(dn, tn, t.ctypes.data, ntaps, decim, interp)
+    if r < 0:
+        raise ReferenceError_(firref().firref_last_error().decode())
+    return int(r)
 
 
 def _as_taps(taps, taps_complex: bool) -> np.ndarray:

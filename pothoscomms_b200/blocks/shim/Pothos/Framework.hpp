@@ -104,6 +104,8 @@ public:
         return Convert<T>::from(*this);
     }
     template <typename T> const T &extract() const { return static_cast<const Holder<T> *>(_p.get())->v; }
+    // Pothos::Object's explicit cast, `double(label.data)` at filter/FIRFilter.cpp:319
+    template <typename T> explicit operator T() const { return convert<T>(); }
 
 private:
     struct Base { virtual ~Base() = default; };
@@ -204,10 +206,23 @@ public:
     virtual void pop(size_t numBytes) = 0;           // `numBytes` of front() were filled
     virtual void push(size_t numBytes) = 0;          // `numBytes` were released by the reader
     virtual std::string domain() const { return ""; } // "" = host memory
-    // factory for host managers is not provided by the shim: device blocks bring their own
-    static Sptr make(const std::string &name, const BufferManagerArgs & = BufferManagerArgs())
+    // Named factories, as PothosCore's plugin tree /framework/buffer_manager/<name> provides them.  The
+    // shim itself registers none (device blocks bring their own managers); a host that wants the reference's
+    // make("circular") (filter/FIRFilter.cpp:198) registers one -- oracle/ref_fir_wrap.cpp does.
+    typedef std::function<Sptr(const BufferManagerArgs &)> Factory;
+    static void registerFactory(const std::string &name, Factory f) { factories()[name] = std::move(f); }
+    static Sptr make(const std::string &name, const BufferManagerArgs &args = BufferManagerArgs())
     {
-        throw Exception("BufferManager::make(" + name + ")", "host buffer managers are not part of the B200 shim");
+        auto it = factories().find(name);
+        if (it == factories().end()) throw Exception("BufferManager::make(" + name + ")", "no such buffer manager factory in this host");
+        return it->second(args);
+    }
+
+private:
+    static std::map<std::string, Factory> &factories()
+    {
+        static std::map<std::string, Factory> f;
+        return f;
     }
 };
 

@@ -1,9 +1,11 @@
-"""Known-answer tests pinning the FIR oracle's structure (CPU, no GPU needed).
+"""Tests pinning the FIR oracle (CPU, no GPU needed).
 
-The reference FIR block cannot be compiled here (needs PothosCore), and its own test
-(filter/TestFIRFilter.cpp:78) only asserts rms > 0.1*amplitude, so the oracle is pinned by
-structural identities that follow from filter/FIRFilter.cpp:278-302,327-354 plus an
-independent numpy restatement of the same loop nest.
+1. Against the REFERENCE ITSELF: filter/FIRFilter.cpp compiled unmodified into oracle/_ref/libfirref.so
+   (oracle/Makefile ref_fir; Pothos API subset + a recalled QFormat.hpp): bit-for-bit on all 18 factory
+   rows x the rate grid x burst flush x chunked streaming, plus _inputRequire and the thrown messages.
+2. Structural identities that follow from filter/FIRFilter.cpp:278-302,327-354 and an independent numpy
+   restatement of the loop nest (the reference's own test, filter/TestFIRFilter.cpp:78, only asserts
+   rms > 0.1*amplitude).
 """
 import os
 
@@ -209,7 +211,8 @@ def test_multithreaded_driver_equals_single(oracle):
     assert a[1:] == b[1:] and np.array_equal(a[0], b[0])
 
 
-def test_fir_regression_fixtures(oracle):
+def test_fir_golden_fixtures(oracle):
+    """tests/golden/fir_*.npz are outputs of the REFERENCE's compiled block (make_golden.py, `source` field)."""
     files = sorted(f for f in os.listdir(GOLDEN) if f.startswith("fir_") and f.endswith(".npz"))
     assert files
     for fn in files:
@@ -217,3 +220,135 @@ def test_fir_regression_fixtures(oracle):
         y, cons, prod = oracle.fir(int(g["dtype"]), bool(g["taps_complex"]), g["taps"], int(g["M"]), int(g["L"]), g["x"])
         assert cons == int(g["consumed"]) and prod == int(g["produced"]), fn
         assert np.array_equal(y.view(np.uint8), g["y"].view(np.uint8)), fn
+        assert str(g["source"]) == "reference:filter/FIRFilter.cpp", fn
+
+
+# ------------------------------------------------------------------------------------------------
+# Pinned against the reference's own compiled block (oracle/_ref/libfirref.so)
+# ------------------------------------------------------------------------------------------------
+RATES = [(1, 1), (2, 1), (3, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3), (5, 4), (4, 6), (7, 3), (16, 1), (1, 16)]
+ROWS = [(dt, tcx) for dt in ("F32", "CF32", "F64", "CF64", "I8", "CI8", "I16", "CI16", "I32", "CI32", "I64", "CI64")
+        for tcx in (False, True) if not (tcx and dt[0] != "C")]
+
+
+def _rand_stream(oracle, code, n, rng):
+    nc = 2 if code & 1 else 1
+    sc = oracle.scalar_np(code)
+    if np.issubdtype(sc, np.integer):
+        info = np.iinfo(sc)
+        return rng.integers(info.min, info.max, size=(n, nc), endpoint=True).astype(sc)   # full scale: sums wrap
+    return rng.standard_normal((n, nc)).astype(sc)
+
+
+def _rand_taps(ntaps, tcx, rng, scale=0.3):
+    t = rng.standard_normal(ntaps) * scale
+    return t + 1j * rng.standard_normal(ntaps) * scale if tcx else t
+
+
+def _same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libfirref.so"))
+                               and not os.path.exists("/root/reference/filter/FIRFilter.cpp"),
+                               reason="oracle/_ref/libfirref.so not built and no reference checkout")
+
+
+@needs_ref
+def test_reference_factory_has_18_rows(oracle):
+    assert len(ROWS) == 18   # filter/FIRFilter.cpp:373-382
+    for dt, tcx in ROWS:
+        oracle.ref_fir(getattr(oracle, dt), tcx, [1.0], 1, 1, np.zeros((4, 2)))
+    for dt in ("F32", "F64", "I8", "I16", "I32", "I64"):   # real data + COMPLEX taps throws (:383)
+        with pytest.raises(oracle.ReferenceError_, match=r"FIRFilterFactory\(.*\).*unsupported types"):
+            oracle.ref_fir(getattr(oracle, dt), True, [1.0 + 0j], 1, 1, np.zeros((4, 1)))
+
+
+@needs_ref
+@pytest.mark.parametrize("dt,tcx", ROWS)
+def test_oracle_equals_reference_block_on_rate_grid(oracle, dt, tcx):
+    """oracle.fir (the restatement every GPU parity test compares with) == one work() of the reference's own
+    compiled block, bit for bit (floats too: same scalar order, no contraction), 18 rows x RATES."""
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(sum(map(ord, dt)) * 2 + tcx)
+    x = _rand_stream(oracle, code, 1500, rng)
+    for M, L in RATES:
+        for ntaps in (1, 2, 33, 101):
+            taps = _rand_taps(ntaps, tcx, rng)
+            y, c, p = oracle.fir(code, tcx, taps, M, L, x)
+            yr, cr, pr = oracle.ref_fir(code, tcx, taps, M, L, x)
+            assert (c, p) == (cr, pr), (M, L, ntaps)
+            assert _same_bits(y, yr), (M, L, ntaps)
+            assert oracle.ref_fir_input_require(code, tcx, taps, M, L) == M + oracle.fir_K(ntaps, L) - 1   # :353
+
+
+@needs_ref
+@pytest.mark.parametrize("dt,tcx", ROWS)
+def test_oracle_zero_tail_equals_reference_burst_flush(oracle, dt, tcx):
+    """A burst ending in a frame-end label: the reference flushes it through a K-1 zero tail (:226-229,263-272)
+    over as many work() calls as it takes; the oracle's zero_tail=True is the same samples in one call."""
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(7700 + sum(map(ord, dt)) * 2 + tcx)
+    for M, L in RATES:
+        for ntaps, B in ((33, 400), (101, 257), (7, 64)):
+            K = oracle.fir_K(ntaps, L)
+            x = _rand_stream(oracle, code, B, rng)
+            taps = _rand_taps(ntaps, tcx, rng)
+            y, c, p = oracle.fir(code, tcx, taps, M, L, x, zero_tail=True)
+            yr, cr, pr, calls = oracle.ref_fir_stream(code, tcx, taps, M, L, x, frame_end=True)
+            assert (c, p) == (cr, pr) == (B // M * M, B // M * L), (M, L, ntaps, B)
+            assert _same_bits(y, yr), (M, L, ntaps, B)
+            assert calls >= (2 if B >= M + K - 1 and K > 1 else 1)
+
+
+@needs_ref
+@pytest.mark.parametrize("dt,tcx", [("CF32", True), ("CF32", False), ("F32", False), ("CI16", True), ("I16", False), ("CI8", True),
+                                    ("I64", False)])
+def test_reference_streaming_in_chunks_equals_one_work_call(oracle, dt, tcx):
+    """The time-domain nest has no block structure: however the scheduler chunks the stream (input arriving
+    in pieces, small output buffers), the reference's outputs are the oracle's one-call outputs, bit for bit."""
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(5)
+    x = _rand_stream(oracle, code, 5000, rng)
+    for (M, L), ntaps in zip([(1, 1), (2, 3), (3, 2), (4, 1)], (64, 101, 255, 17)):
+        taps = _rand_taps(ntaps, tcx, rng)
+        y, c, p = oracle.fir(code, tcx, taps, M, L, x)
+        for in_chunk, out_chunk in ((0, 0), (700, 0), (0, 301), (333, 97)):
+            yr, cr, pr, calls = oracle.ref_fir_stream(code, tcx, taps, M, L, x, in_chunk=in_chunk, out_chunk=out_chunk)
+            assert (c, p) == (cr, pr), (M, L, in_chunk, out_chunk)
+            assert _same_bits(y, yr), (M, L, in_chunk, out_chunk)
+            if in_chunk or out_chunk:
+                assert calls > 1
+
+
+@needs_ref
+def test_reference_setter_errors(oracle):
+    x = np.zeros((8, 2), dtype=np.float32)
+    with pytest.raises(oracle.ReferenceError_, match="taps cannot be empty"):         # :140
+        oracle.ref_fir(oracle.CF32, False, [], 1, 1, x)
+    with pytest.raises(oracle.ReferenceError_, match="decimation cannot be 0"):       # :153
+        oracle.ref_fir(oracle.CF32, False, [1.0], 0, 1, x)
+    with pytest.raises(oracle.ReferenceError_, match="interpolation cannot be 0"):    # :165
+        oracle.ref_fir(oracle.CF32, False, [1.0], 1, 0, x)
+
+
+@needs_ref
+def test_reference_latent_stall_remainder_below_M(oracle):
+    """a flushed remainder < M is never consumed (N = 0 forever, :278)."""
+    x = np.arange(10, dtype=np.float32).reshape(-1, 1)
+    yr, cr, pr, _ = oracle.ref_fir_stream(oracle.F32, False, [1.0, 1.0], 3, 1, x, frame_end=True)
+    assert (cr, pr) == (9, 3)
+    y, c, p = oracle.fir(oracle.F32, False, [1.0, 1.0], 3, 1, x, zero_tail=True)
+    assert (c, p) == (9, 3) and _same_bits(y, yr)
+
+
+@needs_ref
+def test_multithreaded_reference_driver_equals_port_segments(oracle):
+    rng = np.random.default_rng(8)
+    taps = _rand_taps(31, True, rng)
+    x = _rand_stream(oracle, oracle.CF32, 4 * 1000, rng)
+    out, c, p = oracle.ref_fir(oracle.CF32, True, taps, 2, 3, x, threads=4)
+    for t in range(4):
+        y, ct, pt = oracle.fir(oracle.CF32, True, taps, 2, 3, x[t * 1000:(t + 1) * 1000])
+        assert _same_bits(out[t, :pt], y)
+    assert p == 4 * pt and c == 4 * ct
