@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 1
+#define B200C_ABI_VERSION 2
 
 /* status codes */
 #define B200C_OK 0
@@ -170,6 +170,51 @@ int b200c_copy_d2h(void *h_dst, const void *d_src, size_t bytes, int device, voi
 int b200c_copy_d2d(void *d_dst, const void *d_src, size_t bytes, int device, void *stream);
 int b200c_memset(void *d_dst, int value, size_t bytes, int device, void *stream);
 int b200c_stream_sync(int device, void *stream);
+
+/* ------------------------------------------- multi-GPU: the K-1 halo --- */
+/* One long stream cut into contiguous segments, one per GPU, every segment start a multiple of M (the
+ * decimation counter restarts at M in every work() call, filter/FIRFilter.cpp:283,291-292).  The only
+ * dependency between segments is the K-1 samples of left history (:281,298): GPU r keeps its segment as
+ * [K-1 halo | n samples] and, before each pass, pulls the last K-1 samples of GPU r-1's segment into the
+ * halo -- b200c_halo_exchange, ONE copy over NVLink enqueued on the consumer's compute stream.  GPU 0's
+ * halo is the stream's true first K-1 samples (history only, as in the reference).  No torch, no
+ * collective library: a C++ Pothos host shards a stream with these calls alone.
+ *
+ * One process per GPU: the owner exports a range of device memory (cudaMalloc-backed: b200c_dev_alloc or
+ * a framework allocator's block) as a plain 128-byte record, the host program carries the record to the
+ * neighbour process however it likes, the neighbour opens it.  When exporter and opener are the same
+ * process the pointer is used directly (peer access is enabled on first use). */
+typedef struct b200c_peer_mem {
+    unsigned char ipc[64];   /* cudaIpcMemHandle_t of the allocation that holds the range */
+    uint64_t offset, bytes;  /* the range inside it */
+    uint64_t local_ptr;      /* the exporter's own pointer (meaningful in the exporting process only) */
+    int64_t pid;             /* exporting process */
+    int32_t device;          /* exporter's device ordinal */
+    int32_t reserved[7];
+} b200c_peer_mem;
+int b200c_peer_export(const void *d_ptr, size_t bytes, int device, b200c_peer_mem *out);
+/* *d_peer_ptr: the range, addressable from `device`; *mapping: token for b200c_peer_close */
+int b200c_peer_open(const b200c_peer_mem *m, int device, void **d_peer_ptr, void **mapping);
+int b200c_peer_close(void *mapping);
+
+/* Ordering between the producer of a segment's tail and the neighbour that pulls it: an interprocess
+ * event.  The owner records it on its stream once the tail is final; the neighbour makes its compute
+ * stream wait for it before b200c_halo_exchange. */
+typedef struct b200c_peer_event {
+    unsigned char ipc[64];   /* cudaIpcEventHandle_t */
+    uint64_t local_event;    /* meaningful in the creating process only */
+    int64_t pid;
+    int32_t reserved[12];
+} b200c_peer_event;
+int b200c_peer_event_create(void **event, int device, b200c_peer_event *out);
+int b200c_peer_event_open(const b200c_peer_event *e, int device, void **event);
+int b200c_peer_event_record(void *event, int device, void *stream);
+int b200c_peer_event_wait(void *event, int device, void *stream);
+int b200c_peer_event_destroy(void *event, int device);
+
+/* d_halo_dst[0 .. bytes) = d_peer_tail[0 .. bytes), bytes = (K-1) * element size, asynchronous on `stream`
+ * (the stream b200c_fir_run is then given).  d_peer_tail comes from b200c_peer_open. */
+int b200c_halo_exchange(void *d_halo_dst, const void *d_peer_tail, size_t bytes, int device, void *stream);
 
 #ifdef __cplusplus
 }

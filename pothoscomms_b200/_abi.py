@@ -68,7 +68,18 @@ SYMBOLS = {
     "b200c_copy_d2d": (_i, [_vp, _vp, _sz, _i, _vp]),
     "b200c_memset": (_i, [_vp, _i, _sz, _i, _vp]),
     "b200c_stream_sync": (_i, [_i, _vp]),
+    # multi-GPU halo (b200c_peer_mem / b200c_peer_event are 128-byte PODs passed as raw buffers)
+    "b200c_peer_export": (_i, [_vp, _sz, _i, _vp]),
+    "b200c_peer_open": (_i, [_vp, _i, _pvp, _pvp]),
+    "b200c_peer_close": (_i, [_vp]),
+    "b200c_peer_event_create": (_i, [_pvp, _i, _vp]),
+    "b200c_peer_event_open": (_i, [_vp, _i, _pvp]),
+    "b200c_peer_event_record": (_i, [_vp, _i, _vp]),
+    "b200c_peer_event_wait": (_i, [_vp, _i, _vp]),
+    "b200c_peer_event_destroy": (_i, [_vp, _i]),
+    "b200c_halo_exchange": (_i, [_vp, _vp, _sz, _i, _vp]),
 }
+PEER_RECORD_BYTES = 128   # sizeof(b200c_peer_mem) == sizeof(b200c_peer_event)
 
 
 class B200CommsError(RuntimeError):

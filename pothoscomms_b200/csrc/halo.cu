@@ -1,0 +1,180 @@
+// Multi-GPU plumbing of the one exchange the FIR path has: the K-1 history samples at a
+// segment boundary (filter/FIRFilter.cpp:281,298).  One process per GPU: the left neighbour's segment is
+// opened through CUDA IPC (or used directly when both GPUs belong to this process) and the halo is PULLED
+// over NVLink by a copy enqueued on the consumer's compute stream -- no collective, no extra kernel, no
+// host round trip; ordering against the producer is an interprocess event.  See include/b200comms.h.
+#include <cuda.h>
+#include <unistd.h>
+
+#include <cstring>
+
+#include "common.hpp"
+
+using namespace b200c;
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(cudaIpcEventHandle_t) == 64, "IPC handles are 64 bytes");
+
+struct PeerMapping {   // what b200c_peer_open hands out, so that close knows what to undo
+    void *base;        // cudaIpcOpenMemHandle result (nullptr for a same-process pointer)
+    int device;
+};
+
+extern "C" {
+
+int b200c_peer_export(const void *d_ptr, size_t bytes, int device, b200c_peer_mem *out)
+{
+    if (!d_ptr || !out) { set_error("b200c_peer_export: null argument"); return B200C_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    std::memset(out, 0, sizeof(*out));
+    CUdeviceptr base = 0;
+    size_t span = 0;
+    // fetched through the runtime: libb200comms.so has no link-time dependency on libcuda.so.1
+    typedef CUresult (*fn_range)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static fn_range p_range = nullptr;
+    if (!p_range) {
+        cudaDriverEntryPointQueryResult qr;
+        void *fp = nullptr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp) {
+            (void)cudaGetLastError();
+            set_error("CUDA driver entry point cuMemGetAddressRange unavailable");
+            return B200C_ERR_CUDA;
+        }
+        p_range = (fn_range)fp;
+    }
+    B200C_CUDA_TRY(cudaFree(0));
+    if (p_range(&base, &span, (CUdeviceptr)d_ptr) != CUDA_SUCCESS) {
+        set_error("b200c_peer_export: %p is not a device allocation", d_ptr);
+        return B200C_ERR_INVALID;
+    }
+    const size_t off = (size_t)((CUdeviceptr)d_ptr - base);
+    if (off + bytes > span) { set_error("b200c_peer_export: range exceeds its allocation"); return B200C_ERR_INVALID; }
+    cudaIpcMemHandle_t mh;
+    B200C_CUDA_TRY(cudaIpcGetMemHandle(&mh, (void *)base));
+    std::memcpy(out->ipc, &mh, 64);
+    out->offset = off;
+    out->bytes = bytes;
+    out->device = device;
+    out->pid = (int64_t)getpid();
+    out->local_ptr = (uint64_t)(uintptr_t)d_ptr;
+    return B200C_OK;
+}
+
+int b200c_peer_open(const b200c_peer_mem *m, int device, void **d_peer_ptr, void **mapping)
+{
+    if (!m || !d_peer_ptr || !mapping) { set_error("b200c_peer_open: null argument"); return B200C_ERR_INVALID; }
+    *d_peer_ptr = nullptr; *mapping = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    PeerMapping *pm = new PeerMapping{nullptr, device};
+    if (m->pid == (int64_t)getpid()) {
+        // both GPUs in this process: unified addressing makes the pointer usable as it is; direct access
+        // (instead of a staged copy) needs peer access enabled once
+        if (m->device != device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device, m->device) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); }
+                (void)cudaGetLastError();
+            }
+        }
+        *d_peer_ptr = (void *)(uintptr_t)m->local_ptr;
+    } else {
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, m->ipc, 64);
+        void *base = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            delete pm;
+            return B200C_ERR_CUDA;
+        }
+        pm->base = base;
+        *d_peer_ptr = static_cast<char *>(base) + m->offset;
+    }
+    *mapping = pm;
+    return B200C_OK;
+}
+
+int b200c_peer_close(void *mapping)
+{
+    PeerMapping *pm = static_cast<PeerMapping *>(mapping);
+    if (!pm) return B200C_OK;
+    int rc = B200C_OK;
+    if (pm->base) {
+        DeviceGuard g(pm->device);
+        if (cudaIpcCloseMemHandle(pm->base) != cudaSuccess) { (void)cudaGetLastError(); rc = B200C_ERR_CUDA; set_error("cudaIpcCloseMemHandle failed"); }
+    }
+    delete pm;
+    return rc;
+}
+
+int b200c_peer_event_create(void **event, int device, b200c_peer_event *out)
+{
+    if (!event || !out) { set_error("b200c_peer_event_create: null argument"); return B200C_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    cudaEvent_t ev;
+    B200C_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
+    cudaIpcEventHandle_t eh;
+    const cudaError_t e = cudaIpcGetEventHandle(&eh, ev);
+    if (e != cudaSuccess) { cudaEventDestroy(ev); set_error("cudaIpcGetEventHandle failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return B200C_ERR_CUDA; }
+    std::memset(out, 0, sizeof(*out));
+    std::memcpy(out->ipc, &eh, 64);
+    out->pid = (int64_t)getpid();
+    out->local_event = (uint64_t)(uintptr_t)ev;
+    *event = ev;
+    return B200C_OK;
+}
+
+int b200c_peer_event_open(const b200c_peer_event *e, int device, void **event)
+{
+    if (!e || !event) { set_error("b200c_peer_event_open: null argument"); return B200C_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    if (e->pid == (int64_t)getpid()) { *event = (void *)(uintptr_t)e->local_event; return B200C_OK; }
+    cudaIpcEventHandle_t eh;
+    std::memcpy(&eh, e->ipc, 64);
+    cudaEvent_t ev;
+    B200C_CUDA_TRY(cudaIpcOpenEventHandle(&ev, eh));
+    *event = ev;
+    return B200C_OK;
+}
+
+int b200c_peer_event_record(void *event, int device, void *stream)
+{
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    B200C_CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return B200C_OK;
+}
+
+int b200c_peer_event_wait(void *event, int device, void *stream)
+{
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    B200C_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return B200C_OK;
+}
+
+int b200c_peer_event_destroy(void *event, int device)
+{
+    if (!event) return B200C_OK;
+    DeviceGuard g(device);
+    B200C_CUDA_TRY(cudaEventDestroy((cudaEvent_t)event));
+    return B200C_OK;
+}
+
+int b200c_halo_exchange(void *d_halo_dst, const void *d_peer_tail, size_t bytes, int device, void *stream)
+{
+    if (bytes == 0) return B200C_OK;
+    if (!d_halo_dst || !d_peer_tail) { set_error("b200c_halo_exchange: null buffer"); return B200C_ERR_INVALID; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
+    // unified addressing: the runtime routes the copy over NVLink (peer mapped by b200c_peer_open)
+    B200C_CUDA_TRY(cudaMemcpyAsync(d_halo_dst, d_peer_tail, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return B200C_OK;
+}
+
+} // extern "C"

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_dtype_sizes():
     from pothoscomms_b200 import _abi
     lib = _abi.lib()
-    assert lib.b200c_abi_version() == 1
+    assert lib.b200c_abi_version() == 2
     sizes = [lib.b200c_dtype_size(i) for i in range(12)]
     assert sizes == [4, 8, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16]
     assert lib.b200c_dtype_size(99) == 0

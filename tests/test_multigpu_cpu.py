@@ -95,3 +95,16 @@ def test_segment_bounds_are_M_aligned_and_cover():
             assert e0 == s1
         assert all(s % M == 0 and e % M == 0 for s, e in b)
     assert [sharding.channel_range(1024, 8, r) for r in range(8)] == [(128 * r, 128 * (r + 1)) for r in range(8)]
+
+
+def test_segments_shorter_than_the_halo_are_rejected():
+    """A segment shorter than K-1 would forward halo samples it has only just received (its tail and its
+    halo overlap in [halo | segment]): refused, never silently wrong."""
+    from pothoscomms_b200 import sharding
+    with pytest.raises(ValueError, match="shorter than the K-1"):
+        sharding.segment_bounds(1000, 8, 1, K=256)
+    with pytest.raises(ValueError, match="shorter than the K-1"):
+        sharding.check_segment(100, 128, rank=1, world=2)
+    sharding.check_segment(127, 128, rank=1, world=2)
+    sharding.check_segment(5, 128, rank=0, world=1)      # a single rank has no neighbour
+    assert len(sharding.segment_bounds(1 << 16, 8, 2, K=256)) == 8
