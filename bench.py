@@ -688,13 +688,51 @@ def bench_bank(ctx: Ctx, steps: int, warmup: int, e2e: bool, cpu: bool, channels
             "parity": f"channel {c0}: rel RMS error {err:.1e} vs oracle on {p_ref} outputs; == its single-stream filter bit for bit"}
 
 
+def bench_blocks(ctx: Ctx, rounds_budget_s: float = 1.0) -> dict:
+    """The streaming path the drop-in actually runs (filter/FIRFilter.cpp:207-309, :196-199): the C++ /comms/fir_filter
+    block of pothoscomms_b200/blocks between two device neighbours -- work() once per buffer, input in the VMM
+    double-mapped HBM ring with the K-1 history left in place, one kernel launch per work(), no host<->device copy
+    in the loop -- for work() buffers of 1, 4, 8 and 32 MiB.  value = the 8 MiB row (Pothos' default buffer size)."""
+    from pothoscomms_b200 import blocks
+    wl = _workloads_module()
+    taps, tt = wl.config_taps("headline")
+    pat = wl.tone_noise_numpy(DTYPE_CODES["complex_float32"], 1 << 20, seed=0xC0FFEE01)
+    rows = []
+    for mib in (1, 4, 8, 32):
+        chunk = (mib << 20) // 8
+        f = blocks.make("/comms/fir_filter", "complex_float32", tt, in_bytes=max(4 * chunk * 8, 512 << 20), out_bytes=2 * chunk * 8)
+        f.call("setTaps", taps)
+        f.activate()
+        rounds = max(20, min(4000, int(rounds_budget_s * 250e9 / chunk)))
+        secs = f.stream_bench(pat, chunk, rounds)
+        calls = f.work_calls
+        rows.append({"work_buffer_mib": mib, "value": rounds * chunk / secs / 1e6, "unit": UNIT, "work_calls_per_s": rounds / secs,
+                     "us_per_work": secs / rounds * 1e6, "rounds": rounds, "work_calls": calls, "seam_windows": f.seam_windows,
+                     "hbm_frac": 16.0 * rounds * chunk / secs / 1e9 / ctx.peaks["hbm_gbs"]})
+        f.close()
+    main_row = rows[2]
+    wl_text = ("headline_blocks: source -> /comms/fir_filter (C++ block layer, complex_float32 256 COMPLEX taps) -> sink between "
+               "device neighbours, HBM ring + slabs, one launch per work(); work() buffers 1/4/8/32 MiB")
+    return {"workload": wl_text, "config": {"workload": wl_text}, "value": main_row["value"], "unit": UNIT,
+            "ms_per_step": main_row["us_per_work"] / 1e3, "steps": main_row["rounds"], "warmup": 3, "scaling": "weak", "n_gpus": 1,
+            "dtype": "f32",
+            "roofline": {"bound": "hbm", "achieved": main_row["hbm_frac"] * ctx.peaks["hbm_gbs"], "peak": ctx.peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": main_row["hbm_frac"], "traffic": None, "peak_kind": ctx.peak_kind,
+                         "kernel": "fir_os32_kernel", "algorithmic_bytes_per_sample": 16.0,
+                         "note": "wall clock over `rounds` work() calls incl. the block layer's host code; 8 MiB work() buffers; input "
+                                 "streams from a 512 MiB HBM ring (> L2), the two output slabs are reused and stay L2-resident as they "
+                                 "would between two Pothos device blocks"},
+            "per_buffer_size": rows, "cpu_baseline": None, "e2e": None, "gpu_launches": main_row["rounds"], "clocks": None,
+            "parity": "tests/test_blocks_gpu.py (block output == oracle, incl. across the ring seam)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4", "c4_i16", "c5_bank"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4", "c4_i16", "c5_bank", "headline_blocks"])
     ap.add_argument("--configs", default=None, choices=["all", "none"],
                     help="also measure the other BASELINE configs into `configs` (default: all for the headline workload)")
     ap.add_argument("--ntaps", type=int, default=None, help="tap-count sweep: cf32 L=M=1 with this many complex taps")
@@ -710,7 +748,9 @@ def main():
     e2e, cpu = not args.no_e2e, not args.no_cpu
 
     ctx = Ctx()
-    if args.workload in ("c4", "c4_i16"):
+    if args.workload == "headline_blocks":
+        main_rec = bench_blocks(ctx)
+    elif args.workload in ("c4", "c4_i16"):
         main_rec = bench_fft(ctx, args.workload, args.steps, args.warmup, e2e, cpu, args.log2_samples)
     elif args.workload == "c5_bank":
         main_rec = bench_bank(ctx, args.steps, args.warmup, e2e, cpu and ctx.world == 1, args.channels, args.log2_samples)
@@ -722,7 +762,7 @@ def main():
         sub_steps, sub_warm = max(3, min(args.steps, 5)), 3
         if ctx.world == 1:
             plan = [("stream", "c1", 28, "weak"), ("stream", "c2", 28, "weak"), ("stream", "c3", 30, "strong"),
-                    ("fft", "c4"), ("fft", "c4_i16"), ("bank",)]
+                    ("fft", "c4"), ("fft", "c4_i16"), ("bank",), ("blocks",)]
         else:
             plan = [("stream", "c3", 30, "strong"), ("bank",)]
         for item in plan:
@@ -731,6 +771,8 @@ def main():
                 rec = bench_stream(ctx, item[1], sub_steps, sub_warm, e2e, cpu and ctx.world == 1, item[2], split=item[3])
             elif item[0] == "fft":
                 rec = bench_fft(ctx, item[1], sub_steps, sub_warm, e2e, cpu)
+            elif item[0] == "blocks":
+                rec = bench_blocks(ctx)
             else:
                 rec = bench_bank(ctx, sub_steps, sub_warm, e2e, cpu and ctx.world == 1)
             if rec:

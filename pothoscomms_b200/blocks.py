@@ -84,6 +84,14 @@ def lib():
         L.b200c_blk_has_signal.argtypes = [vp, cp]
         L.b200c_blk_call_complex.argtypes = [vp, cp, ctypes.c_double, ctypes.c_double]
         L.b200c_blk_run_source.argtypes = [vp, sz, sz]
+        L.b200c_blk_total_produced.restype = ull
+        L.b200c_blk_total_produced.argtypes = [vp]
+        L.b200c_blk_seam_windows.restype = ull
+        L.b200c_blk_seam_windows.argtypes = [vp]
+        L.b200c_blk_ring_bytes.restype = sz
+        L.b200c_blk_ring_bytes.argtypes = [vp]
+        L.b200c_blk_stream_bench.restype = ctypes.c_double
+        L.b200c_blk_stream_bench.argtypes = [vp, vp, sz, sz, sz]
         _lib = L
     return _lib
 
@@ -269,6 +277,29 @@ class Block:
     @property
     def work_calls(self) -> int:
         return int(lib().b200c_blk_work_calls(self._h))
+
+    @property
+    def total_produced(self) -> int:
+        return int(lib().b200c_blk_total_produced(self._h))
+
+    @property
+    def seam_windows(self) -> int:
+        """work() calls whose readable window (history + new) ran across the end of the ring's first mapping."""
+        return int(lib().b200c_blk_seam_windows(self._h))
+
+    @property
+    def ring_bytes(self) -> int:
+        return int(lib().b200c_blk_ring_bytes(self._h))
+
+    def stream_bench(self, pattern_raw: np.ndarray, chunk_elems: int, rounds: int) -> float:
+        """Seconds for `rounds` rounds of `chunk_elems` new elements through work() between device neighbours
+        (blocks/Harness.cpp streamBench: no host<->device copy inside the loop)."""
+        nc = ncomp(self.dtype)
+        x = np.ascontiguousarray(pattern_raw, dtype=np_scalar(self.dtype)).reshape(-1, nc)
+        secs = lib().b200c_blk_stream_bench(self._h, x.ctypes.data, x.shape[0], chunk_elems, rounds)
+        if secs < 0:
+            _check(int(secs))
+        return float(secs)
 
     @property
     def input_domain(self) -> str:

@@ -42,6 +42,7 @@ public:
     // the consumer's contiguous view of everything not yet released
     Pothos::BufferChunk readable() const { return Pothos::BufferChunk(_base + _rd, _filled); }
     size_t capacity() const { return _size; }
+    size_t base() const { return _base; }
 
 private:
     void update() { _front = Pothos::BufferChunk(_base + (_rd + _filled) % _size, _size - _filled); }

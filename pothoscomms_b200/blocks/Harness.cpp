@@ -7,6 +7,7 @@
 // drains produced elements back to the host.
 #include <Pothos/Framework.hpp>
 
+#include <chrono>
 #include <cstdio>
 #include <memory>
 #include <string>
@@ -74,6 +75,8 @@ public:
             const BufferChunk rd = _inMgr->readable();
             in->_addr = rd.address;
             in->_bytes = rd.length / isz * isz;
+            // the readable window runs past the end of the ring's first mapping: only the VMM double mapping keeps it contiguous
+            if (rd.length && rd.address + rd.length > _inMgr->base() + _inMgr->capacity()) _seamWindows++;
             in->_labels.clear();
             for (const auto &l : _inLabels) {
                 if (l.index >= _totalConsumed && l.index - _totalConsumed < in->elements()) {
@@ -124,6 +127,56 @@ public:
             }
             if (c == 0 && p == 0) break;
         }
+    }
+
+    // Streaming throughput of the block the way a Pothos scheduler drives it between two DEVICE neighbours: the upstream
+    // block has written `chunkElems` new elements into the HBM ring per round (here the ring is filled once with the host
+    // pattern and the producer pointer simply advances over it: no host<->device copy inside the loop), work() runs while it
+    // makes progress -- one kernel launch per call, K-1 history elements left in the ring -- and the downstream side
+    // releases every output slab at once.  Returns wall seconds for `rounds` rounds, device idle on both sides.
+    double streamBench(const void *hostPattern, size_t patternElems, size_t chunkElems, size_t rounds)
+    {
+        InputPort *in = _blk->input(0);
+        OutputPort *out = _blk->output(0);
+        const size_t isz = in->dtype().size(), osz = out->dtype().size();
+        const size_t cap = _inMgr->capacity();
+        if (_inMgr->readable().length != 0 || chunkElems * isz * 2 > cap) throw Exception("Harness::streamBench()", "ring must be empty and hold two chunks");
+        // fill the whole ring with the pattern (repeated) once
+        size_t filled = 0;
+        while (filled < cap) {
+            const size_t n = std::min(cap - filled, patternElems * isz);
+            b200c_blocks::throwOnError(b200c_copy_h2d(reinterpret_cast<void *>(_inMgr->base() + filled), hostPattern, n, _device, nullptr), "Harness::streamBench()");
+            filled += n;
+        }
+        b200c_blocks::throwOnError(b200c_stream_sync(_device, nullptr), "Harness::streamBench()");
+        auto round = [&] {
+            if (_inMgr->front().length < chunkElems * isz) throw Exception("Harness::streamBench()", "ring full: block is not consuming");
+            _inMgr->pop(chunkElems * isz);
+            for (int guard = 0; guard < 64; guard++) {
+                const BufferChunk rd = _inMgr->readable();
+                in->_addr = rd.address;
+                in->_bytes = rd.length / isz * isz;
+                if (rd.length && rd.address + rd.length > _inMgr->base() + cap) _seamWindows++;
+                in->_labels.clear();
+                out->_addr = _outMgr->front().address;
+                out->_bytes = _outMgr->front().length / osz * osz;
+                in->_pendingConsume = 0;
+                out->_pendingProduce = 0;
+                if (in->elements() < std::max<size_t>(in->_reserve, 1)) break;
+                _blk->work();
+                _workCalls++;
+                const size_t c = in->_pendingConsume, p = out->_pendingProduce;
+                if (c) { _inMgr->push(c * isz); _totalConsumed += c; }
+                if (p) { _outMgr->pop(p * osz); _outMgr->push(p * osz); _totalProduced += p; }
+                if (c == 0 && p == 0) break;
+            }
+        };
+        for (int w = 0; w < 3; w++) round();
+        b200c_blocks::throwOnError(b200c_stream_sync(_device, nullptr), "Harness::streamBench()");
+        const auto t0 = std::chrono::steady_clock::now();
+        for (size_t r = 0; r < rounds; r++) round();
+        b200c_blocks::throwOnError(b200c_stream_sync(_device, nullptr), "Harness::streamBench()");
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
 
     // a source block: `nwork` calls of work(), each offered room for `elems` elements (0 = the whole slab)
@@ -190,6 +243,9 @@ public:
     size_t reserve() const { return _blk->_inputs.at(0)._reserve; }
     unsigned long long totalConsumed() const { return _totalConsumed; }
     unsigned long long workCalls() const { return _workCalls; }
+    unsigned long long totalProduced() const { return _totalProduced; }
+    unsigned long long seamWindows() const { return _seamWindows; }
+    size_t ringBytes() const { return _inMgr ? _inMgr->capacity() : 0; }
     std::string inputDomain() const { return _inMgr->domain(); }
 
 private:
@@ -200,7 +256,7 @@ private:
     BufferManager::Sptr _outMgr;
     std::vector<Label> _inLabels, _outLabels;
     std::vector<char> _collected;
-    unsigned long long _totalFed = 0, _totalConsumed = 0, _totalProduced = 0, _workCalls = 0;
+    unsigned long long _totalFed = 0, _totalConsumed = 0, _totalProduced = 0, _workCalls = 0, _seamWindows = 0;
 };
 
 } // namespace Pothos
@@ -405,6 +461,16 @@ long long b200c_blk_collect(void *h, void *host, size_t max_elems) { return (lon
 size_t b200c_blk_reserve(void *h) { return static_cast<Harness *>(h)->reserve(); }
 unsigned long long b200c_blk_total_consumed(void *h) { return static_cast<Harness *>(h)->totalConsumed(); }
 unsigned long long b200c_blk_work_calls(void *h) { return static_cast<Harness *>(h)->workCalls(); }
+unsigned long long b200c_blk_total_produced(void *h) { return static_cast<Harness *>(h)->totalProduced(); }
+// number of work() calls whose readable window straddled the end of the ring's first mapping (base + bytes)
+unsigned long long b200c_blk_seam_windows(void *h) { return static_cast<Harness *>(h)->seamWindows(); }
+size_t b200c_blk_ring_bytes(void *h) { return static_cast<Harness *>(h)->ringBytes(); }
+double b200c_blk_stream_bench(void *h, const void *pattern, size_t pattern_elems, size_t chunk_elems, size_t rounds)
+{
+    double secs = -1.0;
+    const int rc = guarded([&] { secs = static_cast<Harness *>(h)->streamBench(pattern, pattern_elems, chunk_elems, rounds); });
+    return rc ? (double)rc : secs;
+}
 int b200c_blk_input_domain(void *h, char *buf, size_t cap) { std::snprintf(buf, cap, "%s", static_cast<Harness *>(h)->inputDomain().c_str()); return 0; }
 
 long long b200c_blk_num_out_labels(void *h) { return (long long)static_cast<Harness *>(h)->outLabels().size(); }

@@ -431,3 +431,63 @@ def test_signal_probe_rms_at_the_end_of_the_fir_topology(oracle, cuda_device):
         p2.run()
         got, c = p2.last_signal_value()
         assert c == 1 and abs(got - oracle.probe(code, mode, y[:512])) <= 1e-6 * max(1.0, abs(got))
+
+
+@pytest.mark.parametrize("dtype,M,L", [("complex_int16", 1, 1), ("complex_int16", 2, 3), ("int16", 3, 1), ("complex_float32", 1, 1)])
+def test_history_window_across_the_ring_seam(oracle, cuda_device, dtype, M, L):
+    """The device replacement of BufferManager::make("circular") (filter/FIRFilter.cpp:196-199): the K-1 history
+    elements left behind by consume() (:304-307) plus the new data must stay ONE contiguous window when it runs
+    across the end of the ring (base + bytes) -- the second VMM mapping.  The stream is several ring lengths long
+    and fed in pieces that do not divide the ring, so many work() calls see a window that straddles the seam;
+    int16 streams must still equal the oracle's one-shot output bit for bit."""
+    from pothoscomms_b200 import blocks
+    code = oracle.DTYPE_CODES[dtype]
+    rng = np.random.default_rng(42)
+    nc = 2 if code & 1 else 1
+    tcx = bool(code & 1)
+    taps = (rng.standard_normal(128) * 0.05 + (1j * rng.standard_normal(128) * 0.05 if tcx else 0))
+    f = blocks.make("/comms/fir_filter", dtype, "COMPLEX" if tcx else "REAL", in_bytes=1 << 21, out_bytes=1 << 23)
+    f.call("setTaps", taps)
+    f.call("setDecimation", M)
+    f.call("setInterpolation", L)
+    f.activate()
+    esz = nc * (2 if "int16" in dtype else 4)
+    ring_elems = f.ring_bytes // esz
+    n = 3 * ring_elems + 12345
+    if "int" in dtype:
+        x = rng.integers(-30000, 30000, size=(n, nc), dtype=np.int16)
+    else:
+        x = rng.standard_normal((n, nc)).astype(np.float32)
+    piece = ring_elems * 5 // 13 + 7          # does not divide the ring: the write and read windows both wrap
+    outs, pos = [], 0
+    while pos < n:
+        got = f.feed(x[pos: pos + piece])
+        pos += got
+        f.run()
+        outs.append(f.collect())
+        assert got > 0
+    y = np.concatenate(outs)
+    y_ref, cons, prod = oracle.fir(code, tcx, taps, M, L, x)
+    assert f.seam_windows >= 2, "no work() call saw a window across base + bytes: the test did not exercise the seam"
+    assert f.total_consumed == cons and y.shape[0] == prod
+    if "int" in dtype:
+        assert np.array_equal(y, y_ref)
+    else:
+        assert rel_rms(y, y_ref) < 1e-5
+
+
+def test_stream_bench_runs_without_host_copies(oracle, cuda_device):
+    """blocks/Harness.cpp streamBench (bench.py --workload headline_blocks): work() buffers of a fixed size between
+    device neighbours; every round is consumed completely and the ring wraps."""
+    from pothoscomms_b200 import blocks
+    from pothoscomms_b200 import workloads as wl
+    taps, tt = wl.config_taps("headline")
+    chunk = 1 << 17
+    f = blocks.make("/comms/fir_filter", "complex_float32", tt, in_bytes=4 * chunk * 8, out_bytes=2 * chunk * 8)
+    f.call("setTaps", taps)
+    f.activate()
+    pat = wl.tone_noise_numpy(oracle.CF32, 1 << 16, seed=3)
+    secs = f.stream_bench(pat, chunk, 50)
+    assert secs > 0
+    assert f.total_consumed >= 52 * chunk - 255 and f.work_calls >= 53
+    assert f.seam_windows > 0
