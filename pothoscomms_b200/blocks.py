@@ -90,6 +90,8 @@ def lib():
         L.b200c_blk_seam_windows.argtypes = [vp]
         L.b200c_blk_ring_bytes.restype = sz
         L.b200c_blk_ring_bytes.argtypes = [vp]
+        L.b200c_blk_run_host_chain.restype = ll
+        L.b200c_blk_run_host_chain.argtypes = [vp, vp, sz, sz, vp, sz, ctypes.POINTER(ull)]
         L.b200c_blk_stream_bench.restype = ctypes.c_double
         L.b200c_blk_stream_bench.argtypes = [vp, vp, sz, sz, sz]
         _lib = L
@@ -290,6 +292,18 @@ class Block:
     @property
     def ring_bytes(self) -> int:
         return int(lib().b200c_blk_ring_bytes(self._h))
+
+    def run_host_chain(self, x_raw: np.ndarray, chunk: int, out_capacity: int):
+        """feeder (host) -> /b200c/host_to_hbm -> this block -> /b200c/hbm_to_host -> collector (host), the way a topology
+        with host-memory neighbours is wired around the device blocks (blocks/Bridge.cpp).  Returns (output, bridge work() calls)."""
+        nc = ncomp(self.dtype)
+        x = np.ascontiguousarray(x_raw, dtype=np_scalar(self.dtype)).reshape(-1, nc)
+        out = np.empty((out_capacity, nc), dtype=x.dtype)
+        calls = ctypes.c_ulonglong(0)
+        got = lib().b200c_blk_run_host_chain(self._h, x.ctypes.data, x.shape[0], chunk, out.ctypes.data, out_capacity, ctypes.byref(calls))
+        if got < 0:
+            _check(int(got))
+        return out[:got], calls.value
 
     def stream_bench(self, pattern_raw: np.ndarray, chunk_elems: int, rounds: int) -> float:
         """Seconds for `rounds` rounds of `chunk_elems` new elements through work() between device neighbours

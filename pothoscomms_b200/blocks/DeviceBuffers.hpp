@@ -20,6 +20,18 @@ inline void throwOnError(int rc, const std::string &where)
     throw Pothos::Exception(where, text);
 }
 
+// The device blocks hand out HBM buffers, so they can only share them with a neighbour whose port is in the
+// same domain.  A host-memory neighbour (domain "": /blocks/feeder_source, /blocks/collector_sink, any CPU
+// block) would dereference device pointers: refused with Pothos::PortDomainError, and the topology connects
+// it through /b200c/host_to_hbm or /b200c/hbm_to_host (blocks/Bridge.cpp) instead.
+inline void requireHbmPeer(const std::string &who, const std::string &domain)
+{
+    if (domain == kHbmDomain) return;
+    if (domain.empty())
+        throw Pothos::PortDomainError(who, "host-memory neighbour: connect it through /b200c/host_to_hbm or /b200c/hbm_to_host");
+    throw Pothos::PortDomainError(who, "cannot share buffers with domain " + domain);
+}
+
 // "circular": one HBM ring mapped twice back to back (CUDA VMM), so the readable window
 // (K-1 history + new samples) and the writable window are each always contiguous.
 class DeviceCircularBufferManager : public Pothos::BufferManager {

@@ -22,8 +22,8 @@ public:
         _dtype(dtype), _dtypeCode(dtypeCode), _numBins(numBins), _inverse(inverse), _device(device), _fft(nullptr)
     {
         throwOnError(b200c_fft_create(&_fft, dtypeCode, numBins, inverse ? 1 : 0, device), "FFTFactory(" + dtype.toString() + ")");
-        this->setupInput(0, dtype);
-        this->setupOutput(0, dtype);
+        this->setupInput(0, dtype, b200c_blocks::kHbmDomain);
+        this->setupOutput(0, dtype, b200c_blocks::kHbmDomain);
         this->input(0)->setReserve(_numBins);
         //Not in the reference (its FFT block registers no calls, fft/FFT.cpp:43-51); the
         //direction becomes switchable at run time, the factory argument stays the default.
@@ -52,15 +52,13 @@ public:
     //! HBM slabs holding many transforms each (the reference: one transform per slab)
     Pothos::BufferManager::Sptr getOutputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("FFT::getOutputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("FFT::getOutputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceSlabBufferManager(_device));
     }
 
     Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("FFT::getInputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("FFT::getInputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceCircularBufferManager(_device));
     }
 

@@ -30,8 +30,8 @@ public:
         const bool complexTaps = not std::is_same<TapsType, double>::value;
         throwOnError(b200c_fir_create(&_fir, dtypeCode, complexTaps ? B200C_TAPS_COMPLEX : B200C_TAPS_REAL, device),
                      "FIRFilterFactory(" + dtype.toString() + ")");
-        this->setupInput(0, dtype);
-        this->setupOutput(0, dtype);
+        this->setupInput(0, dtype, b200c_blocks::kHbmDomain);
+        this->setupOutput(0, dtype, b200c_blocks::kHbmDomain);
         this->registerCall(this, POTHOS_FCN_TUPLE(FIRFilter, setTaps));
         this->registerCall(this, POTHOS_FCN_TUPLE(FIRFilter, getTaps));
         this->registerCall(this, POTHOS_FCN_TUPLE(FIRFilter, setDecimation));
@@ -92,16 +92,14 @@ public:
     //! always a circular buffer so the sliding window never sees a discontinuity -- in HBM
     Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("FIRFilter::getInputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("FIRFilter::getInputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceCircularBufferManager(_device));
     }
 
     //! output slabs live in HBM as well, so a downstream device block reads them in place
     Pothos::BufferManager::Sptr getOutputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("FIRFilter::getOutputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("FIRFilter::getOutputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceSlabBufferManager(_device));
     }
 

@@ -237,6 +237,84 @@ public:
         return n;
     }
 
+    // The reference's test topology with host neighbours (filter/TestFIRFilter.cpp:49-51), as it has to be wired around the
+    // device blocks:  feeder (host) -> /b200c/host_to_hbm -> `mid` (a device block) -> /b200c/hbm_to_host -> collector (host).
+    // Buffers: the upstream block writes into the manager the DOWNSTREAM input asks for (mid's HBM ring, the d2h block's HBM
+    // ring); the two host ends are plain host memory.  `chunk` elements are fed per round.  Returns elements collected.
+    static size_t runHostChain(Block *mid, const char *in, size_t inElems, size_t chunk, char *out, size_t outCap,
+                               unsigned long long *bridgeCalls)
+    {
+        const DType dt = mid->input(0)->dtype();
+        std::unique_ptr<Block> h2d(BlockRegistry::make("/b200c/host_to_hbm", dt)), d2h(BlockRegistry::make("/b200c/hbm_to_host", dt));
+        const size_t esz = dt.size();
+        // the device blocks refuse to share their buffers with a host-memory neighbour
+        bool refused = false;
+        try { mid->getInputBufferManager("0", ""); } catch (const PortDomainError &) { refused = true; }
+        if (!refused) throw Exception("runHostChain()", "device block accepted a host-domain upstream");
+        refused = false;
+        try { mid->getOutputBufferManager("0", ""); } catch (const PortDomainError &) { refused = true; }
+        if (!refused) throw Exception("runHostChain()", "device block accepted a host-domain downstream");
+        if (h2d->getInputBufferManager("0", "")) throw Exception("runHostChain()", "host_to_hbm should take the default host manager");
+        auto ringA = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(mid->getInputBufferManager("0", h2d->output(0)->domain()));
+        auto ringB = std::dynamic_pointer_cast<b200c_blocks::DeviceCircularBufferManager>(d2h->getInputBufferManager("0", mid->output(0)->domain()));
+        if (!ringA || !ringB) throw Exception("runHostChain()", "no device ring between the device blocks");
+        BufferManagerArgs ra;
+        ra.bufferSize = std::max<size_t>(4 * chunk * esz, 1 << 21); ra.numBuffers = 1;
+        ringA->init(ra);
+        BufferManagerArgs rb = ra;
+        rb.bufferSize = 4 * ra.bufferSize;     // room for interpolated output
+        ringB->init(rb);
+        for (Block *b : {h2d.get(), mid, d2h.get()}) { b->_active = true; b->activate(); }
+        size_t fed = 0, got = 0;
+        unsigned long long calls = 0;
+        for (int guard = 0; guard < 1000000; guard++) {
+            bool progress = false;
+            // feeder -> host_to_hbm -> ring A
+            {
+                InputPort *ip = h2d->input(0); OutputPort *op = h2d->output(0);
+                const size_t n = std::min(chunk, inElems - fed);
+                ip->_addr = reinterpret_cast<size_t>(in + fed * esz); ip->_bytes = n * esz; ip->_labels.clear();
+                op->_addr = ringA->front().address; op->_bytes = ringA->front().length / esz * esz;
+                ip->_pendingConsume = 0; op->_pendingProduce = 0;
+                if (n && op->_bytes) { h2d->work(); calls++; }
+                if (ip->_pendingConsume != op->_pendingProduce) throw Exception("runHostChain()", "bridge must copy 1:1");
+                fed += ip->_pendingConsume;
+                ringA->pop(op->_pendingProduce * esz);
+                progress |= ip->_pendingConsume != 0;
+            }
+            // ring A -> mid -> ring B
+            for (;;) {
+                InputPort *ip = mid->input(0); OutputPort *op = mid->output(0);
+                const BufferChunk rd = ringA->readable();
+                ip->_addr = rd.address; ip->_bytes = rd.length / esz * esz; ip->_labels.clear();
+                op->_addr = ringB->front().address; op->_bytes = ringB->front().length / esz * esz;
+                ip->_pendingConsume = 0; op->_pendingProduce = 0;
+                if (ip->elements() < std::max<size_t>(ip->_reserve, 1) || op->_bytes == 0) break;
+                mid->work();
+                const size_t c = ip->_pendingConsume, p = op->_pendingProduce;
+                ringA->push(c * esz);
+                ringB->pop(p * esz);
+                if (c == 0 && p == 0) break;
+                progress = true;
+            }
+            // ring B -> hbm_to_host -> collector
+            {
+                InputPort *ip = d2h->input(0); OutputPort *op = d2h->output(0);
+                const BufferChunk rd = ringB->readable();
+                ip->_addr = rd.address; ip->_bytes = rd.length / esz * esz; ip->_labels.clear();
+                op->_addr = reinterpret_cast<size_t>(out + got * esz); op->_bytes = (outCap - got) * esz;
+                ip->_pendingConsume = 0; op->_pendingProduce = 0;
+                if (ip->_bytes && op->_bytes) { d2h->work(); calls++; }
+                ringB->push(ip->_pendingConsume * esz);
+                got += op->_pendingProduce;
+                progress |= op->_pendingProduce != 0;
+            }
+            if (!progress) break;
+        }
+        if (bridgeCalls) *bridgeCalls = calls;
+        return got;
+    }
+
     Block *block() { return _blk.get(); }
     const std::vector<Label> &outLabels() const { return _outLabels; }
     size_t pendingOutput() const { return _sink ? 0 : _collected.size() / _blk->output(0)->dtype().size(); }
@@ -465,6 +543,16 @@ unsigned long long b200c_blk_total_produced(void *h) { return static_cast<Harnes
 // number of work() calls whose readable window straddled the end of the ring's first mapping (base + bytes)
 unsigned long long b200c_blk_seam_windows(void *h) { return static_cast<Harness *>(h)->seamWindows(); }
 size_t b200c_blk_ring_bytes(void *h) { return static_cast<Harness *>(h)->ringBytes(); }
+// feeder (host) -> /b200c/host_to_hbm -> the harness's block -> /b200c/hbm_to_host -> collector (host); returns elements collected
+long long b200c_blk_run_host_chain(void *h, const void *in, size_t in_elems, size_t chunk, void *out, size_t out_cap, unsigned long long *bridge_calls)
+{
+    long long got = -1;
+    const int rc = guarded([&] {
+        got = (long long)Harness::runHostChain(static_cast<Harness *>(h)->block(), static_cast<const char *>(in), in_elems,
+                                               chunk, static_cast<char *>(out), out_cap, bridge_calls);
+    });
+    return rc ? rc : got;
+}
 double b200c_blk_stream_bench(void *h, const void *pattern, size_t pattern_elems, size_t chunk_elems, size_t rounds)
 {
     double secs = -1.0;

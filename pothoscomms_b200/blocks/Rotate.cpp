@@ -21,8 +21,8 @@ public:
         this->registerCall(this, POTHOS_FCN_TUPLE(Rotate, getPhase));
         this->registerCall(this, POTHOS_FCN_TUPLE(Rotate, setLabelId));
         this->registerCall(this, POTHOS_FCN_TUPLE(Rotate, getLabelId));
-        this->setupInput(0, dtype);
-        this->setupOutput(0, dtype);
+        this->setupInput(0, dtype, b200c_blocks::kHbmDomain);
+        this->setupOutput(0, dtype, b200c_blocks::kHbmDomain);
     }
 
     void setPhase(const double phase) { _phase = phase; }   //floatToQ(polar(1, phase)) happens inside b200c_rotate (:74)
@@ -32,14 +32,12 @@ public:
 
     Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("Rotate::getInputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("Rotate::getInputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceCircularBufferManager(_device));
     }
     Pothos::BufferManager::Sptr getOutputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("Rotate::getOutputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("Rotate::getOutputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceSlabBufferManager(_device));
     }
 

@@ -23,8 +23,8 @@ public:
         this->registerCall(this, POTHOS_FCN_TUPLE(Scale, getFactor));
         this->registerCall(this, POTHOS_FCN_TUPLE(Scale, setLabelId));
         this->registerCall(this, POTHOS_FCN_TUPLE(Scale, getLabelId));
-        this->setupInput(0, dtype);
-        this->setupOutput(0, dtype);
+        this->setupInput(0, dtype, b200c_blocks::kHbmDomain);
+        this->setupOutput(0, dtype, b200c_blocks::kHbmDomain);
     }
 
     void setFactor(const double factor) { _factor = factor; }   //floatToQ happens inside b200c_scale (Scale.cpp:44)
@@ -34,14 +34,12 @@ public:
 
     Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("Scale::getInputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("Scale::getInputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceCircularBufferManager(_device));
     }
     Pothos::BufferManager::Sptr getOutputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("Scale::getOutputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("Scale::getOutputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceSlabBufferManager(_device));
     }
 

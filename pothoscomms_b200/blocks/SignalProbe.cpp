@@ -20,7 +20,7 @@ class SignalProbe : public Pothos::Block
 public:
     SignalProbe(const Pothos::DType &dtype, const int code, const int device): _code(code), _device(device)
     {
-        this->setupInput(0, dtype);
+        this->setupInput(0, dtype, b200c_blocks::kHbmDomain);
         this->registerCall(this, POTHOS_FCN_TUPLE(SignalProbe, value));
         this->registerCall(this, POTHOS_FCN_TUPLE(SignalProbe, setMode));
         this->registerCall(this, POTHOS_FCN_TUPLE(SignalProbe, getMode));
@@ -44,8 +44,7 @@ public:
 
     Pothos::BufferManager::Sptr getInputBufferManager(const std::string &, const std::string &domain)
     {
-        if (not domain.empty() and domain != b200c_blocks::kHbmDomain)
-            throw Pothos::Exception("SignalProbe::getInputBufferManager()", "cannot share buffers with domain " + domain);
+        b200c_blocks::requireHbmPeer("SignalProbe::getInputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new b200c_blocks::DeviceCircularBufferManager(_device));
     }
 

@@ -24,7 +24,7 @@ public:
     TableSource(const Pothos::DType &dtype, const int code, const int device, const std::string &wave):
         _code(code), _device(device), _wave(wave)
     {
-        this->setupOutput(0, dtype);
+        this->setupOutput(0, dtype, b200c_blocks::kHbmDomain);
         this->registerCall(this, "setWaveform", &TableSource::setWaveform);
         this->registerCall(this, "getWaveform", &TableSource::getWaveform);
         this->registerCall(this, "setOffset", &TableSource::setOffset);
@@ -36,8 +36,7 @@ public:
 
     Pothos::BufferManager::Sptr getOutputBufferManager(const std::string &, const std::string &domain) override
     {
-        if (not domain.empty() and domain != kHbmDomain)
-            throw Pothos::Exception("TableSource::getOutputBufferManager()", "cannot share buffers with domain " + domain);
+        requireHbmPeer("TableSource::getOutputBufferManager()", domain);
         return Pothos::BufferManager::Sptr(new DeviceSlabBufferManager(_device));
     }
 

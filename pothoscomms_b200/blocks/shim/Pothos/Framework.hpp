@@ -38,6 +38,13 @@ public:
         : Exception("Invalid argument: " + what, arg) {}
 };
 
+// thrown by get{Input,Output}BufferManager when a block cannot share buffers with the neighbour's domain
+class PortDomainError : public Exception {
+public:
+    explicit PortDomainError(const std::string &what, const std::string &arg = "")
+        : Exception("Port domain error: " + what, arg) {}
+};
+
 // ----------------------------------------------------------------------------- DType ---
 class DType {
 public:
@@ -239,12 +246,14 @@ public:
     BufferChunk buffer() const { return BufferChunk(_addr, _bytes, _dtype); }
     void consume(size_t numElements) { _pendingConsume += numElements; }
     const DType &dtype() const { return _dtype; }
+    const std::string &domain() const { return _domain; }   // "" = host memory
     unsigned long long totalElements() const { return _totalConsumed; }
 
 private:
     friend class Block;
     friend class Harness;
     DType _dtype;
+    std::string _domain;
     size_t _addr = 0, _bytes = 0, _reserve = 0, _pendingConsume = 0;
     unsigned long long _totalConsumed = 0;
     std::vector<Label> _labels;   // indices relative to the front of buffer()
@@ -258,11 +267,13 @@ public:
     void postLabel(Label &&l) { _posted.emplace_back(std::move(l)); }
     void postLabel(const Label &l) { _posted.push_back(l); }
     const DType &dtype() const { return _dtype; }
+    const std::string &domain() const { return _domain; }   // "" = host memory
 
 private:
     friend class Block;
     friend class Harness;
     DType _dtype;
+    std::string _domain;
     size_t _addr = 0, _bytes = 0, _pendingProduce = 0;
     std::vector<Label> _posted;   // indices relative to the element about to be produced
 };
@@ -334,15 +345,18 @@ protected:
         _signalCounts[name]++;
         for (auto &c : _signalConns[name]) c.first->call(c.second, args);
     }
-    void setupInput(size_t index, const DType &dt)
+    // third argument: the port's buffer domain, as Pothos::Block::setupInput(name, dtype, domain)
+    void setupInput(size_t index, const DType &dt, const std::string &domain = "")
     {
         if (_inputs.size() <= index) _inputs.resize(index + 1);
         _inputs[index]._dtype = dt;
+        _inputs[index]._domain = domain;
     }
-    void setupOutput(size_t index, const DType &dt)
+    void setupOutput(size_t index, const DType &dt, const std::string &domain = "")
     {
         if (_outputs.size() <= index) _outputs.resize(index + 1);
         _outputs[index]._dtype = dt;
+        _outputs[index]._domain = domain;
     }
     // registerCall(this, POTHOS_FCN_TUPLE(Class, method))
     template <typename C, typename R, typename... A>

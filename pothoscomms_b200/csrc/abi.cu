@@ -306,7 +306,14 @@ int b200c_fir_set_taps(b200c_fir *h, const double *taps, size_t ntaps)
     h->taps.assign(taps, taps + ntaps * tc);
     h->ntaps = ntaps;
     const int rc = fir_refresh(h);
-    if (rc) { h->taps = old; h->ntaps = old_n; }
+    if (rc) {
+        // a configure step failed half way (tables are committed before the kernel plans): put the old taps back and
+        // rebuild EVERYTHING for them, so that info/plan/dispatch never see mixed state; the error text is the first one's
+        const std::string first = g_err;
+        h->taps = old; h->ntaps = old_n;
+        (void)fir_refresh(h);
+        g_err = first;
+    }
     return rc;
 }
 
@@ -318,7 +325,12 @@ int b200c_fir_set_rates(b200c_fir *h, size_t decim, size_t interp)
     const size_t oM = h->M, oL = h->L;
     h->M = decim; h->L = interp;
     const int rc = fir_refresh(h);
-    if (rc) { h->M = oM; h->L = oL; }
+    if (rc) {
+        const std::string first = g_err;
+        h->M = oM; h->L = oL;
+        (void)fir_refresh(h);      // rebuild tables and kernel plans for the restored rates
+        g_err = first;
+    }
     return rc;
 }
 
@@ -453,9 +465,16 @@ int b200c_fir_bank_set_rates(b200c_fir_bank *b, size_t decim, size_t interp)
 {
     if (!b) return B200C_ERR_INVALID;
     b->dirty = true;
-    for (auto *c : b->ch) {
-        const int rc = b200c_fir_set_rates(c, decim, interp);
-        if (rc) return rc;
+    const size_t oM = b->ch[0]->M, oL = b->ch[0]->L;
+    for (size_t i = 0; i < b->ch.size(); i++) {
+        const int rc = b200c_fir_set_rates(b->ch[i], decim, interp);
+        if (rc) {
+            // no channel may keep the new rates when one of them failed: undo the ones already switched
+            const std::string first = g_err;
+            for (size_t j = 0; j < i; j++) (void)b200c_fir_set_rates(b->ch[j], oM, oL);
+            g_err = first;
+            return rc;
+        }
     }
     return B200C_OK;
 }

@@ -74,7 +74,12 @@ constexpr size_t kFirOsMaxTaps = 2049;
 constexpr size_t kFirOs1kMaxTaps = 448;       // measured crossover of the 1024- and 4096-point kernels
 // automatic switch from the direct kernel (taps per output phase at or above this take the fused
 // path): real float32 streams, and resamplers where the direct kernel still wins for short phases
-constexpr size_t kFirOsAutoMinTapsReal = 8;
+constexpr size_t kFirOsAutoMinTapsReal = 9;
+// float32 / complex float32, L = M = 1: filters of up to this many taps stay on the direct time-domain kernel (HBM-bound
+// there anyway: <= 64 flop per 16 B), which keeps the reference's per-output semantics for the trivially exact filters
+// (delays, integer gains pass samples bit for bit) and confines a NaN/Inf input sample to K outputs instead of a
+// transform block.  B200C_FIR_ALGO=fft forces the fused path from 2 taps.
+constexpr size_t kFirOsAutoMinTapsFloat = 9;
 constexpr size_t kFirOsAutoMinTapsResamp = 24;
 constexpr size_t kFirOsAutoMinTapsOsp = 16;       // complex float32 resamplers served by fir_osp(g)_kernel
 constexpr long long kFirOsGenMaxSpan = 400;   // general kernel: keep hop >= ~60 % of the block

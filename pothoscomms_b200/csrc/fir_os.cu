@@ -1205,8 +1205,9 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
         return B200C_OK;
     }
     if (dtype == B200C_CF32 && M == 1 && L == 1) {
-        // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up
-        if (ntaps < 2 || ntaps > kFirOsMaxTaps) return B200C_OK;
+        // measured (tools/sweep.sh): the fused kernel beats the direct one from 2 taps up; short filters keep the
+        // time-domain kernel all the same (kFirOsAutoMinTapsFloat)
+        if (ntaps < 2 || ntaps > kFirOsMaxTaps || (!force && ntaps < kFirOsAutoMinTapsFloat)) return B200C_OK;
         std::vector<float> tb, hf;
         int rc;
         p.N = pick_length(ntaps);
@@ -1232,7 +1233,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
         p.ready = true;
         return B200C_OK;
     }
-    if (dtype == B200C_F32 && M == 1 && L == 1 && !complex_taps && ntaps >= 2 && ntaps <= kFirOs1kMaxTaps &&
+    if (dtype == B200C_F32 && M == 1 && L == 1 && !complex_taps && ntaps >= (force ? 2 : kFirOsAutoMinTapsFloat) && ntaps <= kFirOs1kMaxTaps &&
         !(std::getenv("B200C_OS32R") && std::atoi(std::getenv("B200C_OS32R")) == 0)) {
         // real float32 stream: two blocks per complex 1024-point transform (fir_os32r_kernel)
         std::vector<float> tb, hf;

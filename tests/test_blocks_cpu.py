@@ -85,3 +85,11 @@ def test_table_source_argument_errors_and_loud_failure():
     if not torch.cuda.is_available():
         assert lib.b200c_table_source(_abi.CF32, p, 4, 0, 1, p, 4, 0, None) == _abi.ERR_CUDA
         assert b"no CPU fallback" in lib.b200c_last_error()
+
+
+def test_bridge_blocks_are_registered():
+    """/b200c/host_to_hbm and /b200c/hbm_to_host (blocks/Bridge.cpp): the copy blocks a topology puts between a
+    host-memory neighbour and the device blocks, which refuse host-domain peers (Pothos::PortDomainError)."""
+    from pothoscomms_b200 import blocks
+    for path in ("/b200c/host_to_hbm", "/b200c/hbm_to_host"):
+        assert blocks.registry_has(path), path

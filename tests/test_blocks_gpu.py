@@ -491,3 +491,41 @@ def test_stream_bench_runs_without_host_copies(oracle, cuda_device):
     assert secs > 0
     assert f.total_consumed >= 52 * chunk - 255 and f.work_calls >= 53
     assert f.seam_windows > 0
+
+
+@pytest.mark.parametrize("dtype,M,L", [("complex_int16", 1, 1), ("complex_float32", 2, 3), ("int16", 1, 2)])
+def test_host_neighbours_go_through_the_bridge_blocks(oracle, cuda_device, dtype, M, L):
+    """The reference's test topology has HOST neighbours (feeder_source -> fir_filter -> collector_sink,
+    filter/TestFIRFilter.cpp:49-51).  The device block refuses to hand its HBM buffers to a host-domain peer
+    (PortDomainError, checked inside the chain runner); wired through /b200c/host_to_hbm and /b200c/hbm_to_host the
+    same topology produces the oracle's output: one copy per buffer at each edge, HBM in between."""
+    from pothoscomms_b200 import blocks
+    code = oracle.DTYPE_CODES[dtype]
+    tcx = bool(code & 1)
+    rng = np.random.default_rng(17)
+    nc = 2 if code & 1 else 1
+    taps = rng.standard_normal(101) * 0.05 + (1j * rng.standard_normal(101) * 0.05 if tcx else 0)
+    n = 50000
+    x = rng.integers(-30000, 30000, size=(n, nc), dtype=np.int16) if "int" in dtype else rng.standard_normal((n, nc)).astype(np.float32)
+    f = blocks.make("/comms/fir_filter", dtype, "COMPLEX" if tcx else "REAL")
+    f.call("setTaps", taps)
+    f.call("setDecimation", M)
+    f.call("setInterpolation", L)
+    y, bridge_calls = f.run_host_chain(x, chunk=7000, out_capacity=(n // M + 1) * L)
+    y_ref, cons, prod = oracle.fir(code, tcx, taps, M, L, x)
+    assert y.shape[0] == prod and bridge_calls >= 2 * (n // 7000)
+    if "int" in dtype:
+        assert np.array_equal(y, y_ref)
+    else:
+        assert rel_rms(y, y_ref) < 1e-5
+
+
+def test_fft_block_between_host_neighbours(oracle, cuda_device):
+    """fft/TestFFT.cpp:33-46 (feeder -> fft -> collector) wired through the bridge blocks."""
+    from pothoscomms_b200 import blocks
+    rng = np.random.default_rng(5)
+    x = rng.integers(-20000, 20000, size=(16 * 1024, 2), dtype=np.int16)
+    f = blocks.make("/comms/fft", "complex_int16", 1024, False)
+    y, _ = f.run_host_chain(x, chunk=3000, out_capacity=16 * 1024)
+    ref = oracle.ref_fft(oracle.CI16, 1024, False, x) if oracle.have_ref() else oracle.fft(oracle.CI16, 1024, False, x)
+    assert y.shape[0] == 16 * 1024 and np.array_equal(y, ref)

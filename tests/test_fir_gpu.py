@@ -311,7 +311,10 @@ def _with_algo(algo):
     @contextlib.contextmanager
     def cm():
         old = os.environ.get("B200C_FIR_ALGO")
-        os.environ["B200C_FIR_ALGO"] = algo
+        if algo is None:
+            os.environ.pop("B200C_FIR_ALGO", None)
+        else:
+            os.environ["B200C_FIR_ALGO"] = algo
         try:
             yield
         finally:
@@ -619,7 +622,8 @@ def test_real_float32_overlap_save_kernel(oracle, cuda_device, ntaps):
                              (200003, False), (1000, True), (1, True)):
         x = _rand_input(oracle, oracle.F32, ntaps - 1 + n_new, rng)
         y_ref, c_ref, p_ref = oracle.fir(oracle.F32, False, taps, 1, 1, x, zero_tail=zero_tail)
-        y, cons, prod, f = _run_gpu(oracle.F32, "REAL", taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("fft" if ntaps < 9 else None):   # up to 8 taps the automatic choice is the direct kernel
+            y, cons, prod, f = _run_gpu(oracle.F32, "REAL", taps, 1, 1, x, zero_tail=zero_tail)
         assert f.kernel == "fir_os32r_kernel", f.kernel
         assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
         _compare(oracle, oracle.F32, y, y_ref, f"os32r K={ntaps} n={n_new} zt={zero_tail}", rms_hint)
@@ -712,3 +716,38 @@ def test_spectral_resampler_interp3_decim2(oracle, cuda_device, ntaps, taps_type
     torch.cuda.synchronize()
     assert (cons, prod) == (c_ref, p_ref)
     _compare(oracle, code, y.cpu().numpy()[:prod], y_ref_c, "os32x capacity", rms_hint)
+
+
+@pytest.mark.parametrize("dt", ["CF32", "F32"])
+def test_short_float_filters_keep_time_domain_semantics(oracle, cuda_device, dt):
+    """Filters of up to 8 taps stay on the direct kernel (automatic choice): what the reference's time-domain
+    nest guarantees per output then holds here too -- a pure delay or an integer gain passes samples bit for bit,
+    and a non-finite input sample contaminates exactly the K outputs whose window holds it
+    (filter/FIRFilter.cpp:295-299).  Longer filters take fast convolution, where a NaN spreads over its transform
+    block; documented in INTEGRATION.md, checked here as the contract it is."""
+    code = getattr(oracle, dt)
+    rng = np.random.default_rng(3)
+    x = _rand_input(oracle, code, 5000, rng)
+    for taps in ([0.0, 1.0], [2.0], [0.0, 0.0, 0.0, -4.0], [1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]):
+        y_ref, c_ref, p_ref = oracle.fir(code, False, taps, 1, 1, x)
+        y, cons, prod, f = _run_gpu(code, "REAL", taps, 1, 1, x)
+        assert f.kernel in ("fir_tile_kernel", "fir_generic_kernel"), f.kernel
+        assert (cons, prod) == (c_ref, p_ref)
+        assert np.array_equal(y.view(np.uint32), y_ref.view(np.uint32)), taps    # exact filters: bit for bit
+    taps = rng.standard_normal(8)
+    K = 8
+    xn = x.copy()
+    xn[1000, 0] = np.nan
+    xn[3000, -1] = np.inf
+    y, cons, prod, f = _run_gpu(code, "REAL", taps, 1, 1, xn)
+    bad = ~np.isfinite(y).all(axis=1)
+    expect = np.zeros(prod, dtype=bool)
+    for pos in (1000, 3000):
+        expect[max(pos - (K - 1), 0): pos + 1] = True        # outputs n with n <= pos <= n + K - 1 (history offset K-1)
+    assert np.array_equal(bad, expect)
+    # the fused path (forced, or chosen from 9 taps up) spreads the same sample over its transform block(s)
+    with _with_algo("fft"):
+        y2, _, _, f2 = _run_gpu(code, "REAL", taps, 1, 1, xn)
+    assert f2.kernel.startswith("fir_os")
+    bad2 = ~np.isfinite(y2).all(axis=1)
+    assert bad2[expect].all() and bad2.sum() > expect.sum() and bad2.sum() <= 4 * 2048
