@@ -23,7 +23,11 @@ namespace b200c {
 template <typename T> struct FloatTraits {
     using E = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
     using Sc = T;
+    using S = E;   // storage type (global / shared memory) == register type
     static constexpr bool kFixed = false;
+    __device__ static E ld(S s) { return s; }
+    __device__ static E ldtw(S s) { return s; }
+    __device__ static S st(E e) { return e; }
     __device__ static E mk(T r, T i) { E e; e.x = r; e.y = i; return e; }
     __device__ static E add(E a, E b) { return mk(a.x + b.x, a.y + b.y); }
     __device__ static E sub(E a, E b) { return mk(a.x - b.x, a.y - b.y); }
@@ -36,8 +40,12 @@ template <typename T> struct FloatTraits {
 
 struct Q15Traits {   // fft/_kiss_fft_guts.h:44-124 with FIXED_POINT=16
     using E = short2;
+    using S = short2;
     using Sc = int;  // int16 values carried in 32-bit registers, wrapped at every assignment
     static constexpr bool kFixed = true;
+    __device__ static E ld(S s) { return s; }
+    __device__ static E ldtw(S s) { return s; }
+    __device__ static S st(E e) { return e; }
     __device__ static int wrap(int a) { return (int)(short)a; }
     __device__ static int sround(int x) { return (int)(short)((x + (1 << 14)) >> 15); }
     __device__ static E mk(int r, int i) { E e; e.x = (short)r; e.y = (short)i; return e; }
@@ -55,6 +63,42 @@ struct Q15Traits {   // fft/_kiss_fft_guts.h:44-124 with FIXED_POINT=16
     }
     __device__ static int smul(int a, int b) { return sround(a * b); }
     __device__ static int half(int a) { return a >> 1; }
+};
+
+// The same Q15 arithmetic with LAZY wrapping, for the fused 4096-point kernel.  kiss_fft stores every sum in an
+// int16 (wrap mod 2^16, fft/_kiss_fft_guts.h:100-124); wrapping is a ring homomorphism, so a chain of adds and
+// subtractions may be carried unwrapped in 32-bit registers as long as the value is reduced to its int16
+// representative before it is used NON-linearly: as an operand of C_FIXDIV / C_MUL (smul then >> 15,
+// guts:64-78), or when it is stored.  Components live in two 32-bit registers (no short2 packing between
+// operations: the packed form cost one PRMT per assignment, 636 of the kernel's 2400 instructions); memory keeps
+// the reference's packed (re, im) int16 pairs, and packing wraps for free.  Range argument for the products:
+// C_FIXDIV by 4 leaves |x| <= 8191, a twiddle is <= 32767 in magnitude, so |re|, |im| of a C_MUL result are
+// <= (2 * 8191 * 32767 + 16384) >> 15 = 16382: sround's int16 cast never wraps and is left out; sums of four
+// such terms stay below 2^17.
+struct Q15Lazy {
+    using E = int2;        // (re, im), congruent mod 2^16 to the reference's int16 values
+    using S = unsigned;    // packed (re, im) int16 pair as it lies in memory
+    using Sc = int;
+    static constexpr bool kFixed = true;
+    __device__ static int sx(int a) { return (int)(short)a; }
+    __device__ static E ld(S u) { return make_int2((int)u, (int)u >> 16); }          // re keeps garbage high bits (lazy)
+    __device__ static E ldtw(S u) { return make_int2(sx((int)u), (int)u >> 16); }    // twiddles multiply: exact
+    __device__ static S st(E e) { return __byte_perm((unsigned)e.x, (unsigned)e.y, 0x5410); }
+    __device__ static int wrap(int a) { return a; }
+    __device__ static E mk(int r, int i) { return make_int2(r, i); }
+    __device__ static E add(E a, E b) { return mk((int)((unsigned)a.x + (unsigned)b.x), (int)((unsigned)a.y + (unsigned)b.y)); }
+    __device__ static E sub(E a, E b) { return mk((int)((unsigned)a.x - (unsigned)b.x), (int)((unsigned)a.y - (unsigned)b.y)); }
+    // a: exact (a C_FIXDIV result), b: exact twiddle
+    __device__ static E mul(E a, E b)
+    {
+        return mk((int)((unsigned)(a.x * b.x) - (unsigned)(a.y * b.y) + 16384u) >> 15,
+                  (int)((unsigned)(a.x * b.y) + (unsigned)(a.y * b.x) + 16384u) >> 15);
+    }
+    __device__ static E fixdiv(E a, int div)
+    {
+        const int f = 32767 / div;
+        return mk((sx(a.x) * f + 16384) >> 15, (sx(a.y) * f + 16384) >> 15);
+    }
 };
 
 // radix-2/3/4/5 butterflies on F[0], F[m], ... with twiddles tw[q*tws]
@@ -299,9 +343,13 @@ struct Fft4096Args {
 // The three passes on one transform.  In: v[4*k4 + k5] = x[t + 256*(k4 + 4*k5)] (thread t of
 // 256).  Out: v[A] = X[256*A + t].  F is the CTA's 4096+16 element exchange buffer.
 template <typename Tr, bool CONJ, typename E>
-__device__ __forceinline__ void fft4096_core(E (&v)[16], E *F, const E *__restrict__ tw1, const E *__restrict__ tw2,
-                                             const E *__restrict__ tw3, const int t, const int inverse)
+__device__ __forceinline__ void fft4096_core(E (&v)[16], typename Tr::S *F, const typename Tr::S *__restrict__ tw1_s,
+                                             const typename Tr::S *__restrict__ tw2_s, const typename Tr::S *__restrict__ tw3_s,
+                                             const int t, const int inverse)
 {
+    // twiddle tables and the exchange buffer hold the storage type; registers hold Tr::E
+    struct Tw { const typename Tr::S *__restrict__ p; __device__ __forceinline__ E operator[](int i) const { return Tr::ldtw(p[i]); } };
+    const Tw tw1{tw1_s}, tw2{tw2_s}, tw3{tw3_s};
     // pass-1 slot base: t = k0 + 4k1 + 16k2 + 64k3  ->  A = 4k0 + k1, B = 4k2 + k3
     const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
     const int base1 = 257 * A1 + 16 * B1;
@@ -321,11 +369,11 @@ __device__ __forceinline__ void fft4096_core(E (&v)[16], E *F, const E *__restri
     }
     __syncthreads();   // earlier readers of F are done
 #pragma unroll
-    for (int c = 0; c < 16; c++) F[base1 + c] = v[c];
+    for (int c = 0; c < 16; c++) F[base1 + c] = Tr::st(v[c]);
     __syncthreads();
     // ---- pass 2: stages m=16 (k = C, q = B mod 4) and m=64 (k = 16*(B mod 4) + C, q = B div 4)
 #pragma unroll
-    for (int b = 0; b < 16; b++) v[b] = F[base2 + 16 * b];
+    for (int b = 0; b < 16; b++) v[b] = Tr::ld(F[base2 + 16 * b]);
     {
         const E t1 = tw2[0 * 16 + C2], t2 = tw2[1 * 16 + C2], t3 = tw2[2 * 16 + C2];
 #pragma unroll
@@ -336,11 +384,11 @@ __device__ __forceinline__ void fft4096_core(E (&v)[16], E *F, const E *__restri
                                    tw2[(5 + 3 * bm) * 16 + C2], inverse);
     }
 #pragma unroll
-    for (int b = 0; b < 16; b++) F[base2 + 16 * b] = v[b];
+    for (int b = 0; b < 16; b++) F[base2 + 16 * b] = Tr::st(v[b]);
     __syncthreads();
     // ---- pass 3: stages m=256 (k = kk, q = A mod 4) and m=1024 (k = 256*(A mod 4) + kk, q = A div 4)
 #pragma unroll
-    for (int A = 0; A < 16; A++) v[A] = F[257 * A + t];
+    for (int A = 0; A < 16; A++) v[A] = Tr::ld(F[257 * A + t]);
     {
         const E t1 = tw3[0 * 256 + t], t2 = tw3[1 * 256 + t], t3 = tw3[2 * 256 + t];
 #pragma unroll
@@ -352,24 +400,28 @@ __device__ __forceinline__ void fft4096_core(E (&v)[16], E *F, const E *__restri
     }
 }
 
-template <typename Tr>
+// INVT: -1 = direction read from the arguments; 0 / 1 = compiled in (the Q15 kernel is instruction bound: a run-time
+// direction costs ~100 predicated instructions per transform pass set)
+template <typename Tr, int INVT = -1>
 __global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
 {
+    const int inverse = INVT < 0 ? a.inverse : INVT;
     using E = typename Tr::E;
-    __shared__ E F[4096 + 16];
+    using S = typename Tr::S;
+    __shared__ S F[4096 + 16];
     const int t = threadIdx.x;
-    const E *__restrict__ tw1 = static_cast<const E *>(a.tw1);
-    const E *__restrict__ tw2 = static_cast<const E *>(a.tw2);
-    const E *__restrict__ tw3 = static_cast<const E *>(a.tw3);
+    const S *__restrict__ tw1 = static_cast<const S *>(a.tw1);
+    const S *__restrict__ tw2 = static_cast<const S *>(a.tw2);
+    const S *__restrict__ tw3 = static_cast<const S *>(a.tw3);
     for (long long xf = blockIdx.x; xf < a.batch; xf += gridDim.x) {
-        const E *in = static_cast<const E *>(a.in) + xf * 4096;
-        E *out = static_cast<E *>(a.out) + xf * 4096;
+        const S *in = static_cast<const S *>(a.in) + xf * 4096;
+        S *out = static_cast<S *>(a.out) + xf * 4096;
         E v[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = in[t + 256 * j];   // coalesced, digit-reversed by register index
-        fft4096_core<Tr, false, E>(v, F, tw1, tw2, tw3, t, a.inverse);
+        for (int j = 0; j < 16; j++) v[4 * (j & 3) + (j >> 2)] = Tr::ld(in[t + 256 * j]);   // coalesced, digit-reversed by register index
+        fft4096_core<Tr, false, E>(v, F, tw1, tw2, tw3, t, inverse);
 #pragma unroll
-        for (int A = 0; A < 16; A++) out[256 * A + t] = v[A];
+        for (int A = 0; A < 16; A++) out[256 * A + t] = Tr::st(v[A]);
     }
 }
 
@@ -521,7 +573,13 @@ int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_c
         f.batch = (long long)batch; f.inverse = p.inverse;
         const int grid = (int)std::min<long long>((long long)batch, (long long)sm_count * 12);
         if (p.dtype == B200C_CF32) fft4096_kernel<FloatTraits<float>><<<grid, 256, 0, stream>>>(f);
-        else fft4096_kernel<Q15Traits><<<grid, 256, 0, stream>>>(f);
+        else {
+            // lazy-wrap Q15 (bit-identical; B200C_FFT_Q15=packed keeps the per-assignment wrap of round 1 for A/B runs)
+            static const bool packed = [] { const char *e = std::getenv("B200C_FFT_Q15"); return e && std::strcmp(e, "packed") == 0; }();
+            if (packed) fft4096_kernel<Q15Traits><<<grid, 256, 0, stream>>>(f);
+            else if (f.inverse) fft4096_kernel<Q15Lazy, 1><<<grid, 256, 0, stream>>>(f);
+            else fft4096_kernel<Q15Lazy, 0><<<grid, 256, 0, stream>>>(f);
+        }
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }

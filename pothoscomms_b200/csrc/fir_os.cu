@@ -200,6 +200,7 @@ struct FirOs32Args {
     long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
     int nchan;
     int K;
+    int spread;         // TABS form: warp-major task order (launches smaller than one wave of warps)
 };
 
 // TABS: one persistent CTA per SM whose warps share ONE copy of the tap spectrum and the twiddles in (dynamic) shared
@@ -220,19 +221,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     const c2 *__restrict__ hf_tab = nullptr;
     c2 *Lb = F;                                               // where the bulk copy lands
     if constexpr (TABS && EARLY) Lb = os32_dyn + WARPS * kOs32SmemElems + 2048 + w * kOs32Landing;
-    if constexpr (TABS) {
-        c2 *tab = os32_dyn + WARPS * kOs32SmemElems;
-        const c2 *__restrict__ hf0 = static_cast<const c2 *>(a.hf);
-        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
-        __syncthreads();
-        hf_tab = tab; tw = tab + 1024;
-    }
     const int Km1 = a.K - 1;
     const int hop = 1024 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
-    // tasks = (channel, block), channel-major, taken grid-stride by the warps (see fir_os64_kernel)
+    // tasks = (channel, block), channel-major, taken grid-stride by the warps (see fir_os64_kernel).  A launch with
+    // fewer tasks than resident warps (a small work() buffer) is spread warp-major, so that every SM gets a block
+    // before any SM gets a second one.
     const long long tstep = (long long)gridDim.x * WARPS, dch = tstep / nblk, dblk = tstep - dch * nblk;
-    const long long task0 = (long long)blockIdx.x * WARPS + w;
+    const long long task0 = a.spread ? (long long)w * gridDim.x + blockIdx.x : (long long)blockIdx.x * WARPS + w;
     long long ch = task0 / nblk, blk = task0 - ch * nblk;
     // the warp's next block is fetched into its exchange tile by one bulk copy while the warp is
     // in its last register pass; edge blocks use guarded loads
@@ -251,6 +247,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     bool pending = bulk_src(ch, blk, src);
     if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
+    if constexpr (TABS) {
+        // the tables are staged while the first block is in flight (a launch's fixed cost matters for small work() buffers)
+        c2 *tab = os32_dyn + WARPS * kOs32SmemElems;
+        const c2 *__restrict__ hf0 = static_cast<const c2 *>(a.hf);
+        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
+        __syncthreads();
+        hf_tab = tab; tw = tab + 1024;
+    }
     while (ch < a.nchan) {
         const long long base = blk * hop;
         long long nch = ch + dch, nblkpos = blk + dblk;      // this warp's next task
@@ -1451,6 +1455,7 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
         a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
+        a.spread = 0;
         static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 2012; }();
 #define OS32_LAUNCH(W, MB)                                                                                        \
     {                                                                                                             \
@@ -1471,7 +1476,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
                 B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
                 configured[dev] = true;
             }
-            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
+            // fewer blocks than one wave of warps: one CTA per SM anyway, blocks dealt warp-major
+            a.spread = nblk < 12LL * sm_count ? 1 : 0;
+            const int grid = (int)std::min<long long>(a.spread ? nblk : (nblk + 11) / 12, (long long)sm_count);
             if (cfg >= 2000) fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
             else if (cfg >= 1100) fir_os32_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
             else fir_os32_kernel<12, 1, true, false><<<grid, 32 * 12, smem, stream>>>(a);

@@ -101,8 +101,10 @@ class PeerHalo:
     128-byte export records to the neighbour; a C++ Pothos host would use any IPC of its own.
 
     `buf` is this rank's [K-1 halo | segment] tensor (cudaMalloc-backed: torch's default allocator).
-    `mark_tail_ready()` records "my tail is final" on this rank's stream, `pull()` makes the stream wait
-    for the neighbour's mark and enqueues the copy."""
+    `pull(wait=False)` enqueues the copy alone (the caller has ordered producer and consumer on the host);
+    `mark_tail_ready()` / `pull(wait=True)` add the GPU-side edge through an interprocess event.  Note the
+    CUDA semantics: a wait captures the owner's most recent record AT CALL TIME, so hosts that run several
+    steps ahead of their GPUs must sequence record-before-wait themselves."""
 
     def __init__(self, buf, K: int, rank: int, world: int, device: int, gather=None):
         import ctypes

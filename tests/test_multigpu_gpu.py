@@ -51,11 +51,10 @@ def test_two_gpu_segments_with_peer_halo_match_single_stream(oracle, cuda_device
     links = [sharding.PeerHalo(bufs[r], K, r, world, r, gather=gather) for r in range(world)]
     parts = []
     for r in range(world):
-        with torch.cuda.device(r):
-            links[r].mark_tail_ready()
+        torch.cuda.synchronize(r)          # every tail is final (host-level ordering, as in the bench)
     for r in range(world):
         with torch.cuda.device(r):
-            links[r].pull()
+            links[r].pull(wait=False)
             y, c, p = firs[r].run(bufs[r])
             torch.cuda.synchronize(r)
             assert c == bounds[r][1] - bounds[r][0]
