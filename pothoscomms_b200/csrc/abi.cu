@@ -48,40 +48,59 @@ static int dev_info(int device, DevInfo &di)
     return B200C_OK;
 }
 
-constexpr int kHostSlots = 3;
+constexpr int kHostSlotsMax = 8;
+// Host-buffer entry points: chunk size and pipeline depth (streams / staging slots).  Defaults from the sweep in
+// profiles/ (tools/sweep_host_path.py); B200C_HOST_CHUNK_MIB / B200C_HOST_SLOTS override for A/B runs.
+static size_t host_chunk_bytes()
+{
+    static const size_t v = [] { const char *e = std::getenv("B200C_HOST_CHUNK_MIB"); const long m = e ? std::atol(e) : 0; return (size_t)(m > 0 ? m : 32) << 20; }();
+    return v;
+}
+static int host_slots()
+{
+    static const int v = [] { const char *e = std::getenv("B200C_HOST_SLOTS"); const int n = e ? std::atoi(e) : 0; return n >= 2 && n <= kHostSlotsMax ? n : 3; }();
+    return v;
+}
 
 struct HostPipe {   // staging for the *_run_host entry points
-    cudaStream_t streams[kHostSlots] = {nullptr, nullptr, nullptr};
-    void *d_in[kHostSlots] = {nullptr, nullptr, nullptr};
-    void *d_out[kHostSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kHostSlotsMax] = {};
+    void *d_in[kHostSlotsMax] = {};
+    void *d_out[kHostSlotsMax] = {};
     size_t in_bytes = 0, out_bytes = 0;
     bool streams_ok = false;
+    int n = 3;             // slots in use
 
     int ensure(size_t need_in, size_t need_out)
     {
         if (!streams_ok) {
-            for (auto &s : streams) B200C_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            n = host_slots();
+            for (int i = 0; i < n; i++) B200C_CUDA_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
             streams_ok = true;
         }
         if (need_in > in_bytes) {
             for (auto &p : d_in) { if (p) cudaFree(p); p = nullptr; }
             in_bytes = 0;
-            for (auto &p : d_in) B200C_CUDA_TRY(cudaMalloc(&p, need_in));
+            for (int i = 0; i < n; i++) B200C_CUDA_TRY(cudaMalloc(&d_in[i], need_in));
             in_bytes = need_in;
         }
         if (need_out > out_bytes) {
             for (auto &p : d_out) { if (p) cudaFree(p); p = nullptr; }
             out_bytes = 0;
-            for (auto &p : d_out) B200C_CUDA_TRY(cudaMalloc(&p, need_out));
+            for (int i = 0; i < n; i++) B200C_CUDA_TRY(cudaMalloc(&d_out[i], need_out));
             out_bytes = need_out;
         }
+        return B200C_OK;
+    }
+    int sync_all()
+    {
+        for (int i = 0; i < n; i++) B200C_CUDA_TRY(cudaStreamSynchronize(streams[i]));
         return B200C_OK;
     }
     void release()
     {
         for (auto &p : d_in) { if (p) cudaFree(p); p = nullptr; }
         for (auto &p : d_out) { if (p) cudaFree(p); p = nullptr; }
-        if (streams_ok) for (auto &s : streams) cudaStreamDestroy(s);
+        if (streams_ok) for (int i = 0; i < n; i++) cudaStreamDestroy(streams[i]);
         streams_ok = false; in_bytes = out_bytes = 0;
     }
 };
@@ -393,8 +412,8 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
 
     const size_t esz = dtype_bytes(h->dtype), M = h->M, L = h->L, K = h->table.K;
     const size_t nblocks = c / M;
-    // chunks of ~32 MiB of input, a whole number of blocks each
-    size_t cb = std::max<size_t>(1, (32u << 20) / (esz * M));
+    // chunks of ~32 MiB of input (host_chunk_bytes), a whole number of blocks each
+    size_t cb = std::max<size_t>(1, host_chunk_bytes() / (esz * M));
     // overlap-save: chunk on a whole number of FFT hops so chunked and one-shot runs use the very
     // same block partition (bit-identical outputs)
     if (h->use_os) cb = std::max<size_t>(1, cb / h->os.hop()) * h->os.hop();
@@ -405,7 +424,7 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
     const char *src = static_cast<const char *>(h_in);
     char *dst = static_cast<char *>(h_out);
     size_t slot = 0;
-    for (size_t b0 = 0; b0 < nblocks; b0 += cb, slot = (slot + 1) % kHostSlots) {
+    for (size_t b0 = 0; b0 < nblocks; b0 += cb, slot = (slot + 1) % (size_t)h->pipe.n) {
         const size_t nb = std::min(cb, nblocks - b0);
         const size_t first = b0 * M;                                  // element index of the chunk's history start
         const size_t want = nb * M + K - 1;
@@ -416,8 +435,7 @@ int b200c_fir_run_host(b200c_fir *h, const void *h_in, size_t in_elems, void *h_
         if (rc) return rc;
         B200C_CUDA_TRY(cudaMemcpyAsync(dst + b0 * L * esz, h->pipe.d_out[slot], nb * L * esz, cudaMemcpyDeviceToHost, s));
     }
-    for (auto s : h->pipe.streams) B200C_CUDA_TRY(cudaStreamSynchronize(s));
-    return B200C_OK;
+    return h->pipe.sync_all();
 }
 
 /* ----------------------------------------------------------------------- filter bank --- */
@@ -602,14 +620,14 @@ int b200c_fft_run_host(b200c_fft *h, const void *h_in, void *h_out, size_t batch
     DeviceGuard g(h->device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", h->device); return B200C_ERR_CUDA; }
     const size_t tb = (size_t)h->plan.n * dtype_bytes(h->plan.dtype);
-    size_t cb = std::max<size_t>(1, (32u << 20) / tb);
+    size_t cb = std::max<size_t>(1, host_chunk_bytes() / tb);
     cb = std::min(cb, batch);
     int rc = h->pipe.ensure(cb * tb, cb * tb);
     if (rc) return rc;
     const char *src = static_cast<const char *>(h_in);
     char *dst = static_cast<char *>(h_out);
     size_t slot = 0;
-    for (size_t b0 = 0; b0 < batch; b0 += cb, slot = (slot + 1) % kHostSlots) {
+    for (size_t b0 = 0; b0 < batch; b0 += cb, slot = (slot + 1) % (size_t)h->pipe.n) {
         const size_t nb = std::min(cb, batch - b0);
         cudaStream_t s = h->pipe.streams[slot];
         B200C_CUDA_TRY(cudaMemcpyAsync(h->pipe.d_in[slot], src + b0 * tb, nb * tb, cudaMemcpyHostToDevice, s));
@@ -617,8 +635,7 @@ int b200c_fft_run_host(b200c_fft *h, const void *h_in, void *h_out, size_t batch
         if (rc) return rc;
         B200C_CUDA_TRY(cudaMemcpyAsync(dst + b0 * tb, h->pipe.d_out[slot], nb * tb, cudaMemcpyDeviceToHost, s));
     }
-    for (auto s : h->pipe.streams) B200C_CUDA_TRY(cudaStreamSynchronize(s));
-    return B200C_OK;
+    return h->pipe.sync_all();
 }
 
 /* ------------------------------------------------------- device-resident ring (CUDA VMM) --- */

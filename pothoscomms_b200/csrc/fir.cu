@@ -310,9 +310,12 @@ int fir_build_table(FirTable &t, int dtype, int taps_kind, const double *taps, s
 
     // register block: odd R in {9,7,5}, least zero padding wins (ties -> larger R); the 64-bit
     // accumulator types keep R = 5 to bound register pressure
-    const bool wide = acc_scalar_bytes(dtype) == 8;
+    // Only the float32 and int16 families have R = 7 / 9 instantiations (launch_shape); every other type runs R = 5.
+    // (Round 1 searched R for int8 as well while launching R = 5: a tile covered 5/7 of its blocks -- found by the
+    // reference-generated fixture fir_ci8_cc_21_l2.)
+    const bool tuned = (dtype >> 1) == 0 || (dtype >> 1) == 3;
     int bestR = 5;
-    if (!wide) {
+    if (tuned) {
         long long best_pad = -1;
         for (int R : {9, 7, 5}) {
             const long long padded = (smax + R - 1) / R * R;

@@ -110,21 +110,32 @@ int b200c_peer_close(void *mapping)
     return rc;
 }
 
+// An event handle as this library hands it out.  The interprocess event serves neighbours in OTHER processes; a
+// neighbour in the SAME process waits on a plain event recorded next to it (cudaStreamWaitEvent on an interprocess
+// event from another device's stream of the same process faults inside the driver -- tools/probe_peer_halo.cpp).
+struct PeerEvent {
+    cudaEvent_t ipc;      // interprocess event (owner) / opened interprocess event (other process) / nullptr (same-process alias)
+    cudaEvent_t plain;    // same-process event (owner and same-process aliases) / nullptr
+    bool owner;
+};
+
 int b200c_peer_event_create(void **event, int device, b200c_peer_event *out)
 {
     if (!event || !out) { set_error("b200c_peer_event_create: null argument"); return B200C_ERR_INVALID; }
     DeviceGuard g(device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
-    cudaEvent_t ev;
+    cudaEvent_t ev, plain;
     B200C_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
     cudaIpcEventHandle_t eh;
-    const cudaError_t e = cudaIpcGetEventHandle(&eh, ev);
-    if (e != cudaSuccess) { cudaEventDestroy(ev); set_error("cudaIpcGetEventHandle failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return B200C_ERR_CUDA; }
+    cudaError_t e = cudaIpcGetEventHandle(&eh, ev);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plain, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaEventDestroy(ev); set_error("peer event creation failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return B200C_ERR_CUDA; }
+    PeerEvent *pe = new PeerEvent{ev, plain, true};
     std::memset(out, 0, sizeof(*out));
     std::memcpy(out->ipc, &eh, 64);
     out->pid = (int64_t)getpid();
-    out->local_event = (uint64_t)(uintptr_t)ev;
-    *event = ev;
+    out->local_event = (uint64_t)(uintptr_t)pe;
+    *event = pe;
     return B200C_OK;
 }
 
@@ -133,36 +144,49 @@ int b200c_peer_event_open(const b200c_peer_event *e, int device, void **event)
     if (!e || !event) { set_error("b200c_peer_event_open: null argument"); return B200C_ERR_INVALID; }
     DeviceGuard g(device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
-    if (e->pid == (int64_t)getpid()) { *event = (void *)(uintptr_t)e->local_event; return B200C_OK; }
+    if (e->pid == (int64_t)getpid()) {
+        const PeerEvent *own = reinterpret_cast<const PeerEvent *>((uintptr_t)e->local_event);
+        *event = new PeerEvent{nullptr, own->plain, false};
+        return B200C_OK;
+    }
     cudaIpcEventHandle_t eh;
     std::memcpy(&eh, e->ipc, 64);
     cudaEvent_t ev;
     B200C_CUDA_TRY(cudaIpcOpenEventHandle(&ev, eh));
-    *event = ev;
+    *event = new PeerEvent{ev, nullptr, false};
     return B200C_OK;
 }
 
 int b200c_peer_event_record(void *event, int device, void *stream)
 {
+    PeerEvent *pe = static_cast<PeerEvent *>(event);
+    if (!pe || !pe->owner) { set_error("b200c_peer_event_record: only the creating side records"); return B200C_ERR_INVALID; }
     DeviceGuard g(device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
-    B200C_CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    B200C_CUDA_TRY(cudaEventRecord(pe->ipc, (cudaStream_t)stream));
+    B200C_CUDA_TRY(cudaEventRecord(pe->plain, (cudaStream_t)stream));
     return B200C_OK;
 }
 
 int b200c_peer_event_wait(void *event, int device, void *stream)
 {
+    PeerEvent *pe = static_cast<PeerEvent *>(event);
+    if (!pe) { set_error("b200c_peer_event_wait: null event"); return B200C_ERR_INVALID; }
     DeviceGuard g(device);
     if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return B200C_ERR_CUDA; }
-    B200C_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    B200C_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, pe->plain ? pe->plain : pe->ipc, 0));
     return B200C_OK;
 }
 
 int b200c_peer_event_destroy(void *event, int device)
 {
-    if (!event) return B200C_OK;
+    PeerEvent *pe = static_cast<PeerEvent *>(event);
+    if (!pe) return B200C_OK;
     DeviceGuard g(device);
-    B200C_CUDA_TRY(cudaEventDestroy((cudaEvent_t)event));
+    if (pe->owner) { cudaEventDestroy(pe->ipc); cudaEventDestroy(pe->plain); }
+    else if (pe->ipc) cudaEventDestroy(pe->ipc);
+    (void)cudaGetLastError();
+    delete pe;
     return B200C_OK;
 }
 

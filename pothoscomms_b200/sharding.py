@@ -170,6 +170,9 @@ class PeerHalo:
         if self._mapping is not None:
             self.lib.b200c_peer_close(self._mapping)
             self._mapping = None
+        if self._peer_event is not None:
+            self.lib.b200c_peer_event_destroy(self._peer_event, self.device)
+            self._peer_event = None
         if self._event is not None:
             self.lib.b200c_peer_event_destroy(self._event, self.device)
             self._event = None

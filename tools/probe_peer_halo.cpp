@@ -48,6 +48,7 @@ int main(int argc, char **argv)
     STEP(p_b200c_stream_sync(1, nullptr));
     printf("halo bytes %s\n", std::memcmp(g.data(), h.data(), bytes) == 0 ? "MATCH" : "DIFFER");
     STEP(p_b200c_peer_close(mapping));
+    STEP(p_b200c_peer_event_destroy(ev_open, 1));
     STEP(p_b200c_peer_event_destroy(ev, 0));
     p_b200c_dev_free(a, 0); p_b200c_dev_free(b, 1);
     return 0;
