@@ -169,14 +169,15 @@ constexpr bool kOs32PartialTwiddles = B200C_OS32_PARTIAL_TW != 0;
 // k = 4a + b, W^(kt) = W^(4a t) W^(b t).  The 21 extra complex multiplies cost FMA issue slots, the 21
 // saved loads were a fifth of the kernel's L1/shared data-pipe traffic, which is the busier pipe
 // (profiles/r01c_prof_os32_headline.txt).  One more rounding per twiddled element (~1e-7 relative).
-template <bool CONJ, bool SLOT_REV>
+// COMPACT: `tw` holds only the ten rows read here (rows 1, 2, 3 in slots 0..2, rows 4 a in slots 2 + a)
+template <bool CONJ, bool SLOT_REV, bool COMPACT = false>
 __device__ __forceinline__ void twiddle32(c2 (&v)[32], const c2 *__restrict__ tw, const int t)
 {
     c2 A[8], B[4];
 #pragma unroll
-    for (int a = 1; a < 8; a++) A[a] = tw[(4 * a) * 32 + t];
+    for (int a = 1; a < 8; a++) A[a] = tw[(COMPACT ? 2 + a : 4 * a) * 32 + t];
 #pragma unroll
-    for (int b = 1; b < 4; b++) B[b] = tw[b * 32 + t];
+    for (int b = 1; b < 4; b++) B[b] = tw[(COMPACT ? b - 1 : b) * 32 + t];
 #pragma unroll
     for (int k = 1; k < 32; k++) {
         const int a = k >> 2, b = k & 3, r = SLOT_REV ? rev32(k) : k;
@@ -402,9 +403,17 @@ constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
 // WARPS == 1: one warp per CTA, MINB CTAs per SM, tables read through L1.  WARPS > 1: one persistent CTA per SM
 // whose warps share ONE copy of the tables (tap spectrum 24 KB, step twiddles 12 KB + 8 KB) in shared memory.
 constexpr int kX32TabElems = 3072 + 1536 + 1024;
-template <int WARPS, int MINB, bool PT = false>
+// EARLY (WARPS > 1, PT): fewer warps, each with a landing buffer -- the bulk copy of the warp's NEXT block is issued as
+// soon as the current block sits in registers (fir_os32_kernel's step 6); what pays for the buffers is compact tables
+// (only the 10 + 18 twiddle rows the partial-twiddle form reads) and fewer tiles.  The tap spectrum is stored
+// interleaved, (H'[kk], H'[kk + 1536]) side by side, so one 128-bit load fetches both factors of a bin.
+constexpr int kX32TwRows = 10, kX32Tw3Rows = 18;
+constexpr int kX32TabElemsEarly = 3072 + kX32Tw3Rows * 32 + kX32TwRows * 32;
+constexpr int kX32Landing = 1032;
+template <int WARPS, int MINB, bool PT = false, bool EARLY = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOsX32Args a)
 {
+    static_assert(!EARLY || (PT && WARPS > 1), "the landing-buffer form is the persistent partial-twiddle kernel");
     extern __shared__ __align__(16) c2 x32_smem[];
     __shared__ __align__(8) unsigned long long bars[WARPS];
     const int t = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -412,14 +421,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
     const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
     const c2 *__restrict__ hx = static_cast<const c2 *>(a.hx);
     c2 *F = x32_smem + wp * kX32SmemElems;
-    if constexpr (WARPS > 1) {
-        c2 *tab = x32_smem + WARPS * kX32SmemElems;
-        for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
-        for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
-        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
-        __syncthreads();
-        hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
-    }
+    c2 *Lb = F;                                                  // where the bulk copy lands
+    if constexpr (EARLY) Lb = x32_smem + WARPS * kX32SmemElems + kX32TabElemsEarly + wp * kX32Landing;
     unsigned long long &bar = bars[wp];
     const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
     c2 *__restrict__ out = static_cast<c2 *>(a.out);
@@ -439,8 +442,31 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
     const long long bstep = (long long)gridDim.x * WARPS;
     const c2 *src = nullptr;
     bool pending = bulk_src(blk, src);
-    if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+    if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
     unsigned parity = 0;
+    if constexpr (WARPS > 1) {
+        // tables staged while the first block is in flight
+        c2 *tab = x32_smem + WARPS * kX32SmemElems;
+        if constexpr (EARLY) {
+            // interleaved tap spectrum: tab[2 (32 c + t) + {0, 1}] = (H'[32 c + t], H'[1536 + 32 c + t]), c < 48
+            for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) { tab[2 * i] = hx[i]; tab[2 * i + 1] = hx[1536 + i]; }
+            // step twiddles of the inverse: rows 0..16 and row 32 (slot 17)
+            for (int i = threadIdx.x; i < kX32Tw3Rows * 32; i += 32 * WARPS) tab[3072 + i] = tw3[i < 17 * 32 ? i : 32 * 32 + (i - 17 * 32)];
+            // forward twiddles: rows 1, 2, 3 (slots 0..2) and 4 a, a = 1..7 (slots 2 + a)
+            for (int i = threadIdx.x; i < kX32TwRows * 32; i += 32 * WARPS) {
+                const int slot = i >> 5, row = slot < 3 ? slot + 1 : 4 * (slot - 2);
+                tab[3072 + kX32Tw3Rows * 32 + i] = tw[row * 32 + (i & 31)];
+            }
+            __syncthreads();
+            hx = tab; tw3 = tab + 3072; tw = tab + 3072 + kX32Tw3Rows * 32;
+        } else {
+            for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
+            for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
+            for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
+            __syncthreads();
+            hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
+        }
+    }
     for (; blk < nblk; blk += bstep) {
         const long long P = a.p0 + blk * hop_in;
         c2 v[32];
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
             mbar_wait(&bar, parity);
             parity ^= 1;
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = F[mis + 32 * n1 + t];
+            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = Lb[mis + 32 * n1 + t];
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) {
@@ -457,9 +483,15 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
                 v[rev32(n1)] = (g >= 0 && g < a.n_in) ? __ldcg(in + g) : 0ull;
             }
         }
+        if constexpr (EARLY) {
+            __syncwarp();                                    // the landing buffer is in registers: fetch the next block now
+            pending = bulk_src(blk + bstep, src);
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
+        }
         // forward 1024 = 32 x 32 (as fir_os32_kernel): thread t ends with X[t + 32 k2] in v[k2]
         dft32_dit<false>(v);
-        if constexpr (PT) twiddle32<false, false>(v, tw, t);   // ten loaded + 21 computed twiddles
+        if constexpr (EARLY) twiddle32<false, false, true>(v, tw, t);   // the same from the compact table
+        else if constexpr (PT) twiddle32<false, false>(v, tw, t);   // ten loaded + 21 computed twiddles
         else {
 #pragma unroll
             for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
@@ -478,9 +510,16 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             const c2 xa = v[c], xb = v[c + 16];
-            const c2 h0 = hx[32 * c + t], g0 = hx[1536 + 32 * c + t];
-            const c2 h1 = hx[32 * (c + 16) + t], g1 = hx[1536 + 32 * (c + 16) + t];
-            const c2 h2 = hx[32 * (c + 32) + t], g2 = hx[1536 + 32 * (c + 32) + t];
+            c2 h0, g0, h1, g1, h2, g2;
+            if constexpr (EARLY) {
+                const ulonglong2 *hg = reinterpret_cast<const ulonglong2 *>(hx);
+                const ulonglong2 p0 = hg[32 * c + t], p1 = hg[32 * (c + 16) + t], p2 = hg[32 * (c + 32) + t];
+                h0 = p0.x; g0 = p0.y; h1 = p1.x; g1 = p1.y; h2 = p2.x; g2 = p2.y;
+            } else {
+                h0 = hx[32 * c + t]; g0 = hx[1536 + 32 * c + t];
+                h1 = hx[32 * (c + 16) + t]; g1 = hx[1536 + 32 * (c + 16) + t];
+                h2 = hx[32 * (c + 32) + t]; g2 = hx[1536 + 32 * (c + 32) + t];
+            }
             s[c % 3][c / 3] = cmul_acc(xb, g0, cmul_p<false>(xa, h0));
             s[(c + 16) % 3][(c + 16) / 3] = cmul_acc(xa, g1, cmul_p<false>(xb, h1));
             s[(c + 32) % 3][(c + 32) / 3] = cmul_acc(xb, g2, cmul_p<false>(xa, h2));
@@ -491,7 +530,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
         __syncwarp();
         // step twiddles exp(2 pi i t n2 / 1536), n2 = 16 v1 + v2: PT loads the 15 + 2 factors and multiplies
         c2 twb1 = 0, twb2 = 0;
-        if constexpr (PT) { twb1 = tw3[16 * 32 + t]; twb2 = tw3[32 * 32 + t]; }
+        if constexpr (PT) { twb1 = tw3[16 * 32 + t]; twb2 = tw3[(EARLY ? 17 : 32) * 32 + t]; }
 #pragma unroll
         for (int v2 = 0; v2 < 16; v2++) {
             const int r = rev16(v2);
@@ -538,9 +577,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
             for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[(32 + t) * kOs32Stride + k1];
         }
-        __syncwarp();                                        // the tile is free: fetch the next block into it
-        pending = bulk_src(blk + bstep, src);
-        if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+        if constexpr (!EARLY) {
+            __syncwarp();                                    // the tile is free: fetch the next block into it
+            pending = bulk_src(blk + bstep, src);
+            if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+        }
         if (t < 16) {
             dft32_dit<true>(v);
             if (whole) {
@@ -1362,7 +1403,24 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         const size_t tile = sizeof(c2) * kX32SmemElems;
         // partial twiddles (10 + 17 loaded, the rest multiplied up): C3 207.8 -> 211.2 Gsamples/s; B200C_OSX_PT=0 loads all
         static const bool pt = [] { const char *e = std::getenv("B200C_OSX_PT"); return !e || std::atoi(e) != 0; }();
-        if (minb >= 100) {
+        if (minb == 208 || minb == 209) {
+            // 8 / 9 warps per SM, each with a landing buffer, compact tables, interleaved tap spectrum
+            const size_t smem = sizeof(c2) * ((size_t)(minb - 200) * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly);
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<8, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(sizeof(c2) * (8 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<9, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(sizeof(c2) * (9 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
+                configured[dev] = true;
+            }
+            const int w = minb - 200;
+            const int grid = (int)std::min<long long>((nblk + w - 1) / w, (long long)sm_count);
+            if (w == 8) fir_os32x_kernel<8, 1, true, true><<<grid, 32 * 8, smem, stream>>>(a);
+            else fir_os32x_kernel<9, 1, true, true><<<grid, 32 * 9, smem, stream>>>(a);
+        } else if (minb >= 100) {
             auto kern = pt ? fir_os32x_kernel<12, 1, true> : fir_os32x_kernel<12, 1, false>;
             const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
             static thread_local bool configured[16] = {false};
