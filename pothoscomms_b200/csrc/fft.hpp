@@ -81,9 +81,18 @@ constexpr size_t kFirOsAutoMinTapsReal = 9;
 // transform block.  B200C_FIR_ALGO=fft forces the fused path from 2 taps.
 constexpr size_t kFirOsAutoMinTapsFloat = 9;
 constexpr size_t kFirOsAutoMinTapsResamp = 24;
-constexpr size_t kFirOsAutoMinTapsOsp = 16;       // complex float32 resamplers served by fir_osp(g)_kernel
+// complex float32 resamplers served by fir_osp(g)_kernel: crossover against the direct kernel measured between 24 and
+// 64 taps per phase for every rate pair of the sweep (profiles/r02_sweep_dispatch.jsonl); pure decimation by 4 only
+// from ~192 taps; the spectral resampler (L = 3, M = 2) already wins at 16 per phase
+constexpr size_t kFirOsAutoMinTapsOsp = 40;
+constexpr size_t kFirOsAutoMinTapsOspDecim4 = 192;
+constexpr size_t kFirOsAutoMinTapsX32 = 16;
+// general kernel with L >= 5 (one inverse transform per output slot): wins only from ~128 taps per phase at L = 8 and
+// never at L = 16 in the sweep
+constexpr size_t kFirOsAutoMinTapsWideInterp = 112;
 constexpr long long kFirOsGenMaxSpan = 400;   // general kernel: keep hop >= ~60 % of the block
-constexpr size_t kFirOsGenMaxInterp = 64;
+constexpr size_t kFirOsGenForcedMaxInterp = 64;   // what the kernel supports (B200C_FIR_ALGO=fft)
+constexpr size_t kFirOsGenMaxInterp = 8;    // measured: the direct kernel wins at L = 16 for every tap count
 int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, bool complex_taps, size_t M, size_t L,
                      bool force);
 void fir_os_destroy(FirOsPlan &p);

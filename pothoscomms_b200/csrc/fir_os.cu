@@ -410,7 +410,11 @@ constexpr int kX32TabElems = 3072 + 1536 + 1024;
 constexpr int kX32TwRows = 10, kX32Tw3Rows = 18;
 constexpr int kX32TabElemsEarly = 3072 + kX32Tw3Rows * 32 + kX32TwRows * 32;
 constexpr int kX32Landing = 1032;
-template <int WARPS, int MINB, bool PT = false, bool EARLY = false>
+// SPLIT: the 16 rows left for the second inverse round (rows 32..47 on 32 lanes) are transformed by lane PAIRS instead
+// of by lanes 0..15 alone: lane (tt, h) takes the inputs k1 = 2 j + h of row 32 + tt through a 16-point transform, the odd
+// half is twiddled, one shuffle exchange (xor 16) combines them -- w[m] = S0[m] + W^m S1[m] on h = 0, w[m + 16] = S0[m] -
+// W^m S1[m] on h = 1.  126 packed instructions on all lanes instead of 222 on half of them.
+template <int WARPS, int MINB, bool PT = false, bool EARLY = false, bool SPLIT = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOsX32Args a)
 {
     static_assert(!EARLY || (PT && WARPS > 1), "the landing-buffer form is the persistent partial-twiddle kernel");
@@ -571,6 +575,30 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++)
                 if (d0 + 48 * n1 >= 0 && 48 * n1 < left) __stcg(o + 48 * n1, v[n1]);
+        }
+        if constexpr (SPLIT) {
+            // round 2 by lane pairs: lane (tt, h) -> sub-transform over k1 = 2 j + h of row 32 + tt
+            const int tt = t & 15, h = t >> 4;
+            c2 x[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) x[j] = F[(32 + tt) * kOs32Stride + 2 * j + h];
+            if constexpr (!EARLY) {
+                __syncwarp();                                // the tile is free: fetch the next block into it
+                pending = bulk_src(blk + bstep, src);
+                if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
+            }
+            dft16_dif<true>(x);                              // S_h[m] in x[rev16(m)]
+            c2 *const o2 = out + mbase + tt + 32 + 48 * 16 * h;   // w[48 (m + 16 h) + 32 + tt]
+            const int d2 = tt - m0 + 32 + 48 * 16 * h;
+            const int left2 = whole ? 0x7fffffff : (int)(a.n_out - mbase) - tt - 32 - 48 * 16 * h;
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const c2 mine = h ? mul_w64<true>(x[rev16(m)], 2 * m) : x[rev16(m)];     // h = 1: e^{+2 pi i m / 32} S1[m]
+                const c2 other = __shfl_xor_sync(0xffffffffu, mine, 16);
+                const c2 y = h ? sub2(other, mine) : add2(mine, other);
+                if (d2 + 48 * m >= 0 && 48 * m < left2) __stcg(o2 + 48 * m, y);
+            }
+            continue;
         }
         // round 2: lanes 0..15 transform rows 32 + t -> w[48 n1 + 32 + t]
         if (t < 16) {
@@ -1214,7 +1242,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
     // (fir_os32x_kernel); its rate does not depend on the tap count while the hop stays above ~60 % of the block
     const bool no_x32 = [] { const char *e = std::getenv("B200C_OSX"); return e && std::atoi(e) == 0; }();   // read per configure: tests compare both
     if (dtype == B200C_CF32 && L == 3 && M == 2 && !no_x32 && ntaps >= 2 && ntaps <= 1200 &&
-        (force || (ntaps + L - 1) / L >= kFirOsAutoMinTapsOsp)) {
+        (force || (ntaps + L - 1) / L >= kFirOsAutoMinTapsX32)) {
         const long long K = (long long)((ntaps + L - 1) / L);            // filter/FIRFilter.cpp:335
         int m0 = (int)((ntaps - 2 + 1) / 2);                             // ceil((ntaps - 2) / 2): v[i] is alias free from i = ntaps - 1
         m0 = (m0 + 2) / 3 * 3;                                           // whole output blocks q per transform block
@@ -1296,7 +1324,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
     // multi-warp resampler kernel: complex float32, 2 <= max(L, M) <= 4 (pure M <= 2 decimators stay on the one-warp kernel)
     const bool osp = dtype == B200C_CF32 && L <= 4 && M <= 4 && std::max(L, M) >= 2 && !(L == 1 && M <= 2) &&
                      !(std::getenv("B200C_OSP") && std::atoi(std::getenv("B200C_OSP")) == 0);
-    if ((dtype == B200C_CF32 || dtype == B200C_F32) && (M <= 2 || osp) && L <= kFirOsGenMaxInterp) {
+    if ((dtype == B200C_CF32 || dtype == B200C_F32) && (M <= 2 || osp) && L <= (force ? kFirOsGenForcedMaxInterp : kFirOsGenMaxInterp)) {
         const size_t per_phase = (ntaps + L - 1) / L;
         // the grouped resampler runs at the same rate whatever the tap count and beats the direct kernel
         // from 16 taps per phase (measured: 48-tap RRC, L = 3, M = 2: 151 vs 137 Gsamples/s)
@@ -1304,7 +1332,10 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
         const int nw = (int)std::max(L, M), G = nw == 2 ? 6 : nw == 3 ? 4 : 3;
         const bool grouped = osp && !no_group &&
                              sizeof(c2) * ((size_t)L * M * 1024 + 1024 + G * ((size_t)M * kOs32SmemElems + (size_t)L * osp_plane_stride((int)L))) <= 227 * 1024;
-        const size_t min_taps = (M == 1 && L == 1) ? kFirOsAutoMinTapsReal : grouped ? kFirOsAutoMinTapsOsp : kFirOsAutoMinTapsResamp;
+        const size_t min_taps = (M == 1 && L == 1) ? kFirOsAutoMinTapsReal
+                                : (osp && M == 4 && L == 1) ? kFirOsAutoMinTapsOspDecim4
+                                : osp ? kFirOsAutoMinTapsOsp
+                                : L >= 5 ? kFirOsAutoMinTapsWideInterp : kFirOsAutoMinTapsResamp;
         if (!force && per_phase < min_taps) return B200C_OK;
         if (ntaps < 2) return B200C_OK;
         p.osp = osp;
@@ -1403,7 +1434,35 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         const size_t tile = sizeof(c2) * kX32SmemElems;
         // partial twiddles (10 + 17 loaded, the rest multiplied up): C3 207.8 -> 211.2 Gsamples/s; B200C_OSX_PT=0 loads all
         static const bool pt = [] { const char *e = std::getenv("B200C_OSX_PT"); return !e || std::atoi(e) != 0; }();
-        if (minb == 208 || minb == 209) {
+        if (minb == 312) {
+            // 12 warps, tables in shared memory, second inverse round by lane pairs
+            const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev] = true;
+            }
+            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
+            fir_os32x_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem, stream>>>(a);
+        } else if (minb == 308 || minb == 309) {
+            const int w = minb - 300;
+            const size_t smem = sizeof(c2) * ((size_t)w * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly);
+            static thread_local bool configured[16] = {false};
+            int dev = 0;
+            B200C_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 16 && !configured[dev]) {
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<8, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(sizeof(c2) * (8 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
+                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<9, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(sizeof(c2) * (9 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
+                configured[dev] = true;
+            }
+            const int grid = (int)std::min<long long>((nblk + w - 1) / w, (long long)sm_count);
+            if (w == 8) fir_os32x_kernel<8, 1, true, true, true><<<grid, 32 * 8, smem, stream>>>(a);
+            else fir_os32x_kernel<9, 1, true, true, true><<<grid, 32 * 9, smem, stream>>>(a);
+        } else if (minb == 208 || minb == 209) {
             // 8 / 9 warps per SM, each with a landing buffer, compact tables, interleaved tap spectrum
             const size_t smem = sizeof(c2) * ((size_t)(minb - 200) * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly);
             static thread_local bool configured[16] = {false};
