@@ -286,6 +286,29 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.peaks, self.peak_kind = measured_peaks()
 
+    def pcie_peak(self):
+        """Plain cudaMemcpy rates of this box with pinned memory (256 MiB, both directions at once on two streams): the
+        ceiling of any host-buffer path, reported next to e2e.  Measured once per process."""
+        if getattr(self, "_pcie", None) is None:
+            torch = self.torch
+            n = 256 << 20
+            h1, h2 = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+            d1, d2 = torch.empty(n, dtype=torch.uint8, device=self.dev), torch.empty(n, dtype=torch.uint8, device=self.dev)
+            s1, s2 = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s1):
+                    d1.copy_(h1, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h2.copy_(d2, non_blocking=True)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            self._pcie = n / best / 1e9
+        return self._pcie
+
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
@@ -479,6 +502,7 @@ def bench_stream(ctx: Ctx, name: str, steps: int, warmup: int, e2e: bool, cpu: b
         hb, db = int(h_in.numel() * h_in.element_size()), int(h_out.numel() * h_out.element_size())
         e2e_rec = {"value": world * n_host / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
                    "steps": e2e_steps, "h2d_gbs": hb / e2e_s / 1e9, "d2h_gbs": db / e2e_s / 1e9,
+                   "memcpy_peak_gbs_each_way": ctx.pcie_peak(),   # cudaMemcpy both directions at once, pinned: the box's ceiling
                    "sample": None if n_host == n_seg else f"first 2^{n_host.bit_length() - 1} samples of the segment"}
         del h_in, h_out
 

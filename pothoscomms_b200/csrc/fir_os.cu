@@ -160,24 +160,20 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
     }
 }
 
-#ifndef B200C_OS32_PARTIAL_TW
-#define B200C_OS32_PARTIAL_TW 0   // measured: no gain on B200 (headline 269 vs 272 Gsamples/s), kept for reference
-#endif
-constexpr bool kOs32PartialTwiddles = B200C_OS32_PARTIAL_TW != 0;
+constexpr bool kOs32PartialTwiddles = false;   // fir_os32_kernel: measured no gain on B200 (headline 269 vs 272 Gsamples/s); the resampler keeps them
 
 // v[slot(k)] *= W1024^(k t) (CONJ: conjugate) for k = 1..31 from TEN loaded twiddles instead of 31:
 // k = 4a + b, W^(kt) = W^(4a t) W^(b t).  The 21 extra complex multiplies cost FMA issue slots, the 21
 // saved loads were a fifth of the kernel's L1/shared data-pipe traffic, which is the busier pipe
 // (profiles/r01c_prof_os32_headline.txt).  One more rounding per twiddled element (~1e-7 relative).
-// COMPACT: `tw` holds only the ten rows read here (rows 1, 2, 3 in slots 0..2, rows 4 a in slots 2 + a)
-template <bool CONJ, bool SLOT_REV, bool COMPACT = false>
+template <bool CONJ, bool SLOT_REV>
 __device__ __forceinline__ void twiddle32(c2 (&v)[32], const c2 *__restrict__ tw, const int t)
 {
     c2 A[8], B[4];
 #pragma unroll
-    for (int a = 1; a < 8; a++) A[a] = tw[(COMPACT ? 2 + a : 4 * a) * 32 + t];
+    for (int a = 1; a < 8; a++) A[a] = tw[(4 * a) * 32 + t];
 #pragma unroll
-    for (int b = 1; b < 4; b++) B[b] = tw[(COMPACT ? b - 1 : b) * 32 + t];
+    for (int b = 1; b < 4; b++) B[b] = tw[b * 32 + t];
 #pragma unroll
     for (int k = 1; k < 32; k++) {
         const int a = k >> 2, b = k & 3, r = SLOT_REV ? rev32(k) : k;
@@ -403,21 +399,15 @@ constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
 // WARPS == 1: one warp per CTA, MINB CTAs per SM, tables read through L1.  WARPS > 1: one persistent CTA per SM
 // whose warps share ONE copy of the tables (tap spectrum 24 KB, step twiddles 12 KB + 8 KB) in shared memory.
 constexpr int kX32TabElems = 3072 + 1536 + 1024;
-// EARLY (WARPS > 1, PT): fewer warps, each with a landing buffer -- the bulk copy of the warp's NEXT block is issued as
-// soon as the current block sits in registers (fir_os32_kernel's step 6); what pays for the buffers is compact tables
-// (only the 10 + 18 twiddle rows the partial-twiddle form reads) and fewer tiles.  The tap spectrum is stored
-// interleaved, (H'[kk], H'[kk + 1536]) side by side, so one 128-bit load fetches both factors of a bin.
-constexpr int kX32TwRows = 10, kX32Tw3Rows = 18;
-constexpr int kX32TabElemsEarly = 3072 + kX32Tw3Rows * 32 + kX32TwRows * 32;
-constexpr int kX32Landing = 1032;
 // SPLIT: the 16 rows left for the second inverse round (rows 32..47 on 32 lanes) are transformed by lane PAIRS instead
 // of by lanes 0..15 alone: lane (tt, h) takes the inputs k1 = 2 j + h of row 32 + tt through a 16-point transform, the odd
 // half is twiddled, one shuffle exchange (xor 16) combines them -- w[m] = S0[m] + W^m S1[m] on h = 0, w[m + 16] = S0[m] -
 // W^m S1[m] on h = 1.  126 packed instructions on all lanes instead of 222 on half of them.
-template <int WARPS, int MINB, bool PT = false, bool EARLY = false, bool SPLIT = false>
+// (Round 2 also built 8- and 9-warp forms with a landing buffer per warp, compact twiddle tables and an interleaved tap
+// spectrum read with 128-bit loads: 3 % and 17 % SLOWER than this 12-warp form -- profiles/r02_osx_variants.txt -- removed.)
+template <int WARPS, int MINB, bool PT = false, bool SPLIT = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOsX32Args a)
 {
-    static_assert(!EARLY || (PT && WARPS > 1), "the landing-buffer form is the persistent partial-twiddle kernel");
     extern __shared__ __align__(16) c2 x32_smem[];
     __shared__ __align__(8) unsigned long long bars[WARPS];
     const int t = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -425,8 +415,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
     const c2 *__restrict__ tw3 = static_cast<const c2 *>(a.tw3);
     const c2 *__restrict__ hx = static_cast<const c2 *>(a.hx);
     c2 *F = x32_smem + wp * kX32SmemElems;
-    c2 *Lb = F;                                                  // where the bulk copy lands
-    if constexpr (EARLY) Lb = x32_smem + WARPS * kX32SmemElems + kX32TabElemsEarly + wp * kX32Landing;
+    c2 *const Lb = F;                                            // where the bulk copy lands: the exchange tile
     unsigned long long &bar = bars[wp];
     const c2 *__restrict__ in = static_cast<const c2 *>(a.in);
     c2 *__restrict__ out = static_cast<c2 *>(a.out);
@@ -451,25 +440,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
     if constexpr (WARPS > 1) {
         // tables staged while the first block is in flight
         c2 *tab = x32_smem + WARPS * kX32SmemElems;
-        if constexpr (EARLY) {
-            // interleaved tap spectrum: tab[2 (32 c + t) + {0, 1}] = (H'[32 c + t], H'[1536 + 32 c + t]), c < 48
-            for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) { tab[2 * i] = hx[i]; tab[2 * i + 1] = hx[1536 + i]; }
-            // step twiddles of the inverse: rows 0..16 and row 32 (slot 17)
-            for (int i = threadIdx.x; i < kX32Tw3Rows * 32; i += 32 * WARPS) tab[3072 + i] = tw3[i < 17 * 32 ? i : 32 * 32 + (i - 17 * 32)];
-            // forward twiddles: rows 1, 2, 3 (slots 0..2) and 4 a, a = 1..7 (slots 2 + a)
-            for (int i = threadIdx.x; i < kX32TwRows * 32; i += 32 * WARPS) {
-                const int slot = i >> 5, row = slot < 3 ? slot + 1 : 4 * (slot - 2);
-                tab[3072 + kX32Tw3Rows * 32 + i] = tw[row * 32 + (i & 31)];
-            }
-            __syncthreads();
-            hx = tab; tw3 = tab + 3072; tw = tab + 3072 + kX32Tw3Rows * 32;
-        } else {
-            for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
-            for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
-            for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
-            __syncthreads();
-            hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
-        }
+        for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
+        for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
+        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
+        __syncthreads();
+        hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
     }
     for (; blk < nblk; blk += bstep) {
         const long long P = a.p0 + blk * hop_in;
@@ -487,15 +462,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
                 v[rev32(n1)] = (g >= 0 && g < a.n_in) ? __ldcg(in + g) : 0ull;
             }
         }
-        if constexpr (EARLY) {
-            __syncwarp();                                    // the landing buffer is in registers: fetch the next block now
-            pending = bulk_src(blk + bstep, src);
-            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
-        }
         // forward 1024 = 32 x 32 (as fir_os32_kernel): thread t ends with X[t + 32 k2] in v[k2]
         dft32_dit<false>(v);
-        if constexpr (EARLY) twiddle32<false, false, true>(v, tw, t);   // the same from the compact table
-        else if constexpr (PT) twiddle32<false, false>(v, tw, t);   // ten loaded + 21 computed twiddles
+        if constexpr (PT) twiddle32<false, false>(v, tw, t);   // ten loaded + 21 computed twiddles
         else {
 #pragma unroll
             for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw[k1 * 32 + t]);
@@ -514,16 +483,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             const c2 xa = v[c], xb = v[c + 16];
-            c2 h0, g0, h1, g1, h2, g2;
-            if constexpr (EARLY) {
-                const ulonglong2 *hg = reinterpret_cast<const ulonglong2 *>(hx);
-                const ulonglong2 p0 = hg[32 * c + t], p1 = hg[32 * (c + 16) + t], p2 = hg[32 * (c + 32) + t];
-                h0 = p0.x; g0 = p0.y; h1 = p1.x; g1 = p1.y; h2 = p2.x; g2 = p2.y;
-            } else {
-                h0 = hx[32 * c + t]; g0 = hx[1536 + 32 * c + t];
-                h1 = hx[32 * (c + 16) + t]; g1 = hx[1536 + 32 * (c + 16) + t];
-                h2 = hx[32 * (c + 32) + t]; g2 = hx[1536 + 32 * (c + 32) + t];
-            }
+            const c2 h0 = hx[32 * c + t], g0 = hx[1536 + 32 * c + t];
+            const c2 h1 = hx[32 * (c + 16) + t], g1 = hx[1536 + 32 * (c + 16) + t];
+            const c2 h2 = hx[32 * (c + 32) + t], g2 = hx[1536 + 32 * (c + 32) + t];
             s[c % 3][c / 3] = cmul_acc(xb, g0, cmul_p<false>(xa, h0));
             s[(c + 16) % 3][(c + 16) / 3] = cmul_acc(xa, g1, cmul_p<false>(xb, h1));
             s[(c + 32) % 3][(c + 32) / 3] = cmul_acc(xb, g2, cmul_p<false>(xa, h2));
@@ -534,7 +496,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
         __syncwarp();
         // step twiddles exp(2 pi i t n2 / 1536), n2 = 16 v1 + v2: PT loads the 15 + 2 factors and multiplies
         c2 twb1 = 0, twb2 = 0;
-        if constexpr (PT) { twb1 = tw3[16 * 32 + t]; twb2 = tw3[(EARLY ? 17 : 32) * 32 + t]; }
+        if constexpr (PT) { twb1 = tw3[16 * 32 + t]; twb2 = tw3[32 * 32 + t]; }
 #pragma unroll
         for (int v2 = 0; v2 < 16; v2++) {
             const int r = rev16(v2);
@@ -582,11 +544,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
             c2 x[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) x[j] = F[(32 + tt) * kOs32Stride + 2 * j + h];
-            if constexpr (!EARLY) {
-                __syncwarp();                                // the tile is free: fetch the next block into it
-                pending = bulk_src(blk + bstep, src);
-                if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
-            }
+            __syncwarp();                                    // the tile is free: fetch the next block into it
+            pending = bulk_src(blk + bstep, src);
+            if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
             dft16_dif<true>(x);                              // S_h[m] in x[rev16(m)]
             c2 *const o2 = out + mbase + tt + 32 + 48 * 16 * h;   // w[48 (m + 16 h) + 32 + tt]
             const int d2 = tt - m0 + 32 + 48 * 16 * h;
@@ -605,11 +565,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
 #pragma unroll
             for (int k1 = 0; k1 < 32; k1++) v[rev32(k1)] = F[(32 + t) * kOs32Stride + k1];
         }
-        if constexpr (!EARLY) {
-            __syncwarp();                                    // the tile is free: fetch the next block into it
-            pending = bulk_src(blk + bstep, src);
-            if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
-        }
+        __syncwarp();                                        // the tile is free: fetch the next block into it
+        pending = bulk_src(blk + bstep, src);
+        if (pending && t == 0) bulk_load(F, src, kBulk * (unsigned)sizeof(c2), &bar);
         if (t < 16) {
             dft32_dit<true>(v);
             if (whole) {
@@ -1428,78 +1386,21 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hx = p.d_hx; a.tw = p.d_tw1k; a.tw3 = p.d_tw3;
         a.n_in = (long long)in_elems; a.n_out = (long long)nq * 3; a.p0 = p.p0; a.m0 = p.m0;
         const long long nblk = (a.n_out + (1536 - p.m0) - 1) / (1536 - p.m0);
-        // B200C_OSX_MINB: 8 / 10 / 12 one-warp CTAs per SM (tables through L1); 112 (default): one persistent 12-warp
-        // CTA per SM with the tables in shared memory
-        static const int minb = [] { const char *e = std::getenv("B200C_OSX_MINB"); return e ? std::atoi(e) : 112; }();
+        // One persistent 12-warp CTA per SM, tables in shared memory, partial twiddles, second inverse round by lane pairs.
+        // Measured alternatives (profiles/r02_osx_variants.txt): 12 one-warp CTAs per SM with tables through L1 (-11 %),
+        // all twiddles loaded (-2 %), 8 / 9 warps with landing buffers and compact tables (-3 % / -17 %: the kernel is
+        // FMA-pipe bound, fewer warps lose more than the earlier prefetch gains), lanes 0..15 alone in the second round (-1.5 %).
         const size_t tile = sizeof(c2) * kX32SmemElems;
-        // partial twiddles (10 + 17 loaded, the rest multiplied up): C3 207.8 -> 211.2 Gsamples/s; B200C_OSX_PT=0 loads all
-        static const bool pt = [] { const char *e = std::getenv("B200C_OSX_PT"); return !e || std::atoi(e) != 0; }();
-        if (minb == 312) {
-            // 12 warps, tables in shared memory, second inverse round by lane pairs
-            const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
-            static thread_local bool configured[16] = {false};
-            int dev = 0;
-            B200C_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured[dev] = true;
-            }
-            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
-            fir_os32x_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem, stream>>>(a);
-        } else if (minb == 308 || minb == 309) {
-            const int w = minb - 300;
-            const size_t smem = sizeof(c2) * ((size_t)w * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly);
-            static thread_local bool configured[16] = {false};
-            int dev = 0;
-            B200C_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<8, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(sizeof(c2) * (8 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<9, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(sizeof(c2) * (9 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
-                configured[dev] = true;
-            }
-            const int grid = (int)std::min<long long>((nblk + w - 1) / w, (long long)sm_count);
-            if (w == 8) fir_os32x_kernel<8, 1, true, true, true><<<grid, 32 * 8, smem, stream>>>(a);
-            else fir_os32x_kernel<9, 1, true, true, true><<<grid, 32 * 9, smem, stream>>>(a);
-        } else if (minb == 208 || minb == 209) {
-            // 8 / 9 warps per SM, each with a landing buffer, compact tables, interleaved tap spectrum
-            const size_t smem = sizeof(c2) * ((size_t)(minb - 200) * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly);
-            static thread_local bool configured[16] = {false};
-            int dev = 0;
-            B200C_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<8, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(sizeof(c2) * (8 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<9, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(sizeof(c2) * (9 * (kX32SmemElems + kX32Landing) + kX32TabElemsEarly))));
-                configured[dev] = true;
-            }
-            const int w = minb - 200;
-            const int grid = (int)std::min<long long>((nblk + w - 1) / w, (long long)sm_count);
-            if (w == 8) fir_os32x_kernel<8, 1, true, true><<<grid, 32 * 8, smem, stream>>>(a);
-            else fir_os32x_kernel<9, 1, true, true><<<grid, 32 * 9, smem, stream>>>(a);
-        } else if (minb >= 100) {
-            auto kern = pt ? fir_os32x_kernel<12, 1, true> : fir_os32x_kernel<12, 1, false>;
-            const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
-            static thread_local bool configured[16] = {false};
-            int dev = 0;
-            B200C_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured[dev] = true;
-            }
-            const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
-            kern<<<grid, 32 * 12, smem, stream>>>(a);
-        } else {
-            const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
-            switch (minb) {
-            case 8: fir_os32x_kernel<1, 8><<<grid, 32, tile, stream>>>(a); break;
-            case 10: fir_os32x_kernel<1, 10><<<grid, 32, tile, stream>>>(a); break;
-            default: fir_os32x_kernel<1, 12><<<grid, 32, tile, stream>>>(a); break;
-            }
+        const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
+        static thread_local bool configured[16] = {false};
+        int dev = 0;
+        B200C_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 16 && !configured[dev]) {
+            B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = true;
         }
+        const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
+        fir_os32x_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
@@ -1541,27 +1442,19 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = static_cast<const float *>(d_in); a.out = static_cast<float *>(d_out); a.hf = p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)nq; a.K = p.K;
         const long long npair = ((long long)nq + p.hop() - 1) / p.hop();
-        // one persistent 12-warp CTA per SM with the tables in shared memory (B200C_OS32R_CFG=112: 12 one-warp CTAs)
-        // 2012 (default): the same with a landing buffer per warp (the next pair is fetched a whole pair ahead)
-        static const int rcfg = [] { const char *e = std::getenv("B200C_OS32R_CFG"); return e ? std::atoi(e) : 2012; }();
+        // one persistent 12-warp CTA per SM, tables in shared memory, a landing buffer per warp (the next pair is fetched a
+        // whole pair ahead).  Round 1 measured the alternatives: 12 one-warp CTAs 656, no landing buffers 690, this 707 Gsamples/s.
         const size_t tile = sizeof(c2) * kOs32SmemElems;
-        if (rcfg >= 1000) {
-            const size_t smem = 12 * tile + sizeof(c2) * 2048, smem_early = smem + sizeof(c2) * 12 * kOs32Landing;
-            static thread_local bool configured[16] = {false};
-            int dev = 0;
-            B200C_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
-                configured[dev] = true;
-            }
-            const int grid = (int)std::min<long long>((npair + 11) / 12, (long long)sm_count);
-            if (rcfg >= 2000) fir_os32r_kernel<12, 1, true><<<grid, 32 * 12, smem_early, stream>>>(a);
-            else fir_os32r_kernel<12, 1, false><<<grid, 32 * 12, smem, stream>>>(a);
-        } else {
-            const int grid = (int)std::min<long long>(npair, (long long)sm_count * 12 * 4);
-            fir_os32r_kernel<1, 12><<<grid, 32, tile, stream>>>(a);
+        const size_t smem_early = 12 * tile + sizeof(c2) * 2048 + sizeof(c2) * 12 * kOs32Landing;
+        static thread_local bool configured[16] = {false};
+        int dev = 0;
+        B200C_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 16 && !configured[dev]) {
+            B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32r_kernel<12, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
+            configured[dev] = true;
         }
+        const int grid = (int)std::min<long long>((npair + 11) / 12, (long long)sm_count);
+        fir_os32r_kernel<12, 1, true><<<grid, 32 * 12, smem_early, stream>>>(a);
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
@@ -1573,47 +1466,30 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
         a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
         a.spread = 0;
-        static const int cfg = [] { const char *e = std::getenv("B200C_OS32_CFG"); return e ? std::atoi(e) : 2012; }();
-#define OS32_LAUNCH(W, MB)                                                                                        \
-    {                                                                                                             \
-        const int grid = (int)std::min<long long>((nblk + (W) - 1) / (W), (long long)sm_count * (MB) * 4);        \
-        fir_os32_kernel<W, MB><<<grid, 32 * (W), 0, stream>>>(a);                                                  \
-    }
-        // 1012 / 1112: one persistent 12-warp CTA per SM, tap spectrum + twiddles in shared memory (single stream only),
-        // all twiddles loaded / partial twiddles
-        if (cfg >= 1000 && nchan == 1) {
-            // 2012: the same with a landing buffer per warp (the next block is fetched a whole block ahead)
-            const size_t smem = sizeof(c2) * (12 * (size_t)kOs32SmemElems + 2048), smem_early = smem + sizeof(c2) * 12 * kOs32Landing;
+        if (nchan == 1) {
+            // single stream: one persistent 12-warp CTA per SM, tap spectrum + twiddles in shared memory, a landing buffer per
+            // warp (the next block is fetched a whole block ahead).  Round-1 steps, headline Gsamples/s: 12 one-warp CTAs 272,
+            // persistent + shared tables 288, + landing buffers 300; partial twiddles measured no gain and are gone.
+            const size_t smem_early = sizeof(c2) * (12 * (size_t)kOs32SmemElems + 2048 + 12 * (size_t)kOs32Landing);
             static thread_local bool configured[16] = {false};
             int dev = 0;
             B200C_CUDA_TRY(cudaGetDevice(&dev));
             if (dev < 16 && !configured[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32_kernel<12, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_early));
                 configured[dev] = true;
             }
             // fewer blocks than one wave of warps: one CTA per SM anyway, blocks dealt warp-major
             a.spread = nblk < 12LL * sm_count ? 1 : 0;
             const int grid = (int)std::min<long long>(a.spread ? nblk : (nblk + 11) / 12, (long long)sm_count);
-            if (cfg >= 2000) fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
-            else if (cfg >= 1100) fir_os32_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
-            else fir_os32_kernel<12, 1, true, false><<<grid, 32 * 12, smem, stream>>>(a);
+            fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
             B200C_CUDA_TRY(cudaGetLastError());
             return B200C_OK;
         }
-        switch (cfg) {   // (warps per CTA)(CTAs per SM)
-        case 42: OS32_LAUNCH(4, 2) break;
-        case 25: OS32_LAUNCH(2, 5) break;
-        case 26: OS32_LAUNCH(2, 6) break;
-        case 24: OS32_LAUNCH(2, 4) break;
-        case 43: OS32_LAUNCH(4, 3) break;
-        case 110: OS32_LAUNCH(1, 10) break;
-        case 114: OS32_LAUNCH(1, 14) break;
-        case 116: OS32_LAUNCH(1, 16) break;
-        default: OS32_LAUNCH(1, 12) break;
+        // filter bank (one spectrum per channel): one-warp CTAs, 12 per SM, tables through L1
+        {
+            const int grid = (int)std::min<long long>(nblk, (long long)sm_count * 12 * 4);
+            fir_os32_kernel<1, 12><<<grid, 32, 0, stream>>>(a);
         }
-#undef OS32_LAUNCH
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
@@ -1621,14 +1497,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
     a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
     a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
-    static const int minb = [] { const char *e = std::getenv("B200C_OS_MINB"); return e ? std::atoi(e) : 4; }();
-    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * minb * 4);
-    switch (minb) {
-    case 3: fir_os64_kernel<3><<<grid, 64, 0, stream>>>(a); break;
-    case 5: fir_os64_kernel<5><<<grid, 64, 0, stream>>>(a); break;
-    case 6: fir_os64_kernel<6><<<grid, 64, 0, stream>>>(a); break;
-    default: fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a); break;
-    }
+    // 4 CTAs of 64 threads per SM (252 registers); 3 / 5 / 6 per SM measured slower in round 1
+    const int grid = (int)std::min<long long>(nblk, (long long)sm_count * 4 * 4);
+    fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
     return B200C_OK;
 }

@@ -237,197 +237,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) fir_umma_kernel(const FirUmma
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ALLOC) : "memory");
 }
 
-// ------------------------------------------------------------------ warp-specialised variant ---
-// One persistent CTA per SM, roles connected by mbarrier pipelines so that the three phases of
-// consecutive tiles overlap (the single-role kernel above serialises them per CTA):
-//   warp 13      : bulk-copy issuer   raw[s]    <- global                 (raw_empty -> raw_full)
-//   warps 8..11  : stagers            planes[s] <- PRMT(raw[s])           (raw_full, planes_empty -> planes_full, raw_empty)
-//   warp 12      : MMA issuer         acc[s]    += planes[s] x B tiles    (planes_full, acc_empty -> planes_empty, acc_full)
-//   warps 0..7   : epilogue           out       <- recombine(acc[s])      (acc_full -> acc_empty)
-// Two stages of everything; the two accumulator stages fill tensor memory's 512 columns for the
-// complex x complex case, so exactly one CTA may live on an SM.
-constexpr int kWsEpiWarps = 8, kWsStageWarps = 4, kWsMaxRing = 8;
-constexpr int kWsThreads = 32 * (kWsEpiWarps + kWsStageWarps + 2);
-
-template <int DC, int TC, int NLT>
-__global__ void __launch_bounds__(kWsThreads, 1) fir_umma_ws_kernel(const FirUmmaArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_u[];
-    constexpr int NPL = DC * 2, NQ = TC * NLT, N = 16 * NQ, COLS = NPL * N;
-    constexpr int ALLOC = 2 * COLS <= 32 ? 32 : 2 * COLS <= 64 ? 64 : 2 * COLS <= 128 ? 128 : 2 * COLS <= 256 ? 256 : 512;
-    constexpr int ESZ = DC * 2, CH = 16 / NQ;
-    static_assert(2 * COLS <= 512, "two accumulator stages exceed tensor memory");
-    const int NB = a.NB, PL = a.PL;
-    unsigned char *btile = smem_u;
-    unsigned char *planes = btile + (size_t)NB * N * 32;             // [2][NPL * PL]
-    unsigned char *raw = planes + 2 * (size_t)NPL * PL;              // [R][NPL * PL]: enough bytes in flight to cover HBM latency
-    const int R = a.R;
-    __shared__ __align__(8) unsigned long long raw_full[kWsMaxRing], raw_empty[kWsMaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
-    __shared__ unsigned tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    for (int i = tid; i < NB * N * 2; i += kWsThreads)
-        reinterpret_cast<uint4 *>(btile)[i] = __ldg(static_cast<const uint4 *>(a.btile) + i);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (tid == 0) {
-        for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * kWsStageWarps); }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&planes_full[s], 32 * kWsStageWarps); mbar_init(&planes_empty[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * kWsEpiWarps);
-        }
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ALLOC) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem_base = tmem_base_s;
-    const long long first = blockIdx.x, step = gridDim.x;
-    const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;   // this CTA's tiles
-    const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
-    auto bulk_ok = [&](long long tile) { return al && tile * kUmmaTile + PL <= a.n_in; };
-    long long w0 = 0, w1 = 0;                      // cycles spent in this role's two barrier waits
-    const long long t_begin = clock64();
-
-    if (warp == kWsEpiWarps + kWsStageWarps + 1) {
-        // ================================================================ bulk-copy issuer
-        if (lane == 0)
-            for (int i = 0, r = 0, ph = 0; i < ntl; i++) {
-                const long long tile = first + (long long)i * step;
-                timed_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
-                if (bulk_ok(tile))
-                    bulk_load(raw + (size_t)r * NPL * PL, static_cast<const unsigned char *>(a.in) + (size_t)tile * kUmmaTile * ESZ,
-                              (unsigned)(NPL * PL), &raw_full[r]);
-                else
-                    mbar_arrive(&raw_full[r]);           // edge tile: the stagers read it with guarded loads
-                if (++r == R) { r = 0; ph ^= 1; }
-            }
-    } else if (warp == kWsEpiWarps + kWsStageWarps) {
-        // ====================================================================== MMA issuer
-        if (lane == 0) {
-            const unsigned btile_s = smem_u32(btile);
-            long long t_iss = 0, t_com = 0;
-            for (int i = 0; i < ntl; i++) {
-                const int s = i & 1;
-                const unsigned ph = (unsigned)(i >> 1) & 1;
-                timed_wait(&planes_full[s], ph, w0);
-                timed_wait(&acc_empty[s], ph ^ 1, w1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const long long t_issue = clock64();
-                const unsigned planes_s = smem_u32(planes + (size_t)s * NPL * PL);
-                for (int b = 0; b < NB; b++) {
-                    const unsigned long long bdesc = umma_smem_desc(btile_s + (unsigned)b * N * 32, 128, 256);
-#pragma unroll
-                    for (int p = 0; p < NPL; p++) {
-                        const unsigned long long adesc = umma_smem_desc(planes_s + (unsigned)p * PL + 32u * b, 16, 128);
-                        umma_i8(tmem_base + (unsigned)(s * COLS + p * N), adesc, bdesc, umma_idesc_i8((p & 1) != 0, N), b > 0);
-                    }
-                }
-                const long long t_commit = clock64();
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[s])) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[s])) : "memory");
-                t_iss += t_commit - t_issue;
-                t_com += clock64() - t_commit;
-            }
-            if (a.dbg) { a.dbg[(size_t)gridDim.x * 8 + blockIdx.x * 2] = t_iss; a.dbg[(size_t)gridDim.x * 8 + blockIdx.x * 2 + 1] = t_com; }
-        }
-    } else if (warp >= kWsEpiWarps) {
-        // ========================================================================= stagers
-        const int st = tid - 32 * kWsEpiWarps;
-        constexpr int NST = 32 * kWsStageWarps;
-        for (int i = 0, r = 0, rph = 0; i < ntl; i++) {
-            const int s = i & 1;
-            const unsigned ph = (unsigned)(i >> 1) & 1;
-            const long long tile = first + (long long)i * step, o0 = tile * kUmmaTile;
-            const bool landed = bulk_ok(tile);
-            timed_wait(&raw_full[r], (unsigned)rph, w0);
-            timed_wait(&planes_empty[s], ph ^ 1, w1);
-            unsigned char *pl = planes + (size_t)s * NPL * PL;
-            const unsigned char *rw = raw + (size_t)r * NPL * PL;
-            if constexpr (DC == 2) {
-                const unsigned *__restrict__ in32 = static_cast<const unsigned *>(a.in);
-                for (int q = st; q < PL / 4; q += NST) {
-                    const long long sm = o0 + 4LL * q;
-                    unsigned s0, s1, s2, s3;
-                    if (landed) {
-                        const uint4 v = reinterpret_cast<const uint4 *>(rw)[q];
-                        s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
-                    } else {
-                        s0 = sm < a.n_in ? __ldg(in32 + sm) : 0u;
-                        s1 = sm + 1 < a.n_in ? __ldg(in32 + sm + 1) : 0u;
-                        s2 = sm + 2 < a.n_in ? __ldg(in32 + sm + 2) : 0u;
-                        s3 = sm + 3 < a.n_in ? __ldg(in32 + sm + 3) : 0u;
-                    }
-                    const unsigned t01 = prmt_u(s0, s1, 0x5140), t23 = prmt_u(s2, s3, 0x5140);
-                    const unsigned u01 = prmt_u(s0, s1, 0x7362), u23 = prmt_u(s2, s3, 0x7362);
-                    unsigned *p = reinterpret_cast<unsigned *>(pl) + q;
-                    p[0] = prmt_u(t01, t23, 0x5410);
-                    p[PL / 4] = prmt_u(t01, t23, 0x7632);
-                    p[2 * (PL / 4)] = prmt_u(u01, u23, 0x5410);
-                    p[3 * (PL / 4)] = prmt_u(u01, u23, 0x7632);
-                }
-            } else {
-                const unsigned short *__restrict__ in16 = static_cast<const unsigned short *>(a.in);
-                for (int q = st; q < PL / 4; q += NST) {
-                    const long long sm = o0 + 4LL * q;
-                    unsigned w0, w1;
-                    if (landed) {
-                        const uint2 v = reinterpret_cast<const uint2 *>(rw)[q];
-                        w0 = v.x; w1 = v.y;
-                    } else {
-                        const unsigned x0 = sm < a.n_in ? __ldg(in16 + sm) : 0u, x1 = sm + 1 < a.n_in ? __ldg(in16 + sm + 1) : 0u;
-                        const unsigned x2 = sm + 2 < a.n_in ? __ldg(in16 + sm + 2) : 0u, x3 = sm + 3 < a.n_in ? __ldg(in16 + sm + 3) : 0u;
-                        w0 = x0 | (x1 << 16); w1 = x2 | (x3 << 16);
-                    }
-                    unsigned *p = reinterpret_cast<unsigned *>(pl) + q;
-                    p[0] = prmt_u(w0, w1, 0x6420);
-                    p[PL / 4] = prmt_u(w0, w1, 0x7531);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes -> visible to the tensor core
-            mbar_arrive(&planes_full[s]);
-            mbar_arrive(&raw_empty[r]);
-            if (++r == R) { r = 0; rph ^= 1; }
-        }
-    } else {
-        // ======================================================================== epilogue
-        // warp w reads TMEM lanes 32 (w % 4) .. +31 (rows m) and the output columns n of its half
-        const int m = 32 * (warp & 3) + lane, half = warp >> 2;
-        const unsigned lane_addr = tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
-        for (int i = 0; i < ntl; i++) {
-            const int s = i & 1;
-            const unsigned ph = (unsigned)(i >> 1) & 1;
-            const long long tile = first + (long long)i * step, orow = tile * kUmmaTile + 16LL * m;
-            timed_wait(&acc_full[s], ph, w0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c = 0; c < 8 / CH; c++) {
-                const int n0 = 8 * half + CH * c;
-                unsigned v[NPL][CH * NQ];
-                load_acc<NPL, NQ, CH>(lane_addr + (unsigned)(s * COLS), N, n0, v);
-                if (c == 8 / CH - 1) {                 // this thread is done with the accumulator stage
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[s]);
-                }
-                finish_chunk<DC, TC, NLT, CH>(v, orow + n0, a);
-            }
-        }
-    }
-    if (a.dbg && lane == 0) {
-        // [0] total, [1] tiles, issuer: [2] raw_empty; MMA: [3] planes_full [4] acc_empty; stager: [5] raw_full [6] planes_empty; epilogue: [7] acc_full
-        long long *d = a.dbg + (size_t)blockIdx.x * 8;
-        if (warp == 0) { d[0] = clock64() - t_begin; d[1] = ntl; d[7] = w0; }
-        if (warp == kWsEpiWarps) { d[5] = w0; d[6] = w1; }
-        if (warp == kWsEpiWarps + kWsStageWarps) { d[3] = w0; d[4] = w1; }
-        if (warp == kWsEpiWarps + kWsStageWarps + 1) d[2] = w0;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ALLOC) : "memory");
-}
+// (A warp-specialised form of this kernel -- bulk-copy issuer / stagers / MMA issuer / epilogue on mbarrier pipelines --
+// was the stepping stone to fir_umma32_kernel in round 1; it never beat the 32-outputs-per-row kernel that took over its
+// structure and was removed in round 2.  This single-role kernel stays for filters whose tables exceed what
+// fir_umma32_kernel keeps in shared memory: complex int16 from ~300 to ~1000 taps, 2.8x the mma.sync kernel there,
+// profiles/r02_sweep_dispatch.jsonl.)
 
 // ------------------------------------------------------------------------------- host ---
 static int8_t umma_digit(int32_t q, int l)
@@ -485,58 +299,22 @@ void fir_umma_destroy(FirUmmaPlan &p)
 template <int DC, int TC, int NLT>
 static int launch_umma(const FirUmmaArgs &a, size_t smem, int sm_count, cudaStream_t stream)
 {
-    static const int variant = [] { const char *e = std::getenv("B200C_UMMA_V"); return e ? std::atoi(e) : 1; }();   // 1: one role, 2 CTAs/SM; 2: warp-specialised
     int dev = 0;
     B200C_CUDA_TRY(cudaGetDevice(&dev));
     // Tensor memory holds 512 columns per SM: the CTAs resident on one SM must not ask for more, or
     // tcgen05.alloc would wait forever.  Shared memory is padded so that at most `per_sm` CTAs fit.
-    if (variant == 1) {
-        auto kern = fir_umma_kernel<DC, TC, NLT>;
-        static thread_local bool configured[16] = {false};
-        if (dev < 16 && !configured[dev]) {
-            B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-            configured[dev] = true;
-        }
-        constexpr int COLS = DC * 2 * 16 * TC * NLT;
-        constexpr int ALLOC = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
-        const int per_sm = std::min(512 / ALLOC, 4);
-        smem = std::max(smem, (size_t)(227 * 1024) / (per_sm + 1) + 1024);   // more than a (per_sm + 1)-th of the SM
-        const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count * per_sm);
-        kern<<<grid, kUmmaThreads, smem, stream>>>(a);
-    } else {
-        auto kern = fir_umma_ws_kernel<DC, TC, NLT>;
-        static thread_local bool configured[16] = {false};
-        if (dev < 16 && !configured[dev]) {
-            B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured[dev] = true;
-        }
-        // B tiles + two stages of planes + a landing ring as deep as fits (<= 8: ~10 MB in flight over
-        // the chip); padded past half an SM: one CTA per SM
-        static const int ring = [] { const char *e = std::getenv("B200C_UMMA_RING"); return e ? std::atoi(e) : kWsMaxRing; }();
-        const size_t fixed = (size_t)a.NB * 16 * TC * NLT * 32 + 2 * ((size_t)DC * 2 * a.PL) + 128, one = (size_t)DC * 2 * a.PL;
-        FirUmmaArgs b = a;
-        b.R = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, std::min(ring, kWsMaxRing)), (190 * 1024 - fixed) / one));
-        const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
-        static const bool dbg = std::getenv("B200C_UMMA_DBG") != nullptr;
-        if (dbg) {   // diagnostic run: per-role barrier wait cycles, averaged over the CTAs (synchronous)
-            B200C_CUDA_TRY(cudaMalloc(&b.dbg, (size_t)grid * 10 * sizeof(long long)));
-            B200C_CUDA_TRY(cudaMemset(b.dbg, 0, (size_t)grid * 10 * sizeof(long long)));
-        }
-        kern<<<grid, kWsThreads, std::max<size_t>(fixed + b.R * one, 116 * 1024), stream>>>(b);
-        if (dbg) {
-            std::vector<long long> h((size_t)grid * 10);
-            B200C_CUDA_TRY(cudaStreamSynchronize(stream));
-            B200C_CUDA_TRY(cudaMemcpy(h.data(), b.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            cudaFree(b.dbg);
-            double s8[8] = {0};
-            for (int g = 0; g < grid; g++) for (int k = 0; k < 8; k++) s8[k] += (double)h[(size_t)g * 8 + k] / grid;
-            double iss = 0, com = 0;
-            for (int g = 0; g < grid; g++) { iss += (double)h[(size_t)grid * 8 + 2 * g] / grid; com += (double)h[(size_t)grid * 8 + 2 * g + 1] / grid; }
-            std::fprintf(stderr, "umma_ws: mma issue loop %.0f commit %.0f cycles/tile\n", iss / s8[1], com / s8[1]);
-            std::fprintf(stderr, "umma_ws: cycles/tile %.0f | issuer wait raw_empty %.0f | mma wait planes_full %.0f acc_empty %.0f | stager wait raw_full %.0f planes_empty %.0f | epilogue wait acc_full %.0f (tiles/CTA %.1f, R %d)\n",
-                         s8[0] / s8[1], s8[2] / s8[1], s8[3] / s8[1], s8[4] / s8[1], s8[5] / s8[1], s8[6] / s8[1], s8[7] / s8[1], s8[1], b.R);
-        }
+    auto kern = fir_umma_kernel<DC, TC, NLT>;
+    static thread_local bool configured[16] = {false};
+    if (dev < 16 && !configured[dev]) {
+        B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        configured[dev] = true;
     }
+    constexpr int COLS = DC * 2 * 16 * TC * NLT;
+    constexpr int ALLOC = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+    const int per_sm = std::min(512 / ALLOC, 4);
+    smem = std::max(smem, (size_t)(227 * 1024) / (per_sm + 1) + 1024);   // more than a (per_sm + 1)-th of the SM
+    const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count * per_sm);
+    kern<<<grid, kUmmaThreads, smem, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
     return B200C_OK;
 }
