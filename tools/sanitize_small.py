@@ -48,17 +48,37 @@ fir("complex_float32", "REAL", 255, 4, 3, 30001)
 fir("float32", "REAL", 64, 1, 1, 30001)
 fir("float32", "REAL", 600, 1, 1, 30001)
 fir("float32", "REAL", 101, 2, 1, 30001)
-# the same kernels in their one-warp-CTA forms, and the grouped polyphase kernel the spectral resampler replaced
-for var, val in (("B200C_OS32_CFG", "112"), ("B200C_OS32_CFG", "1012"), ("B200C_OS32R_CFG", "112"), ("B200C_OSX_MINB", "12"), ("B200C_OSX", "0")):
-    print("spawn", var, val)   # these knobs are read once per process: one child process per setting
-    import subprocess
-    child = ("import os, sys; sys.path.insert(0, %r); os.environ[%r] = %r; import numpy as np, torch; from pothoscomms_b200 import FirFilter; "
-             "f = FirFilter('complex_float32', 'REAL'); f.set_taps(np.hanning(255) / 40); f.set_rates(2, 3); "
-             "y, c, p = f.run(torch.randn((30001, 2), device='cuda')); torch.cuda.synchronize(); print(f.kernel, c, p); "
-             "g = FirFilter('complex_float32', 'COMPLEX'); g.set_taps(np.hanning(256) / 40); y, c, p = g.run(torch.randn((30001, 2), device='cuda')); "
-             "h = FirFilter('float32', 'REAL'); h.set_taps(np.hanning(64) / 10); y, c, p = h.run(torch.randn((30001, 1), device='cuda')); "
-             "torch.cuda.synchronize(); print(g.kernel, h.kernel)") % (ROOT, var, val)
-    subprocess.run([sys.executable, "-c", child], check=True)
+fir("complex_float32", "COMPLEX", 256, 1, 1, 700)       # a launch smaller than one wave of warps (warp-major spread)
+fir("complex_float32", "REAL", 5, 1, 1, 30001)           # <= 8 taps: the direct kernel
+fir("complex_int8", "COMPLEX", 21, 1, 2, 2000)           # the round-1 R = 7 / R = 5 mismatch case
+fir("complex_float32", "REAL", 64, 3, 1, 30001)          # grouped polyphase kernel
+fir("complex_float32", "REAL", 128, 1, 8, 30001)         # general kernel, wide interpolation
+# the grouped polyphase kernel the spectral resampler replaced (knob read once per process: a child process)
+import subprocess  # noqa: E402
+child = ("import os, sys; sys.path.insert(0, %r); os.environ['B200C_OSX'] = '0'; import numpy as np, torch; from pothoscomms_b200 import FirFilter; "
+         "f = FirFilter('complex_float32', 'REAL'); f.set_taps(np.hanning(255) / 40); f.set_rates(2, 3); "
+         "y, c, p = f.run(torch.randn((30001, 2), device='cuda')); torch.cuda.synchronize(); print(f.kernel, c, p)") % ROOT
+subprocess.run([sys.executable, "-c", child], check=True)
+# filter bank: one launch over (channel, block) with the 4096-point and the 1024-point kernels
+from pothoscomms_b200 import FirFilterBank  # noqa: E402
+for ntaps in (1024, 100):
+    bank = FirFilterBank("complex_float32", "COMPLEX", 5)
+    for c in range(5):
+        bank.set_taps(c, (rng.standard_normal(ntaps) + 1j * rng.standard_normal(ntaps)) / ntaps)
+    xb = torch.randn((5, ntaps - 1 + 20000, 2), device="cuda")
+    ob = torch.empty((5, 20000, 2), device="cuda")
+    print("bank", ntaps, bank.run(xb, ob))
+# the halo copy kernel (same device: the peer-load path without a second GPU) and the int16 4096-point FFT (lazy wrap)
+import ctypes  # noqa: E402
+from pothoscomms_b200 import _abi  # noqa: E402
+src, dst = torch.arange(2040, device="cuda", dtype=torch.uint8), torch.zeros(2040, device="cuda", dtype=torch.uint8)
+_abi.check(_abi.lib().b200c_halo_exchange(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()), 2040, 0, None))
+torch.cuda.synchronize()
+assert torch.equal(src, dst)
+xq = (torch.randn((3 * 4096, 2), device="cuda") * 8000).to(torch.int16)
+Fft("complex_int16", 4096, False).run(xq)
+Fft("complex_int16", 4096, True).run(xq)
+Fft("complex_int16", 1000, False).run(xq)
 t = (torch.randn((4096, 2), device="cuda")).float()
 print(handles.table_source("complex_float32", t, 12345, 123, 100003).shape, handles.table_source("complex_float32", t, 5, 1, 7).shape)
 x = (torch.randn((4 * 4096, 2), device="cuda")).float()
