@@ -1,9 +1,11 @@
 // Minimal stand-in for the subset of <Pothos/Framework.hpp> (PothosCore >= 0.6) that the
 // reference's FIR and FFT blocks touch (SURVEY.md section 8b lists it with file:line).
-// PothosCore is not available in this build environment; this header exists ONLY so that
-// FIRFilter.cpp / FFT.cpp in this directory compile and can be driven from tests.  With a
-// real PothosCore on the include path this directory is simply left out (-I order) and the
-// same block sources build against the real framework.
+// PothosCore is not available in this build environment; this header exists so that the block
+// sources in this directory -- and, for the oracle, the REFERENCE's own filter/FIRFilter.cpp
+// (oracle/Makefile ref_fir) -- compile and can be driven from tests.  The blocks use only calls the
+// reference blocks use; the BufferManager interface below (pop / push by byte count, readable window)
+// is this shim's own, so blocks/DeviceBuffers.hpp needs its glue rewritten against PothosCore's
+// ManagedBuffer / SharedBuffer signatures before it loads into a real Pothos process.
 #pragma once
 
 #include <algorithm>

@@ -67,9 +67,12 @@ class FirFilter:
         _abi.check(_abi.lib().b200c_fir_create(ctypes.byref(self._h), self.dtype, int(self.complex_taps), device))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            _abi.lib().b200c_fir_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                _abi.lib().b200c_fir_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except (TypeError, AttributeError):   # interpreter shutdown: module globals are already gone
+            pass
 
     __del__ = close
 
@@ -156,9 +159,12 @@ class FirFilterBank:
         _abi.check(_abi.lib().b200c_fir_bank_create(ctypes.byref(self._h), self.dtype, int(self.complex_taps), self.nchan, device))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            _abi.lib().b200c_fir_bank_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                _abi.lib().b200c_fir_bank_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except (TypeError, AttributeError):
+            pass
 
     __del__ = close
 
@@ -204,9 +210,12 @@ class Fft:
         _abi.check(_abi.lib().b200c_fft_create(ctypes.byref(self._h), self.dtype, self.num_bins, int(self.inverse), device))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            _abi.lib().b200c_fft_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                _abi.lib().b200c_fft_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except (TypeError, AttributeError):
+            pass
 
     __del__ = close
 
@@ -241,9 +250,12 @@ class DeviceRing:
         self.bytes = _abi.lib().b200c_ring_bytes(self._h)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            _abi.lib().b200c_ring_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                _abi.lib().b200c_ring_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except (TypeError, AttributeError):
+            pass
 
     __del__ = close
 
