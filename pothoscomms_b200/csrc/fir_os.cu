@@ -30,6 +30,7 @@ struct FirOs64Args {
     const void *hf;     // [nchan][4096] spectrum of the taps / 4096, natural order
     const void *twa;    // [8][64]  W4096^(8*a*t)
     const void *twb;    // [8][64]  W4096^(b*t)
+    const void *twf;    // [64][64] W4096^(j*t): the whole step-twiddle table (fir_os64p_kernel stages it in shared memory)
     long long n_in;     // valid input elements per channel (beyond: zeros -> burst zero tail)
     long long n_out;    // outputs to produce per channel
     long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
@@ -142,6 +143,111 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
         if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), &bar);
         dft64_dif<true>(v);
         // circular result c[i], i = 64 n1 + t; the alias-free part i >= K-1 is y[base + i - (K-1)]
+        c2 *o = out + (base - Km1);
+        if (base + hop <= a.n_out) {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const int i = 64 * n1 + t;
+                if (i >= Km1) __stcg(o + i, v[rev64(n1)]);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const int i = 64 * n1 + t;
+                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev64(n1)]);
+            }
+        }
+        ch = nch; blk = nblkpos;
+    }
+}
+
+// ------------------------------------------------- 4096-point variant, persistent form ---
+// The same 64 x 64 algorithm as fir_os64_kernel with the four transform groups of an SM gathered in ONE persistent
+// 256-thread CTA (group = 2 warps, synchronised on its own named barrier) so that they can share one copy of the
+// WHOLE step-twiddle table W4096^(j t) in shared memory (32 KB): a step twiddle is then 63 LDS + 63 complex
+// multiplies instead of 14 global loads + 112 multiplies (two factors per element) -- 7 % fewer FMA-pipe
+// instructions in a kernel ncu shows bound by that pipe (profiles/r01c_prof_os64_c5.txt: 60 % busy, 8 warps).
+constexpr int kOs64Groups = 4;
+__global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const FirOs64Args a)
+{
+    extern __shared__ __align__(16) c2 os64p_dyn[];            // [4][kOs64SmemElems] tiles | [4096] twiddles
+    __shared__ __align__(8) unsigned long long bars[kOs64Groups];
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+    c2 *F = os64p_dyn + g * kOs64SmemElems;
+    c2 *TW = os64p_dyn + kOs64Groups * kOs64SmemElems;
+    unsigned long long *bar = &bars[g];
+    auto gsync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); };
+    const int Km1 = a.K - 1;
+    const int hop = 4096 - Km1;
+    const long long nblk = (a.n_out + hop - 1) / hop;
+    const long long tstep = (long long)gridDim.x * kOs64Groups, dch = tstep / nblk, dblk = tstep - dch * nblk;
+    const long long task0 = (long long)blockIdx.x * kOs64Groups + g;
+    long long ch = task0 / nblk, blk = task0 - ch * nblk;
+    auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
+        if (ch >= a.nchan) return false;
+        const long long base = blk * hop;
+        const c2 *in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
+        src = in + (base - mis);
+        return base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
+    };
+    if (t == 0) mbar_init(bar, 1);
+    gsync();
+    const c2 *src = nullptr;
+    bool pending = bulk_src(ch, blk, src);
+    if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
+    unsigned parity = 0;
+    {   // the table is staged while the first blocks are in flight
+        const c2 *__restrict__ twf = static_cast<const c2 *>(a.twf);
+        for (int i = threadIdx.x; i < 4096; i += 64 * kOs64Groups) TW[i] = twf[i];
+        __syncthreads();
+    }
+    while (ch < a.nchan) {
+        const long long base = blk * hop;
+        long long nch = ch + dch, nblkpos = blk + dblk;      // this group's next task
+        if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
+        const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
+        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 4096;
+        c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
+        c2 v[64];
+        if (pending) {
+            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) v[rev64(n1)] = F[mis + 64 * n1 + t];
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 64; n1++) {
+                const long long gi = base + 64 * n1 + t;
+                v[rev64(n1)] = gi < a.n_in ? __ldcg(in + gi) : 0ull;
+            }
+        }
+        dft64_dit<false>(v);                                 // v[k1] = Y[n2 = t][k1]
+#pragma unroll
+        for (int k1 = 1; k1 < 64; k1++) v[k1] = cmul_p<false>(v[k1], TW[k1 * 64 + t]);   // * W4096^(n2 k1)
+        gsync();                                             // every thread of the group has taken its input out of F
+#pragma unroll
+        for (int k1 = 0; k1 < 64; k1++) F[k1 * kOs64Stride + t] = v[k1];
+        gsync();
+#pragma unroll
+        for (int n2 = 0; n2 < 64; n2++) v[rev64(n2)] = F[t * kOs64Stride + n2];
+        dft64_dit<false>(v);                                 // v[k2] = X[k1 + 64 k2]
+#pragma unroll
+        for (int k2 = 0; k2 < 64; k2++) v[k2] = cmul_p<false>(v[k2], hf[64 * k2 + t]);
+        dft64_dif<true>(v);
+#pragma unroll
+        for (int n2 = 1; n2 < 64; n2++) v[rev64(n2)] = cmul_p<true>(v[rev64(n2)], TW[n2 * 64 + t]);   // * conj W4096^(n2 k1)
+        gsync();                                             // step-2 readers are done
+#pragma unroll
+        for (int n2 = 0; n2 < 64; n2++) F[t * kOs64Stride + n2] = v[rev64(n2)];
+        gsync();
+#pragma unroll
+        for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
+        gsync();                                             // F is free: fetch the next block into it
+        pending = bulk_src(nch, nblkpos, src);
+        if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
+        dft64_dif<true>(v);
         c2 *o = out + (base - Km1);
         if (base + hop <= a.n_out) {
 #pragma unroll
@@ -1249,6 +1355,8 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
                 if ((rc = upload(&p.d_twa, tb))) return rc;
                 unit_root_table(tb, 4096, 8, 64, 1);
                 if ((rc = upload(&p.d_twb, tb))) return rc;
+                unit_root_table(tb, 4096, 64, 64, 1);          // the whole table, for the persistent form
+                if ((rc = upload(&p.d_twf, tb))) return rc;
             }
             taps_spectrum(hf, 4096, taps, ntaps, complex_taps);
             if ((rc = upload(&p.d_hf, hf))) return rc;
@@ -1308,7 +1416,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
 
 void fir_os_destroy(FirOsPlan &p)
 {
-    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_hf1k, &p.d_tw1k, &p.d_H, &p.d_hx, &p.d_tw3}) {
+    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_twf, &p.d_hf1k, &p.d_tw1k, &p.d_H, &p.d_hx, &p.d_tw3}) {
         if (*d) cudaFree(*d);
         *d = nullptr;
     }
@@ -1494,9 +1602,24 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         return B200C_OK;
     }
     FirOs64Args a;
-    a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb;
+    a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb; a.twf = p.d_twf;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
     a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
+    static const bool persistent = [] { const char *e = std::getenv("B200C_OS64P"); return e && std::atoi(e) != 0; }();
+    if (persistent && nblk >= 4LL * sm_count) {
+        // one persistent 256-thread CTA per SM: four transform groups sharing the whole step-twiddle table in shared memory
+        const size_t smem = sizeof(c2) * ((size_t)kOs64Groups * kOs64SmemElems + 4096);
+        static thread_local bool configured[16] = {false};
+        int dev = 0;
+        B200C_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 16 && !configured[dev]) {
+            B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os64p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev] = true;
+        }
+        fir_os64p_kernel<<<sm_count, 64 * kOs64Groups, smem, stream>>>(a);
+        B200C_CUDA_TRY(cudaGetLastError());
+        return B200C_OK;
+    }
     // 4 CTAs of 64 threads per SM (252 registers); 3 / 5 / 6 per SM measured slower in round 1
     const int grid = (int)std::min<long long>(nblk, (long long)sm_count * 4 * 4);
     fir_os64_kernel<4><<<grid, 64, 0, stream>>>(a);
