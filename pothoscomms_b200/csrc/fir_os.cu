@@ -164,106 +164,119 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
 
 // ------------------------------------------------- 4096-point variant, persistent form ---
 // The same 64 x 64 algorithm as fir_os64_kernel with the four transform groups of an SM gathered in ONE persistent
-// 256-thread CTA (group = 2 warps, synchronised on its own named barrier) so that they can share one copy of the
-// WHOLE step-twiddle table W4096^(j t) in shared memory (32 KB): a step twiddle is then 63 LDS + 63 complex
-// multiplies instead of 14 global loads + 112 multiplies (two factors per element) -- 7 % fewer FMA-pipe
-// instructions in a kernel ncu shows bound by that pipe (profiles/r01c_prof_os64_c5.txt: 60 % busy, 8 warps).
+// 256-thread CTA (group = 2 warps, synchronised on its own named barrier) that keeps, in shared memory, one copy of
+//   * the WHOLE step-twiddle table W4096^(j t) (32 KB): a step twiddle is 63 LDS + 63 complex multiplies instead of
+//     14 global loads + 112 multiplies (two factors per element), 7 % fewer FMA-pipe instructions;
+//   * the tap spectrum of the channel the CTA is working on (32 KB): in a filter bank every CTA takes whole channels
+//     (channel = blockIdx.x, + gridDim.x, ...; its four groups share the channel's blocks), so the spectrum is staged
+//     once per channel and the 64 loads per thread and block become LDS -- ncu had the global loads as the
+//     long_scoreboard / lg_throttle stalls of the one-transform-per-CTA kernel (profiles/r02j_prof_os64p_c5.txt).
+// A single stream (nchan == 1) deals its blocks over all CTAs and stages the one spectrum once.
 constexpr int kOs64Groups = 4;
 __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const FirOs64Args a)
 {
-    extern __shared__ __align__(16) c2 os64p_dyn[];            // [4][kOs64SmemElems] tiles | [4096] twiddles
+    extern __shared__ __align__(16) c2 os64p_dyn[];            // [4][kOs64SmemElems] tiles | [4096] twiddles | [4096] tap spectrum
     __shared__ __align__(8) unsigned long long bars[kOs64Groups];
     const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
     c2 *F = os64p_dyn + g * kOs64SmemElems;
     c2 *TW = os64p_dyn + kOs64Groups * kOs64SmemElems;
+    c2 *HF = TW + 4096;
     unsigned long long *bar = &bars[g];
     auto gsync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); };
     const int Km1 = a.K - 1;
     const int hop = 4096 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
-    const long long tstep = (long long)gridDim.x * kOs64Groups, dch = tstep / nblk, dblk = tstep - dch * nblk;
-    const long long task0 = (long long)blockIdx.x * kOs64Groups + g;
-    long long ch = task0 / nblk, blk = task0 - ch * nblk;
+    const bool per_cta = a.nchan > 1;                          // host: nchan == 1 or nchan >= gridDim.x
+    const long long first = per_cta ? g : (long long)blockIdx.x * kOs64Groups + g;
+    const long long bstep = per_cta ? kOs64Groups : (long long)gridDim.x * kOs64Groups;
+    const long long chstep = per_cta ? gridDim.x : a.nchan;   // nchan == 1: the channel loop runs once
     auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
-        if (ch >= a.nchan) return false;
+        if (ch >= a.nchan || blk >= nblk) return false;
         const long long base = blk * hop;
         const c2 *in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
         const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
         src = in + (base - mis);
         return base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
     };
+    long long ch = per_cta ? blockIdx.x : 0;
     if (t == 0) mbar_init(bar, 1);
     gsync();
     const c2 *src = nullptr;
-    bool pending = bulk_src(ch, blk, src);
+    bool pending = bulk_src(ch, first, src);
     if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
-    {   // the table is staged while the first blocks are in flight
+    {   // the twiddle table is staged while the first blocks are in flight
         const c2 *__restrict__ twf = static_cast<const c2 *>(a.twf);
         for (int i = threadIdx.x; i < 4096; i += 64 * kOs64Groups) TW[i] = twf[i];
-        __syncthreads();
     }
-    while (ch < a.nchan) {
-        const long long base = blk * hop;
-        long long nch = ch + dch, nblkpos = blk + dblk;      // this group's next task
-        if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
+    for (; ch < a.nchan; ch += chstep) {
+        {   // this channel's tap spectrum (the previous channel's readers are past the barrier that ends the loop body)
+            const c2 *__restrict__ hfg = static_cast<const c2 *>(a.hf) + ch * 4096;
+            for (int i = threadIdx.x; i < 4096; i += 64 * kOs64Groups) HF[i] = __ldg(hfg + i);
+            __syncthreads();
+        }
         const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
-        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 4096;
         c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
-        c2 v[64];
-        if (pending) {
-            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
-            mbar_wait(bar, parity);
-            parity ^= 1;
+        for (long long blk = first; blk < nblk; blk += bstep) {
+            const long long base = blk * hop;
+            c2 v[64];
+            if (pending) {
+                const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
+                mbar_wait(bar, parity);
+                parity ^= 1;
 #pragma unroll
-            for (int n1 = 0; n1 < 64; n1++) v[rev64(n1)] = F[mis + 64 * n1 + t];
-        } else {
+                for (int n1 = 0; n1 < 64; n1++) v[rev64(n1)] = F[mis + 64 * n1 + t];
+            } else {
 #pragma unroll
-            for (int n1 = 0; n1 < 64; n1++) {
-                const long long gi = base + 64 * n1 + t;
-                v[rev64(n1)] = gi < a.n_in ? __ldcg(in + gi) : 0ull;
+                for (int n1 = 0; n1 < 64; n1++) {
+                    const long long gi = base + 64 * n1 + t;
+                    v[rev64(n1)] = gi < a.n_in ? __ldcg(in + gi) : 0ull;
+                }
+            }
+            dft64_dit<false>(v);                             // v[k1] = Y[n2 = t][k1]
+#pragma unroll
+            for (int k1 = 1; k1 < 64; k1++) v[k1] = cmul_p<false>(v[k1], TW[k1 * 64 + t]);   // * W4096^(n2 k1)
+            gsync();                                         // every thread of the group has taken its input out of F
+#pragma unroll
+            for (int k1 = 0; k1 < 64; k1++) F[k1 * kOs64Stride + t] = v[k1];
+            gsync();
+#pragma unroll
+            for (int n2 = 0; n2 < 64; n2++) v[rev64(n2)] = F[t * kOs64Stride + n2];
+            dft64_dit<false>(v);                             // v[k2] = X[k1 + 64 k2]
+#pragma unroll
+            for (int k2 = 0; k2 < 64; k2++) v[k2] = cmul_p<false>(v[k2], HF[64 * k2 + t]);
+            dft64_dif<true>(v);
+#pragma unroll
+            for (int n2 = 1; n2 < 64; n2++) v[rev64(n2)] = cmul_p<true>(v[rev64(n2)], TW[n2 * 64 + t]);   // * conj W4096^(n2 k1)
+            gsync();                                         // step-2 readers are done
+#pragma unroll
+            for (int n2 = 0; n2 < 64; n2++) F[t * kOs64Stride + n2] = v[rev64(n2)];
+            gsync();
+#pragma unroll
+            for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
+            gsync();                                         // F is free: fetch the group's next block into it
+            {
+                const bool last = blk + bstep >= nblk;       // next: the same channel, or the CTA's next channel
+                pending = bulk_src(last ? ch + chstep : ch, last ? first : blk + bstep, src);
+                if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
+            }
+            dft64_dif<true>(v);
+            c2 *o = out + (base - Km1);
+            if (base + hop <= a.n_out) {
+#pragma unroll
+                for (int n1 = 0; n1 < 64; n1++) {
+                    const int i = 64 * n1 + t;
+                    if (i >= Km1) __stcg(o + i, v[rev64(n1)]);
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 64; n1++) {
+                    const int i = 64 * n1 + t;
+                    if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev64(n1)]);
+                }
             }
         }
-        dft64_dit<false>(v);                                 // v[k1] = Y[n2 = t][k1]
-#pragma unroll
-        for (int k1 = 1; k1 < 64; k1++) v[k1] = cmul_p<false>(v[k1], TW[k1 * 64 + t]);   // * W4096^(n2 k1)
-        gsync();                                             // every thread of the group has taken its input out of F
-#pragma unroll
-        for (int k1 = 0; k1 < 64; k1++) F[k1 * kOs64Stride + t] = v[k1];
-        gsync();
-#pragma unroll
-        for (int n2 = 0; n2 < 64; n2++) v[rev64(n2)] = F[t * kOs64Stride + n2];
-        dft64_dit<false>(v);                                 // v[k2] = X[k1 + 64 k2]
-#pragma unroll
-        for (int k2 = 0; k2 < 64; k2++) v[k2] = cmul_p<false>(v[k2], hf[64 * k2 + t]);
-        dft64_dif<true>(v);
-#pragma unroll
-        for (int n2 = 1; n2 < 64; n2++) v[rev64(n2)] = cmul_p<true>(v[rev64(n2)], TW[n2 * 64 + t]);   // * conj W4096^(n2 k1)
-        gsync();                                             // step-2 readers are done
-#pragma unroll
-        for (int n2 = 0; n2 < 64; n2++) F[t * kOs64Stride + n2] = v[rev64(n2)];
-        gsync();
-#pragma unroll
-        for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
-        gsync();                                             // F is free: fetch the next block into it
-        pending = bulk_src(nch, nblkpos, src);
-        if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
-        dft64_dif<true>(v);
-        c2 *o = out + (base - Km1);
-        if (base + hop <= a.n_out) {
-#pragma unroll
-            for (int n1 = 0; n1 < 64; n1++) {
-                const int i = 64 * n1 + t;
-                if (i >= Km1) __stcg(o + i, v[rev64(n1)]);
-            }
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 64; n1++) {
-                const int i = 64 * n1 + t;
-                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev64(n1)]);
-            }
-        }
-        ch = nch; blk = nblkpos;
+        __syncthreads();                                     // every group is done with this channel's spectrum
     }
 }
 
@@ -1755,9 +1768,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         return B200C_OK;
     }
     static const bool persistent = [] { const char *e = std::getenv("B200C_OS64P"); return e && std::atoi(e) != 0; }();
-    if (persistent && nblk >= 4LL * sm_count) {
-        // one persistent 256-thread CTA per SM: four transform groups sharing the whole step-twiddle table in shared memory
-        const size_t smem = sizeof(c2) * ((size_t)kOs64Groups * kOs64SmemElems + 4096);
+    if (persistent && ((nchan == 1 && (long long)n_out >= 4LL * sm_count * p.hop()) || nchan >= sm_count)) {
+        // one persistent 256-thread CTA per SM: four transform groups sharing the step-twiddle table and the tap spectrum
+        const size_t smem = sizeof(c2) * ((size_t)kOs64Groups * kOs64SmemElems + 4096 + 4096);
         static thread_local bool configured[16] = {false};
         int dev = 0;
         B200C_CUDA_TRY(cudaGetDevice(&dev));
