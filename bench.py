@@ -669,7 +669,10 @@ def bench_bank(ctx: Ctx, steps: int, warmup: int, e2e: bool, cpu: bool, channels
     f1 = FirFilter(code, "COMPLEX", device=ctx.local_rank)
     f1.set_taps(wl.bank_taps(c0, nchan_total, ntaps))
     y1, _, _ = f1.run(x[0].contiguous())
-    assert torch.equal(y1[:4096], out[0, :4096]), "bank channel differs from its single-stream filter"
+    # (the two may run different kernels -- one launch over whole channels vs a short single stream -- whose step twiddles
+    # are formed differently: equal to rounding, not bit for bit)
+    d1 = float((y1[:4096] - out[0, :4096]).double().pow(2).mean().sqrt() / out[0, :4096].double().pow(2).mean().sqrt())
+    assert d1 < 2e-6, f"bank channel differs from its single-stream filter ({d1:.2e} of RMS)"
     import oracle
     nb = 8192
     y_ref, _, p_ref = oracle.fir(code, True, wl.bank_taps(c0, nchan_total, ntaps), 1, 1, x[0, : K - 1 + nb].cpu().numpy())
@@ -714,7 +717,7 @@ def bench_bank(ctx: Ctx, steps: int, warmup: int, e2e: bool, cpu: bool, channels
                          "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": 16.0,
                          "note": "fused overlap-save, one launch over (channel, block); 16 B per sample"},
             "cpu_baseline": cpu_rec, "e2e": e2e_rec, "gpu_launches": steps, "clocks": clocks,
-            "parity": f"channel {c0}: rel RMS error {err:.1e} vs oracle on {p_ref} outputs; == its single-stream filter bit for bit"}
+            "parity": f"channel {c0}: rel RMS error {err:.1e} vs oracle on {p_ref} outputs; {d1:.1e} from its single-stream filter"}
 
 
 def bench_blocks(ctx: Ctx, rounds_budget_s: float = 1.0) -> dict:

@@ -91,9 +91,11 @@ int b200c_fir_set_taps(b200c_fir *h, const double *taps, size_t ntaps);
 int b200c_fir_set_rates(b200c_fir *h, size_t decim, size_t interp);
 /* K (:335) and _inputRequire = M + K - 1 (:353) */
 int b200c_fir_info(const b200c_fir *h, size_t *K, size_t *input_require, size_t *decim, size_t *interp);
-/* Name of the device kernel b200c_fir_run() launches for the current taps/rates (diagnostic,
- * used by bench.py's roofline record): "fir_os32_kernel" / "fir_os64_kernel" (fused overlap-save,
- * complex float32 streams) or "fir_tile_kernel" / "fir_generic_kernel" (direct form). */
+/* Name of the device kernel family b200c_fir_run() launches for the current taps/rates (diagnostic, used by
+ * bench.py's roofline record): "fir_os32_kernel" / "fir_os64p_kernel" / "fir_os32r_kernel" / "fir_os32x_kernel" /
+ * "fir_ospg_kernel" / "fir_osp_kernel" / "fir_os32g_kernel" (fused fast convolution, float streams),
+ * "fir_umma32_kernel" / "fir_umma_kernel" / "fir_ummap_kernel" / "fir_imma_kernel" (int16 on the int8 tensor cores),
+ * "fir_tile_kernel" / "fir_generic_kernel" (direct form). */
 const char *b200c_fir_kernel(const b200c_fir *h);
 
 /* The N arithmetic of work(), filter/FIRFilter.cpp:278:

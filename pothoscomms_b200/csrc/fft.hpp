@@ -64,7 +64,6 @@ struct FirOsPlan {
     void *d_twa = nullptr;    // [8][64] float2: W4096^(8*a*t)
     void *d_twb = nullptr;    // [8][64] float2: W4096^(b*t)
     void *d_twf = nullptr;    // [64][64] float2: W4096^(j*t), the whole step-twiddle table
-    void *d_tw128 = nullptr;  // [32][128] float2: W4096^(k1*n2), step twiddles of the 128-thread kernel
     void *d_hf1k = nullptr;   // [1024] float2: spectrum of the taps / 1024
     void *d_tw1k = nullptr;   // [32][32] float2: W1024^(j*t)
     void *d_H = nullptr;      // general: [L*M][1024] float2 tap-phase spectra / 1024

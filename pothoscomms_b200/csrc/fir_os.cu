@@ -21,7 +21,6 @@
 #include "bulk.cuh"
 #include "fft.hpp"
 #include "os64_core.cuh"
-#include "os128_core.cuh"
 
 namespace b200c {
 
@@ -280,137 +279,11 @@ __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const Fi
     }
 }
 
-// ------------------------------------------ 4096-point variant, 128 threads x 32 points ---
-// fir_os64_kernel keeps 64 points (128 registers) per thread: 252 registers, two warps per scheduler, and ncu shows
-// what that costs (profiles/r01c_prof_os64_c5.txt, r02j_prof_os64p_c5.txt: FMA pipe 57-60 % busy, every stall class
-// exposed because there is only one other warp to switch to).  Here a transform is spread over 128 threads x 32 points
-// (os128_core.cuh): the same arithmetic count (1392 packed instructions per thread against 2752), twice the warps per SM.
-// Step twiddles W4096^(n2 k1) come from a [32][128] table through L1 (coalesced over n2), the W128 twiddles of the
-// in-row radix-4 stage are compile-time constants.  `twf` carries the table.
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) fir_os128_kernel(const FirOs64Args a)
-{
-    __shared__ __align__(16) c2 T[kOs128SmemElems];
-    __shared__ __align__(8) unsigned long long bar;
-    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-    const c2 *__restrict__ tw1 = static_cast<const c2 *>(a.twf);        // [32][128] W4096^(n2 k1)
-    const int Km1 = a.K - 1;
-    const int hop = 4096 - Km1;
-    const long long nblk = (a.n_out + hop - 1) / hop;
-    const long long tstep = gridDim.x, dch = tstep / nblk, dblk = tstep - dch * nblk;
-    long long ch = (long long)blockIdx.x / nblk, blk = (long long)blockIdx.x - ch * nblk;
-    auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
-        if (ch >= a.nchan) return false;
-        const long long base = blk * hop;
-        const c2 *in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
-        const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
-        src = in + (base - mis);
-        return base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
-    };
-    if (tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    const c2 *src = nullptr;
-    bool pending = bulk_src(ch, blk, src);
-    if (pending && tid == 0) bulk_load(T, src, kBulkElems * (unsigned)sizeof(c2), &bar);
-    unsigned parity = 0;
-    while (ch < a.nchan) {
-        const long long base = blk * hop;
-        long long nch = ch + dch, nblkpos = blk + dblk;      // this CTA's next task
-        if (nblkpos >= nblk) { nblkpos -= nblk; nch++; }
-        const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
-        const c2 *__restrict__ hf = static_cast<const c2 *>(a.hf) + ch * 4096;
-        c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
-        c2 v[32];
-        // ---- step 1: thread n2 = tid, x[128 n1 + n2] over n1
-        if (pending) {
-            const int mis = (int)(((reinterpret_cast<unsigned long long>(in) >> 3) + base) & 1);
-            mbar_wait(&bar, parity);
-            parity ^= 1;
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[rev32(n1)] = T[mis + 128 * n1 + tid];
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const long long gi = base + 128 * n1 + tid;
-                v[rev32(n1)] = gi < a.n_in ? __ldcg(in + gi) : 0ull;
-            }
-        }
-        dft32_dit<false>(v);
-#pragma unroll
-        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<false>(v[k1], tw1[k1 * 128 + tid]);
-        __syncthreads();                                     // every thread has taken its input out of the tile
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) T[k1 * kOs128Stride + tid] = v[k1];
-        __syncthreads();
-        // ---- step 2: thread (lane = k1, warp = r): its row, radix-4 over the quarters, W128 twiddle, 32-point transform
-        {
-            const c2 *row = T + lane * kOs128Stride;
-            switch (wq) {
-            case 0: os128_fwd_gather<0>(v, row); break;
-            case 1: os128_fwd_gather<1>(v, row); break;
-            case 2: os128_fwd_gather<2>(v, row); break;
-            default: os128_fwd_gather<3>(v, row); break;
-            }
-        }
-        dft32_dit<false>(v);                                 // v[m] = X[k1 + 32 (4 m + r)]
-        // ---- tap spectrum
-#pragma unroll
-        for (int m = 0; m < 32; m++) v[m] = cmul_p<false>(v[m], hf[lane + 32 * wq + 128 * m]);
-        // ---- step 2': same thread, same registers
-        dft32_dif<true>(v);
-        __syncthreads();                                     // every row has been read
-        {
-            c2 *row = T + lane * kOs128Stride;
-            switch (wq) {
-            case 0: os128_inv_scatter<0>(v, row); break;
-            case 1: os128_inv_scatter<1>(v, row); break;
-            case 2: os128_inv_scatter<2>(v, row); break;
-            default: os128_inv_scatter<3>(v, row); break;
-            }
-        }
-        __syncthreads();
-        // ---- step 1': thread n2 = lane + 32 wq: column lane, quarters combined over r, conj step twiddle, 32-point transform
-        switch (wq) {
-        case 0:
-#pragma unroll
-            for (int k1 = 0; k1 < 32; k1++) v[k1] = os128_inv_col<0>(T, k1, lane);
-            break;
-        case 1:
-#pragma unroll
-            for (int k1 = 0; k1 < 32; k1++) v[k1] = os128_inv_col<1>(T, k1, lane);
-            break;
-        case 2:
-#pragma unroll
-            for (int k1 = 0; k1 < 32; k1++) v[k1] = os128_inv_col<2>(T, k1, lane);
-            break;
-        default:
-#pragma unroll
-            for (int k1 = 0; k1 < 32; k1++) v[k1] = os128_inv_col<3>(T, k1, lane);
-            break;
-        }
-        __syncthreads();                                     // the tile is free: fetch the next block into it
-        pending = bulk_src(nch, nblkpos, src);
-        if (pending && tid == 0) bulk_load(T, src, kBulkElems * (unsigned)sizeof(c2), &bar);
-#pragma unroll
-        for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul_p<true>(v[k1], tw1[k1 * 128 + tid]);
-        dft32_dif<true>(v);                                  // c[128 n1 + tid] in v[rev32(n1)]
-        c2 *o = out + (base - Km1);
-        if (base + hop <= a.n_out) {
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const int i = 128 * n1 + tid;
-                if (i >= Km1) __stcg(o + i, v[rev32(n1)]);
-            }
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const int i = 128 * n1 + tid;
-                if (i >= Km1 && base + i - Km1 < a.n_out) __stcg(o + i, v[rev32(n1)]);
-            }
-        }
-        ch = nch; blk = nblkpos;
-    }
-}
+// (Round 2 also built this transform on 128 threads x 32 points -- half the register state, 16 warps per SM, the
+// radix-4 stage of each 128-point row folded into a 4x redundant read of the exchange tile.  Correct (same tests) and
+// 25 % SLOWER than fir_os64_kernel: four warps per transform branch into four different straight-line code paths after
+// every barrier, so no two warps share instruction-cache lines (ncu: no_instruction 3.7 stall cycles per issue) and the
+// shared-memory pipe is 2.2x as busy.  profiles/r02l_prof_os128_c5.txt; the code was removed.)
 
 constexpr bool kOs32PartialTwiddles = false;   // fir_os32_kernel: measured no gain on B200 (headline 269 vs 272 Gsamples/s); the resampler keeps them
 
@@ -1503,8 +1376,6 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
                 if ((rc = upload(&p.d_twb, tb))) return rc;
                 unit_root_table(tb, 4096, 64, 64, 1);          // the whole table, for the persistent form
                 if ((rc = upload(&p.d_twf, tb))) return rc;
-                unit_root_table(tb, 4096, 32, 128, 1);         // W4096^(k1 n2), k1 < 32, n2 < 128: fir_os128_kernel
-                if ((rc = upload(&p.d_tw128, tb))) return rc;
             }
             taps_spectrum(hf, 4096, taps, ntaps, complex_taps);
             if ((rc = upload(&p.d_hf, hf))) return rc;
@@ -1564,7 +1435,7 @@ int fir_os_configure(FirOsPlan &p, int dtype, const double *taps, size_t ntaps, 
 
 void fir_os_destroy(FirOsPlan &p)
 {
-    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_twf, &p.d_tw128, &p.d_hf1k, &p.d_tw1k, &p.d_H, &p.d_hx, &p.d_tw3}) {
+    for (void **d : {&p.d_hf, &p.d_twa, &p.d_twb, &p.d_twf, &p.d_hf1k, &p.d_tw1k, &p.d_H, &p.d_hx, &p.d_tw3}) {
         if (*d) cudaFree(*d);
         *d = nullptr;
     }
@@ -1577,7 +1448,9 @@ const char *fir_os_kernel_name(const FirOsPlan &p)
     if (p.x32) return "fir_os32x_kernel";
     if (p.general) return p.osp ? (p.ospg ? "fir_ospg_kernel" : "fir_osp_kernel") : "fir_os32g_kernel";
     if (p.real32) return "fir_os32r_kernel";
-    return p.N == 1024 ? "fir_os32_kernel" : "fir_os64_kernel";
+    // (4096-point: launches too small for the persistent form -- a few hundred blocks, or a bank of fewer channels than
+    // SMs -- run fir_os64_kernel, the same transform with one group per CTA)
+    return p.N == 1024 ? "fir_os32_kernel" : "fir_os64p_kernel";
 }
 
 template <int M, bool MULTI_L, bool REAL, bool TILE_OUT, int MINB>
@@ -1753,21 +1626,8 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
     a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb; a.twf = p.d_twf;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
     a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
-    static const int os128 = [] { const char *e = std::getenv("B200C_OS128"); return e ? std::atoi(e) : 0; }();
-    if (os128 >= 3 && os128 <= 5) {
-        // 128 threads x 32 points per transform, os128 CTAs per SM
-        FirOs64Args b = a;
-        b.twf = p.d_tw128;
-        const int grid = (int)std::min<long long>(nblk, (long long)sm_count * os128 * 4);
-        switch (os128) {
-        case 3: fir_os128_kernel<3><<<grid, 128, 0, stream>>>(b); break;
-        case 5: fir_os128_kernel<5><<<grid, 128, 0, stream>>>(b); break;
-        default: fir_os128_kernel<4><<<grid, 128, 0, stream>>>(b); break;
-        }
-        B200C_CUDA_TRY(cudaGetLastError());
-        return B200C_OK;
-    }
-    static const bool persistent = [] { const char *e = std::getenv("B200C_OS64P"); return e && std::atoi(e) != 0; }();
+    // default: the persistent form wherever it applies (B200C_OS64P=0: always the one-transform-per-CTA kernel, for A/B runs)
+    static const bool persistent = [] { const char *e = std::getenv("B200C_OS64P"); return !e || std::atoi(e) != 0; }();
     if (persistent && ((nchan == 1 && (long long)n_out >= 4LL * sm_count * p.hop()) || nchan >= sm_count)) {
         // one persistent 256-thread CTA per SM: four transform groups sharing the step-twiddle table and the tap spectrum
         const size_t smem = sizeof(c2) * ((size_t)kOs64Groups * kOs64SmemElems + 4096 + 4096);
