@@ -713,7 +713,7 @@ def bench_bank(ctx: Ctx, steps: int, warmup: int, e2e: bool, cpu: bool, channels
             "value": value, "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "scaling": "strong",
             "n_gpus": ctx.world, "dtype": "f32",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / ctx.peaks["hbm_gbs"], "traffic": workload_traffic("c5", nch * n_new), "peak_kind": ctx.peak_kind,
+                         "frac": achieved / ctx.peaks["hbm_gbs"], "traffic": workload_traffic("c5_bank", nch * n_new), "peak_kind": ctx.peak_kind,
                          "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": 16.0,
                          "note": "fused overlap-save, one launch over (channel, block); 16 B per sample"},
             "cpu_baseline": cpu_rec, "e2e": e2e_rec, "gpu_launches": steps, "clocks": clocks,

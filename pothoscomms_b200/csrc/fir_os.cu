@@ -36,6 +36,7 @@ struct FirOs64Args {
     long long in_stride, out_stride;   // elements between consecutive channels (filter bank)
     int nchan;
     int K;              // taps
+    int parts;          // fir_os64p_kernel: a channel's blocks are dealt over this many CTA-tasks
 };
 
 // v[slot(j)] *= W4096^(j*t) (CONJ: conjugate), j = 8a + b, from the two 8-entry tables.
@@ -166,11 +167,12 @@ __global__ void __launch_bounds__(64, MINB) fir_os64_kernel(const FirOs64Args a)
 // 256-thread CTA (group = 2 warps, synchronised on its own named barrier) that keeps, in shared memory, one copy of
 //   * the WHOLE step-twiddle table W4096^(j t) (32 KB): a step twiddle is 63 LDS + 63 complex multiplies instead of
 //     14 global loads + 112 multiplies (two factors per element), 7 % fewer FMA-pipe instructions;
-//   * the tap spectrum of the channel the CTA is working on (32 KB): in a filter bank every CTA takes whole channels
-//     (channel = blockIdx.x, + gridDim.x, ...; its four groups share the channel's blocks), so the spectrum is staged
-//     once per channel and the 64 loads per thread and block become LDS -- ncu had the global loads as the
+//   * the tap spectrum of the channel the CTA is working on (32 KB): a CTA-task is (channel, part) -- the channel's
+//     blocks part*4 + g, + parts*4, ... for the four groups g -- so the spectrum is staged once per task (once per
+//     channel when parts = 1) and the 64 loads per thread and block become LDS; ncu had the global loads as the
 //     long_scoreboard / lg_throttle stalls of the one-transform-per-CTA kernel (profiles/r02j_prof_os64p_c5.txt).
-// A single stream (nchan == 1) deals its blocks over all CTAs and stages the one spectrum once.
+// The host picks `parts` so that nchan * parts tasks fill whole rounds of CTAs: 1 for a 1024-channel bank, 15 for the
+// 128 channels one of 8 GPUs holds, gridDim.x for a single stream (every CTA one task, the spectrum staged once).
 constexpr int kOs64Groups = 4;
 __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const FirOs64Args a)
 {
@@ -185,10 +187,8 @@ __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const Fi
     const int Km1 = a.K - 1;
     const int hop = 4096 - Km1;
     const long long nblk = (a.n_out + hop - 1) / hop;
-    const bool per_cta = a.nchan > 1;                          // host: nchan == 1 or nchan >= gridDim.x
-    const long long first = per_cta ? g : (long long)blockIdx.x * kOs64Groups + g;
-    const long long bstep = per_cta ? kOs64Groups : (long long)gridDim.x * kOs64Groups;
-    const long long chstep = per_cta ? gridDim.x : a.nchan;   // nchan == 1: the channel loop runs once
+    const long long parts = a.parts, ntask = (long long)a.nchan * parts;
+    const long long bstep = parts * kOs64Groups;
     auto bulk_src = [&](long long ch, long long blk, const c2 *&src) {
         if (ch >= a.nchan || blk >= nblk) return false;
         const long long base = blk * hop;
@@ -197,23 +197,26 @@ __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const Fi
         src = in + (base - mis);
         return base - mis >= 0 && base - mis + kBulkElems <= a.n_in;
     };
-    long long ch = per_cta ? blockIdx.x : 0;
+    long long task = blockIdx.x;
     if (t == 0) mbar_init(bar, 1);
     gsync();
     const c2 *src = nullptr;
-    bool pending = bulk_src(ch, first, src);
+    bool pending = task < ntask && bulk_src(task / parts, (task % parts) * kOs64Groups + g, src);
     if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
     {   // the twiddle table is staged while the first blocks are in flight
         const c2 *__restrict__ twf = static_cast<const c2 *>(a.twf);
         for (int i = threadIdx.x; i < 4096; i += 64 * kOs64Groups) TW[i] = twf[i];
     }
-    for (; ch < a.nchan; ch += chstep) {
-        {   // this channel's tap spectrum (the previous channel's readers are past the barrier that ends the loop body)
+    long long staged = -1;
+    for (; task < ntask; task += gridDim.x) {
+        const long long ch = task / parts, first = (task - ch * parts) * kOs64Groups + g;
+        if (ch != staged) {   // this channel's tap spectrum (the previous task's readers are past the barrier that ends the loop body)
             const c2 *__restrict__ hfg = static_cast<const c2 *>(a.hf) + ch * 4096;
             for (int i = threadIdx.x; i < 4096; i += 64 * kOs64Groups) HF[i] = __ldg(hfg + i);
-            __syncthreads();
+            staged = ch;
         }
+        __syncthreads();
         const c2 *__restrict__ in = static_cast<const c2 *>(a.in) + ch * a.in_stride;
         c2 *__restrict__ out = static_cast<c2 *>(a.out) + ch * a.out_stride;
         for (long long blk = first; blk < nblk; blk += bstep) {
@@ -255,8 +258,9 @@ __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const Fi
             for (int k1 = 0; k1 < 64; k1++) v[k1] = F[k1 * kOs64Stride + t];
             gsync();                                         // F is free: fetch the group's next block into it
             {
-                const bool last = blk + bstep >= nblk;       // next: the same channel, or the CTA's next channel
-                pending = bulk_src(last ? ch + chstep : ch, last ? first : blk + bstep, src);
+                const bool last = blk + bstep >= nblk;       // next: the same task, or the first block of the CTA's next task
+                const long long nt = task + gridDim.x;
+                pending = last ? (nt < ntask && bulk_src(nt / parts, (nt % parts) * kOs64Groups + g, src)) : bulk_src(ch, blk + bstep, src);
                 if (pending && t == 0) bulk_load(F, src, kBulkElems * (unsigned)sizeof(c2), bar);
             }
             dft64_dif<true>(v);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(64 * kOs64Groups, 1) fir_os64p_kernel(const Fi
                 }
             }
         }
-        __syncthreads();                                     // every group is done with this channel's spectrum
+        __syncthreads();                                     // every group is done with this task's spectrum
     }
 }
 
@@ -1626,11 +1630,24 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
     a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf; a.twa = p.d_twa; a.twb = p.d_twb; a.twf = p.d_twf;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
     a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
+    a.parts = 1;
     // default: the persistent form wherever it applies (B200C_OS64P=0: always the one-transform-per-CTA kernel, for A/B runs)
     static const bool persistent = [] { const char *e = std::getenv("B200C_OS64P"); return !e || std::atoi(e) != 0; }();
-    if (persistent && ((nchan == 1 && (long long)n_out >= 4LL * sm_count * p.hop()) || nchan >= sm_count)) {
-        // one persistent 256-thread CTA per SM: four transform groups sharing the step-twiddle table and the tap spectrum
+    const long long blocks_per_chan = ((long long)n_out + p.hop() - 1) / p.hop();
+    if (persistent && (long long)nchan * blocks_per_chan >= 4LL * kOs64Groups * sm_count) {
+        // one persistent 256-thread CTA per SM: four transform groups sharing the step-twiddle table and the tap spectrum.
+        // CTA-tasks = (channel, part); `parts` is the split (>= 16 blocks per part) whose task count fills rounds of CTAs best
         const size_t smem = sizeof(c2) * ((size_t)kOs64Groups * kOs64SmemElems + 4096 + 4096);
+        if (nchan == 1) a.parts = sm_count;
+        else {
+            const long long maxp = std::max<long long>(1, blocks_per_chan / 16);
+            double best = -1.0;
+            for (long long q = 1; q <= std::min<long long>(maxp, 32); q++) {
+                const long long T = (long long)nchan * q, rounds = (T + sm_count - 1) / sm_count;
+                const double util = (double)T / (double)(rounds * sm_count) - 1e-4 * (double)q;   // ties: fewer parts
+                if (util > best) { best = util; a.parts = (int)q; }
+            }
+        }
         static thread_local bool configured[16] = {false};
         int dev = 0;
         B200C_CUDA_TRY(cudaGetDevice(&dev));
