@@ -1527,7 +1527,8 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         // One persistent 12-warp CTA per SM, tables in shared memory, partial twiddles, second inverse round by lane pairs.
         // Measured alternatives (profiles/r02_osx_variants.txt): 12 one-warp CTAs per SM with tables through L1 (-11 %),
         // all twiddles loaded (-2 %), 8 / 9 warps with landing buffers and compact tables (-3 % / -17 %: the kernel is
-        // FMA-pipe bound, fewer warps lose more than the earlier prefetch gains), lanes 0..15 alone in the second round (-1.5 %).
+        // FMA-pipe bound, fewer warps lose more than the earlier prefetch gains), lanes 0..15 alone in the second round (-1.5 %),
+        // 13 / 14 warps at 128 registers (-14 % / -9 %: the register cap costs more than the extra warps hide).
         const size_t tile = sizeof(c2) * kX32SmemElems;
         const size_t smem = 12 * tile + sizeof(c2) * kX32TabElems;
         static thread_local bool configured[16] = {false};
@@ -1536,21 +1537,6 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         if (dev < 16 && !configured[dev]) {
             B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<12, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured[dev] = true;
-        }
-        static const int xw = [] { const char *e = std::getenv("B200C_OSX_WARPS"); return e ? std::atoi(e) : 12; }();
-        if (xw == 13 || xw == 14) {   // experiment: more warps per SM at fewer registers
-            const size_t smem_w = (size_t)xw * tile + sizeof(c2) * kX32TabElems;
-            static thread_local bool configured_w[16] = {false};
-            if (dev < 16 && !configured_w[dev]) {
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<13, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(13 * tile + sizeof(c2) * kX32TabElems)));
-                B200C_CUDA_TRY(cudaFuncSetAttribute(fir_os32x_kernel<14, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(14 * tile + sizeof(c2) * kX32TabElems)));
-                configured_w[dev] = true;
-            }
-            const int gridw = (int)std::min<long long>((nblk + xw - 1) / xw, (long long)sm_count);
-            if (xw == 13) fir_os32x_kernel<13, 1, true, true><<<gridw, 32 * 13, smem_w, stream>>>(a);
-            else fir_os32x_kernel<14, 1, true, true><<<gridw, 32 * 14, smem_w, stream>>>(a);
-            B200C_CUDA_TRY(cudaGetLastError());
-            return B200C_OK;
         }
         const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
         fir_os32x_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
