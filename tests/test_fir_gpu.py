@@ -776,3 +776,33 @@ def test_untuned_types_at_tap_counts_that_prefer_wider_register_blocks(oracle, c
             y, cons, prod, f = _run_gpu(code, "COMPLEX" if tcx else "REAL", taps, M, L, x)
             assert (cons, prod) == (c_ref, p_ref)
             _compare(oracle, code, y, y_ref, f"{dt} M={M} L={L} ntaps={ntaps} [{f.kernel}]")
+
+
+@pytest.mark.parametrize("cfg,code_name,M,L,log2n", [("c2", "CI16", 1, 1, 28), ("c3", "CF32", 2, 3, 30), ("c5", "CF32", 1, 1, 26)])
+def test_baseline_configs_at_their_stated_sizes_sampled_windows(oracle, cuda_device, cfg, code_name, M, L, log2n):
+    """BASELINE.json's C2 (complex int16, 128 taps, 2^28 samples), C3 (L = 3 / M = 2 resampler, ONE 2^30-sample stream on one
+    GPU: 8 GiB in, 12 GiB out) and a C5 channel at the full stated sizes: the oracle cannot run these end to end, so windows
+    are sampled -- the start (history-only prefix), block boundaries deep inside, the ragged end -- and compared with the
+    oracle run on the same input slice: bit-exact for int16, 1e-5 of RMS for float."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    from pothoscomms_b200 import workloads as wl
+    code = getattr(oracle, code_name)
+    taps, tt = wl.config_taps(cfg)
+    f = FirFilter(code, tt)
+    f.set_taps(taps)
+    f.set_rates(M, L)
+    K = f.K
+    n = (1 << log2n) // M * M
+    x = wl.tone_noise_torch(code, K - 1 + n, 0xC0FFEE00 + log2n, cuda_device)
+    y, cons, prod = f.run(x)
+    torch.cuda.synchronize()
+    assert (cons, prod) == (n, n // M * L)
+    wlen = 30_000 // M * M
+    for w0 in (0, (n // 3) // M * M, (n // 2 + 7777) // M * M, n - wlen):       # input offsets, multiples of M
+        seg = x[w0: w0 + K - 1 + wlen].cpu().numpy()
+        y_ref, c_ref, p_ref = oracle.fir(code, tt == "COMPLEX", taps, M, L, seg, threads=8)
+        o0 = w0 // M * L
+        _compare(oracle, code, y[o0: o0 + p_ref].cpu().numpy(), y_ref, f"{cfg} 2^{log2n} window at {w0} [{f.kernel}]")
+    del x, y
+    torch.cuda.empty_cache()
