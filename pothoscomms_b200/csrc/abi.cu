@@ -223,7 +223,9 @@ static int fir_refresh(b200c_fir *h)
         }
         h->use_u32 = false;
         if (h->use_imma && !(algo && (std::strcmp(algo, "imma") == 0 || std::strcmp(algo, "umma") == 0))) {
-            rc = fir_umma32_configure(h->u32, h->imma, h->taps.data(), algo && std::strcmp(algo, "umma32") == 0);
+            // umma32t: the operand-swapped variant (complex int16 data); umma32 pins the original formulation
+            const bool t = algo && std::strcmp(algo, "umma32t") == 0, o = algo && std::strcmp(algo, "umma32") == 0;
+            rc = fir_umma32_configure(h->u32, h->imma, h->taps.data(), t || o, t ? 1 : o ? 0 : -1);
             if (rc) return rc;
             h->use_u32 = h->u32.ready;
         }
@@ -368,7 +370,7 @@ const char *b200c_fir_kernel(const b200c_fir *h)
     if (!h) return "";
     if (h->use_os) return fir_os_kernel_name(h->os);
     if (h->use_up) return "fir_ummap_kernel";
-    if (h->use_u32) return "fir_umma32_kernel";
+    if (h->use_u32) return h->u32.swapped ? "fir_umma32t_kernel" : "fir_umma32_kernel";
     if (h->use_umma) return "fir_umma_kernel";
     if (h->use_imma) return "fir_imma_kernel";
     return h->table.smem_path ? "fir_tile_kernel" : "fir_generic_kernel";

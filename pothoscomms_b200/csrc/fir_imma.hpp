@@ -53,8 +53,13 @@ struct FirUmma32Plan {
     int dc = 1;
     void *d_bmat = nullptr;   // [dc][NB][N x 32 B] B tiles, N = 32 x dc x 2
     size_t capacity = 0;
+    // operand-swapped variant (fir_umma32t_kernel, complex int16 data): tap tiles as the A operand in tensor
+    // memory, row-major [dc][NB][128 rows x 32 B]
+    bool swapped = false;
+    void *d_amat = nullptr;
+    size_t a_capacity = 0;
 };
-int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force);
+int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force, int swap = -1);
 void fir_umma32_destroy(FirUmma32Plan &p);
 int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems, void *d_out, size_t n_out, int sm_count,
                       cudaStream_t stream);

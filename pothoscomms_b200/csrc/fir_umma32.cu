@@ -39,35 +39,53 @@ struct FirUmma32Args {
 };
 
 constexpr int kU32Tile = 4096;
+// operand-swapped variant (TS = true, complex int16 only): the tap tiles are the A operand and live in
+// TENSOR MEMORY, the data planes are the B operand with N = NW windows per tile.  Columns: two stages x
+// two data limbs x NW accumulators + 8 per (data component, k-block) tap tile <= 512.
+constexpr int kU32tNW = 96, kU32tTile = 32 * kU32tNW, kU32tMaxNB = (512 - 4 * kU32tNW) / 16;
 constexpr int kU32EpiWarps = 8, kU32StageWarps = 8, kU32MaxRing = 8;
 constexpr int kU32Batch = 5;      // stager loads in flight per thread: their latency under the MMA's operand traffic is long
 constexpr int kU32Threads = 32 * (kU32EpiWarps + kU32StageWarps + 2);
+// the swapped kernel is bound by instruction issue (ncu r02ad: 1.3 warp instructions per sample, 47 % of them the
+// stagers' -- mostly per-tile overhead of eight warps converting three items each): four stager warps with
+// compile-time sizes
+constexpr int kU32tStageWarps = 4;
+constexpr int kU32tThreads = 32 * (kU32EpiWarps + kU32tStageWarps + 2);
 
-template <int DC>
-__global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmma32Args a)
+template <int DC, bool TS, int NBT>   // NBT: the k-block count at compile time (0: a.NB)
+__device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
 {
     extern __shared__ __align__(1024) unsigned char smem_v[];
     constexpr int NQ = DC * 2;                     // (output component, tap digit) per output
     constexpr int N = 32 * NQ;                     // MMA N = columns of one data-limb region
-    constexpr int COLS = 2 * N;                    // lo and hi regions
-    constexpr int ALLOC = 2 * COLS;                // two stages: 512 (complex) / 256 (real) columns
+    constexpr int NW = kU32tNW;                    // TS: windows per tile = MMA N
+    constexpr int TILE = TS ? kU32tTile : kU32Tile;
+    constexpr int COLS = TS ? 2 * NW : 2 * N;      // lo and hi regions
+    constexpr int ALLOC = TS ? 512 : 2 * COLS;     // two stages: 512 (complex) / 256 (real) columns
+    constexpr int ACOL = 2 * COLS;                 // TS: first column of the tap tiles
+    constexpr int SW = TS ? kU32tStageWarps : kU32StageWarps, NTHR = TS ? kU32tThreads : kU32Threads;
+    static_assert(!TS || DC == 2, "the swapped formulation needs M = 128 = 32 outputs x 2 components x 2 digits");
     constexpr int NPL = DC * 2, ESZ = DC * 2;
     constexpr int CH = 16 / NQ;                    // outputs per 16-column epilogue chunk
-    const int NB = a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
-    unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024)
-    unsigned char *planes = bmat + (size_t)DC * NB * N * 32;         // [2][NPL][PLa], 256-byte aligned, swizzled
+    const int NB = NBT ? NBT : a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
+    unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024); TS: none
+    unsigned char *planes = bmat + (TS ? 0 : (size_t)DC * NB * N * 32);   // [2][NPL][PLa], 256-byte aligned, swizzled
     unsigned char *raw = planes + 2 * (size_t)NPL * PLa;             // [R][PL * ESZ]
     __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
     __shared__ unsigned tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < DC * NB * N * 2; i += kU32Threads)
-        reinterpret_cast<uint4 *>(bmat)[i] = __ldg(static_cast<const uint4 *>(a.bmat) + i);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if constexpr (!TS) {
+        for (int i = tid; i < DC * NB * N * 2; i += NTHR)
+            reinterpret_cast<uint4 *>(bmat)[i] = __ldg(static_cast<const uint4 *>(a.bmat) + i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (tid == 0) {
-        for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * kU32StageWarps); }
+        // every stager / epilogue thread waits and arrives itself: one lane per warp followed by a warp barrier measured
+        // 2x slower (profiles/r02ab: the stagers' proxy fence + arrival went from ~80 to ~1800 cycles per tile)
+        for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * SW); }
         for (int s = 0; s < 2; s++) {
-            mbar_init(&planes_full[s], 32 * kU32StageWarps); mbar_init(&planes_empty[s], 1);
+            mbar_init(&planes_full[s], 32 * SW); mbar_init(&planes_empty[s], 1);
             mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * kU32EpiWarps);
         }
     }
@@ -79,29 +97,51 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = tmem_base_s;
+    if constexpr (TS) {
+        // tap tiles -> tensor memory: row m' (TMEM lane) of tile t is 32 bytes = 8 columns (tools/probe_umma_tmem_a.cu)
+        if (warp < 4) {
+            const unsigned at = tmem_base + ((unsigned)(32 * warp) << 16) + ACOL;
+            const uint4 *am = static_cast<const uint4 *>(a.bmat) + (32 * warp + lane) * 2;
+            for (int t = 0; t < DC * NB; t++) {
+                const uint4 v0 = __ldg(am + t * 256), v1 = __ldg(am + t * 256 + 1);
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(at + 8u * t), "r"(v0.x),
+                             "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w)
+                             : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     const long long first = blockIdx.x, step = gridDim.x;
     const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;
     const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
-    auto bulk_ok = [&](long long tile) { return al && tile * kU32Tile + PL <= a.n_in; };
+    auto bulk_ok = [&](long long tile) { return al && tile * TILE + PL <= a.n_in; };
     long long w0 = 0, w1 = 0, t_conv = 0, t_fence = 0;
     const long long t_begin = clock64();
+    if (g_umma_watch && blockIdx.x == 0 && tid == 0) {     // barrier addresses, to decode the watchdog's records
+        unsigned long long *w = g_umma_watch + 32 * gridDim.x;
+        w[0] = smem_u32(raw_full); w[1] = smem_u32(raw_empty); w[2] = smem_u32(planes_full); w[3] = smem_u32(planes_empty);
+        w[4] = smem_u32(acc_full); w[5] = smem_u32(acc_empty);
+    }
 
-    if (warp == kU32EpiWarps + kU32StageWarps + 1) {
+    if (warp == kU32EpiWarps + SW + 1) {
         // ================================================================ bulk-copy issuer
         if (lane == 0)
             for (int i = 0, r = 0, ph = 0; i < ntl; i++) {
                 const long long tile = first + (long long)i * step;
-                timed_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
+                watched_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
                 if (bulk_ok(tile))
-                    bulk_load(raw + (size_t)r * PL * ESZ, static_cast<const unsigned char *>(a.in) + (size_t)tile * kU32Tile * ESZ,
+                    bulk_load(raw + (size_t)r * PL * ESZ, static_cast<const unsigned char *>(a.in) + (size_t)tile * TILE * ESZ,
                               (unsigned)(PL * ESZ), &raw_full[r]);
                 else
                     mbar_arrive(&raw_full[r]);
                 if (++r == R) { r = 0; ph ^= 1; }
             }
-    } else if (warp == kU32EpiWarps + kU32StageWarps) {
+    } else if (warp == kU32EpiWarps + SW) {
         // ====================================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             // One thread feeds the tensor core: everything per MMA beyond two 64-bit adds is hoisted out
             // of the loop (with descriptors rebuilt per MMA the issue rate, not the MMA, set the pace).
             unsigned long long a_base[2][NPL], b_base[DC];
@@ -110,29 +150,61 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
 #pragma unroll
                 for (int p = 0; p < NPL; p++)      // A: plane p of stage s, rows of 32-byte pitch (SWIZZLE_32B)
                     a_base[s][p] = umma_smem_desc(smem_u32(planes + ((size_t)s * NPL + p) * PLa), 16, 256, 6);
+            if constexpr (!TS) {
 #pragma unroll
-            for (int dc = 0; dc < DC; dc++) b_base[dc] = umma_smem_desc(smem_u32(bmat + (size_t)dc * NB * N * 32), 128, 256, 0);
+                for (int dc = 0; dc < DC; dc++) b_base[dc] = umma_smem_desc(smem_u32(bmat + (size_t)dc * NB * N * 32), 128, 256, 0);
+            }
             constexpr unsigned long long kAStep = 32 >> 4, kBStep = (N * 32) >> 4;   // start-address field is in 16-byte units
             // the tile loop is unrolled over the two stages so that every index below is a compile-time
             // constant (dynamically indexed descriptor arrays would live in local memory)
             auto issue_tile = [&](auto stage_c, const unsigned ph) {
                 constexpr int S = decltype(stage_c)::value;
-                timed_wait(&planes_full[S], ph, w0);
-                timed_wait(&acc_empty[S], ph ^ 1, w1);
+                watched_wait(&planes_full[S], ph, w0);
+                watched_wait(&acc_empty[S], ph ^ 1, w1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if constexpr (TS) {
+                    // D'[m' = (output j, component, digit)][n' = window] += taps[m'][k] . plane[32 (n' + b) + k]:
+                    // the data planes are the B operand (same Hankel descriptor, NW rows), 3 KB of shared
+                    // memory per MMA instead of 8
 #pragma unroll
-                for (int dl = 0; dl < 2; dl++) {                       // data limb: its own accumulator region
-                    const unsigned d = tmem_base + (unsigned)(S * COLS + dl * N);
-                    constexpr unsigned idesc_lo = umma_idesc_i8(false, N), idesc_hi = umma_idesc_i8(true, N);
+                    for (int dl = 0; dl < 2; dl++) {
+                        const unsigned d = tmem_base + (unsigned)(S * COLS + dl * NW);
+                        constexpr unsigned idesc_lo = umma_idesc_i8_ab(true, false, NW), idesc_hi = umma_idesc_i8_ab(true, true, NW);
 #pragma unroll
-                    for (int dc = 0; dc < DC; dc++) {
-                        // k-block b: the A window starts one 32-byte row later (Hankel), B is the next tile
-                        unsigned long long ad = a_base[S][2 * dc + dl], bd = b_base[dc];
-                        if (dc == 0) { umma_i8_first(d, ad, bd, dl ? idesc_hi : idesc_lo); ad += kAStep; bd += kBStep; }
+                        for (int dc = 0; dc < DC; dc++) {
+                            unsigned long long bd = a_base[S][2 * dc + dl];
+                            unsigned at = tmem_base + (unsigned)(ACOL + 8 * dc * NB);
+                            if (dc == 0) { umma_i8_ts_first(d, at, bd, dl ? idesc_hi : idesc_lo); bd += kAStep; at += 8; }
+                            if constexpr (NBT > 0) {
+#pragma unroll
+                                for (int b = dc == 0 ? 1 : 0; b < NBT; b++) {
+                                    umma_i8_ts_acc(d, at, bd, dl ? idesc_hi : idesc_lo);
+                                    bd += kAStep; at += 8;
+                                }
+                            } else {
 #pragma unroll 4
-                        for (int b = dc == 0 ? 1 : 0; b < NB; b++) {
-                            umma_i8_acc(d, ad, bd, dl ? idesc_hi : idesc_lo);
-                            ad += kAStep; bd += kBStep;
+                                for (int b = dc == 0 ? 1 : 0; b < NB; b++) {
+                                    umma_i8_ts_acc(d, at, bd, dl ? idesc_hi : idesc_lo);
+                                    bd += kAStep; at += 8;
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int dl = 0; dl < 2; dl++) {                       // data limb: its own accumulator region
+                        const unsigned d = tmem_base + (unsigned)(S * COLS + dl * N);
+                        constexpr unsigned idesc_lo = umma_idesc_i8(false, N), idesc_hi = umma_idesc_i8(true, N);
+#pragma unroll
+                        for (int dc = 0; dc < DC; dc++) {
+                            // k-block b: the A window starts one 32-byte row later (Hankel), B is the next tile
+                            unsigned long long ad = a_base[S][2 * dc + dl], bd = b_base[dc];
+                            if (dc == 0) { umma_i8_first(d, ad, bd, dl ? idesc_hi : idesc_lo); ad += kAStep; bd += kBStep; }
+#pragma unroll 4
+                            for (int b = dc == 0 ? 1 : 0; b < NB; b++) {
+                                umma_i8_acc(d, ad, bd, dl ? idesc_hi : idesc_lo);
+                                ad += kAStep; bd += kBStep;
+                            }
                         }
                     }
                 }
@@ -150,19 +222,45 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
         // raw (re, im) int16 samples -> byte planes, stored with the 32-byte swizzle: the 16-byte chunk
         // c of a plane lives at chunk c ^ (c >> 3 & 1)
         const int st = tid - 32 * kU32EpiWarps;
-        constexpr int NST = 32 * kU32StageWarps;
+        constexpr int NST = 32 * SW;
         const int nq = PL / 4;
         for (int i = 0, r = 0, rph = 0; i < ntl; i++) {
             const int s = i & 1;
             const unsigned ph = (unsigned)(i >> 1) & 1;
-            const long long tile = first + (long long)i * step, o0 = tile * kU32Tile;
+            const long long tile = first + (long long)i * step, o0 = tile * TILE;
             const bool landed = bulk_ok(tile);
-            timed_wait(&raw_full[r], (unsigned)rph, w0);
-            timed_wait(&planes_empty[s], ph ^ 1, w1);
+            watched_wait(&raw_full[r], (unsigned)rph, w0);
+            watched_wait(&planes_empty[s], ph ^ 1, w1);
             unsigned *pl = reinterpret_cast<unsigned *>(planes + (size_t)s * NPL * PLa);
             const unsigned char *rw = raw + (size_t)r * PL * ESZ;
             const long long t_c0 = clock64();
-            if constexpr (DC == 2) {
+            if (TS && landed) {
+                // every size is a compile-time constant here: item q = st + 128 u of this thread (four samples: 16 raw
+                // bytes -> one word of each plane) sits 2048 bytes further in the landing slot and 512 bytes further
+                // in the planes (q + 128 is 32 chunks on: the swizzle bit (c >> 3) & 1 does not change)
+                constexpr int PLc = kU32tTile + 32 * (NBT ? NBT : 1), PLac = (PLc + 255) / 256 * 256, NQc = PLc / 4;
+                constexpr int FULL = NQc / NST, REM = NQc % NST;
+                static_assert(NST % 64 == 0, "q + NST must keep the swizzle bit");
+                const int c0 = st >> 2;
+                const uint4 *src = reinterpret_cast<const uint4 *>(rw) + st;
+                unsigned *dst = pl + (((c0 ^ ((c0 >> 3) & 1)) << 2) | (st & 3));
+                auto split = [&](const uint4 v, unsigned *p) {
+                    const unsigned t01 = prmt_u(v.x, v.y, 0x5140), t23 = prmt_u(v.z, v.w, 0x5140);
+                    const unsigned u01 = prmt_u(v.x, v.y, 0x7362), u23 = prmt_u(v.z, v.w, 0x7362);
+                    p[0] = prmt_u(t01, t23, 0x5410);
+                    p[PLac / 4] = prmt_u(t01, t23, 0x7632);
+                    p[2 * (PLac / 4)] = prmt_u(u01, u23, 0x5410);
+                    p[3 * (PLac / 4)] = prmt_u(u01, u23, 0x7632);
+                };
+                uint4 v[FULL];
+#pragma unroll
+                for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                uint4 vt = make_uint4(0, 0, 0, 0);
+                if (REM && st < REM) vt = src[FULL * NST];
+#pragma unroll
+                for (int u = 0; u < FULL; u++) split(v[u], dst + u * NST);
+                if (REM && st < REM) split(vt, dst + FULL * NST);
+            } else if constexpr (DC == 2) {
                 const unsigned *__restrict__ in32 = static_cast<const unsigned *>(a.in);
                 for (int q0 = st; q0 < nq; q0 += kU32Batch * NST) {
                     uint4 v[kU32Batch];
@@ -230,6 +328,61 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
             t_conv += t_c1 - t_c0; t_fence += t_c2 - t_c1;
             if (++r == R) { r = 0; rph ^= 1; }
         }
+    } else if constexpr (TS) {
+        // ============================================================= epilogue (swapped operands)
+        // TMEM lane m' = 32 quad + 16 cls + 8 digit + jr  (output j = 8 quad + jr), column = window n'.
+        // The 16-lane load shape hands thread t the accumulator fragment of an m16n8 tile: rows t / 4 and
+        // t / 4 + 8 -- the two tap digits of one (j, component) -- and columns 2 (t % 4), + 1 of every
+        // 8-column group (tools/probe_tmem_ld_shapes.cu); the re and im halves are the two 16-lane loads.
+        // Per output and component, as in the other kernels:
+        //   y = lo_d0 + ((lo_d1 + hi_d0) << 8) + (hi_d1 << 16)  mod 2^32, bits [16, 32) kept (fromQ)
+        // warp = (lane quadrant = 8 values of j, half of the windows); a store instruction writes 8 consecutive
+        // outputs (32 bytes) of 4 windows.
+        const int quad = warp & 3, half = warp >> 2, q = lane & 3;
+        const unsigned lane_addr = tmem_base + ((unsigned)(32 * quad) << 16);
+        unsigned *out32 = static_cast<unsigned *>(a.out);
+        for (int i = 0; i < ntl; i++) {
+            const int s = i & 1;
+            const unsigned ph = (unsigned)(i >> 1) & 1;
+            const long long tile = first + (long long)i * step;
+            // output of (window n0 + 2 q, j); the thread's others are whole windows (32 outputs) further on
+            const long long o00 = tile * TILE + 32LL * ((NW / 2) * half + 2 * q) + 8 * quad + (lane >> 2);
+            const bool whole = (tile + 1) * TILE <= a.n_out;
+            const unsigned tcol = lane_addr + (unsigned)(s * COLS + (NW / 2) * half);
+            unsigned *const ot = out32 + o00;
+            watched_wait(&acc_full[s], ph, w0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < NW / 32; c++) {
+                unsigned lr[8], li[8], hr[8], hi[8];      // limb (lo / hi) x component (re / im)
+                tmem_ld16x256b_x2(tcol + 16 * c, lr);
+                tmem_ld16x256b_x2(tcol + (16u << 16) + 16 * c, li);
+                tmem_ld16x256b_x2(tcol + NW + 16 * c, hr);
+                tmem_ld16x256b_x2(tcol + (16u << 16) + NW + 16 * c, hi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == NW / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[s]);
+                }
+                unsigned *o = ot + 32 * 16 * c;
+                unsigned res[4];
+#pragma unroll
+                for (int g = 0; g < 2; g++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int k = 4 * g + e;                              // digit 0 at k, digit 1 at k + 2
+                        const unsigned yr = lr[k] + ((lr[k + 2] + hr[k]) << 8) + (hr[k + 2] << 16);
+                        const unsigned yi = li[k] + ((li[k + 2] + hi[k]) << 8) + (hi[k + 2] << 16);
+                        const int w = 32 * (8 * g + e);                       // window 8 g + 2 q + e of the chunk
+                        res[2 * g + e] = prmt_u(yr, yi, 0x7632);
+                        if (whole) __stcg(o + w, res[2 * g + e]);
+                    }
+                if (!whole)       // the stream's last tile
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (o00 + 32 * 16 * c + 32 * (8 * (k >> 1) + (k & 1)) < a.n_out) o[32 * (8 * (k >> 1) + (k & 1))] = res[k];
+            }
+        }
     } else {
         // ======================================================================== epilogue
         // thread = (row m = TMEM lane, half of the row's 32 outputs); per output and component:
@@ -239,8 +392,8 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
         for (int i = 0; i < ntl; i++) {
             const int s = i & 1;
             const unsigned ph = (unsigned)(i >> 1) & 1;
-            const long long tile = first + (long long)i * step, orow = tile * kU32Tile + 32LL * m + 16 * half;
-            timed_wait(&acc_full[s], ph, w0);
+            const long long tile = first + (long long)i * step, orow = tile * TILE + 32LL * m + 16 * half;
+            watched_wait(&acc_full[s], ph, w0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < 16 / CH; c++) {
@@ -291,14 +444,19 @@ __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmm
         long long *d = a.dbg + (size_t)blockIdx.x * 8;
         if (warp == 0) { d[0] = clock64() - t_begin; d[1] = ntl; d[7] = w0; }
         if (warp == kU32EpiWarps) { d[5] = w0; d[6] = w1; a.dbg[(size_t)gridDim.x * 8 + 2 * blockIdx.x] = t_conv; a.dbg[(size_t)gridDim.x * 8 + 2 * blockIdx.x + 1] = t_fence; }
-        if (warp == kU32EpiWarps + kU32StageWarps) { d[3] = w0; d[4] = w1; }
-        if (warp == kU32EpiWarps + kU32StageWarps + 1) d[2] = w0;
+        if (warp == kU32EpiWarps + SW) { d[3] = w0; d[4] = w1; }
+        if (warp == kU32EpiWarps + SW + 1) d[2] = w0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ALLOC) : "memory");
 }
+
+template <int DC>
+__global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmma32Args a) { fir_umma32_body<DC, false, 0>(a); }
+template <int NBT>
+__global__ void __launch_bounds__(kU32tThreads, 1) fir_umma32t_kernel(const FirUmma32Args a) { fir_umma32_body<2, true, NBT>(a); }
 
 // ------------------------------------------------------------------------------- host ---
 // balanced byte digits (d0, d1) of q = d0 + 256 d1, both in [-128, 127]; false if q does not fit
@@ -310,19 +468,25 @@ static bool two_digits(long long q, int8_t &d0, int8_t &d1)
     return true;
 }
 
-static size_t u32_fixed_smem(int dc, int NB, int PLa) { return (size_t)dc * NB * (32 * dc * 2) * 32 + 2 * ((size_t)dc * 2 * PLa) + 1024; }
-
-int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force)
+static size_t u32_fixed_smem(int dc, int NB, int PLa, bool swapped = false)
 {
-    p.ready = false;
+    return (swapped ? 0 : (size_t)dc * NB * (32 * dc * 2) * 32) + 2 * ((size_t)dc * 2 * PLa) + 1024;
+}
+
+// swap: 1 forces the operand-swapped kernel where it applies, 0 forbids it, -1 follows B200C_UMMA32T
+int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double *taps, bool force, int swap)
+{
+    p.ready = false; p.swapped = false;
     const bool enabled = [] { const char *e = std::getenv("B200C_UMMA32"); return !e || std::atoi(e) != 0; }();   // B200C_UMMA32=0: stay on fir_umma_kernel
     if (!base.ready || !(enabled || force) || base.nlt != 2) return B200C_OK;
     const int K = base.K, dc = base.dc, tc = base.tc, NQ = dc * 2, N = 32 * NQ;
     const int NB = (K + 31 + 31) / 32;
-    const int PL = kU32Tile + 32 * NB, PLa = (PL + 255) / 256 * 256;
+    static const bool swap_default = [] { const char *e = std::getenv("B200C_UMMA32T"); return e && std::atoi(e) != 0; }();
+    const bool swapped = dc == 2 && NB <= kU32tMaxNB && (swap < 0 ? swap_default : swap != 0);
+    const int PL = (swapped ? kU32tTile : kU32Tile) + 32 * NB, PLa = (PL + 255) / 256 * 256;
     // B tiles, two plane stages and at least a 3-deep landing ring must fit
-    if (u32_fixed_smem(dc, NB, PLa) + 3 * (size_t)PL * dc * 2 > 200 * 1024) return B200C_OK;
-    std::vector<uint8_t> bm((size_t)dc * NB * N * 32, 0);
+    if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * (size_t)PL * dc * 2 > 200 * 1024) return B200C_OK;
+    std::vector<uint8_t> bm((size_t)dc * NB * N * 32, 0), am(swapped ? (size_t)dc * NB * N * 32 : 0, 0);
     for (int d = 0; d < K; d++)
         for (int c = 0; c < tc; c++) {
             const long long q = (long long)(int32_t)(long long)std::ldexp(taps[(size_t)d * tc + c], 16);
@@ -347,6 +511,12 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
                         const size_t at = (size_t)(uses[u].dcx * NB + b) * N * 32 + (size_t)(col / 8) * 256 + (size_t)(jj / 16) * 128 +
                                           (size_t)(col % 8) * 16 + (jj % 16);
                         bm[at] = (uint8_t)(uses[u].negate ? neg[l] : pos[l]);
+                        // the same element of the swapped kernel's A tile: row-major, 32 bytes per row, rows ordered so
+                        // that one thread of the epilogue's 16-lane tensor-memory loads holds both digits
+                        if (swapped) {
+                            const int row = 32 * (n / 8) + 16 * uses[u].cls + 8 * l + n % 8;   // TMEM lane: see the epilogue
+                            am[((size_t)(uses[u].dcx * NB + b) * N + row) * 32 + jj] = bm[at];
+                        }
                     }
                 }
         }
@@ -357,7 +527,16 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
         p.capacity = bm.size();
     }
     B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
-    p.K = K; p.NB = NB; p.dc = dc;
+    if (swapped) {
+        if (am.size() > p.a_capacity) {
+            if (p.d_amat) cudaFree(p.d_amat);
+            p.d_amat = nullptr; p.a_capacity = 0;
+            B200C_CUDA_TRY(cudaMalloc(&p.d_amat, am.size()));
+            p.a_capacity = am.size();
+        }
+        B200C_CUDA_TRY(cudaMemcpy(p.d_amat, am.data(), am.size(), cudaMemcpyHostToDevice));
+    }
+    p.K = K; p.NB = NB; p.dc = dc; p.swapped = swapped;
     p.ready = true;
     return B200C_OK;
 }
@@ -365,36 +544,74 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
 void fir_umma32_destroy(FirUmma32Plan &p)
 {
     if (p.d_bmat) cudaFree(p.d_bmat);
-    p.d_bmat = nullptr; p.capacity = 0; p.ready = false;
+    if (p.d_amat) cudaFree(p.d_amat);
+    p.d_bmat = nullptr; p.capacity = 0; p.d_amat = nullptr; p.a_capacity = 0; p.ready = false; p.swapped = false;
 }
 
-template <int DC>
+static_assert(kU32tMaxNB == 8, "launch_u32 instantiates fir_umma32t_kernel for 1..8 k-blocks");
+template <int DC, bool TS>
 static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
 {
-    auto kern = fir_umma32_kernel<DC>;
-    static thread_local bool configured[16] = {false};
+    void (*kern)(FirUmma32Args) = fir_umma32_kernel<DC>;
+    if (TS) {
+        switch (a.NB) {
+        case 1: kern = fir_umma32t_kernel<1>; break;
+        case 2: kern = fir_umma32t_kernel<2>; break;
+        case 3: kern = fir_umma32t_kernel<3>; break;
+        case 4: kern = fir_umma32t_kernel<4>; break;
+        case 5: kern = fir_umma32t_kernel<5>; break;
+        case 6: kern = fir_umma32t_kernel<6>; break;
+        case 7: kern = fir_umma32t_kernel<7>; break;
+        default: kern = fir_umma32t_kernel<8>; break;
+        }
+    }
+    static thread_local bool configured[16][9] = {{false}};
     int dev = 0;
     B200C_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 16 && !configured[dev]) {
+    const int slot = TS ? a.NB : 0;
+    if (dev < 16 && !configured[dev][slot]) {
         B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        configured[dev] = true;
+        configured[dev][slot] = true;
     }
     static const int ring = [] { const char *e = std::getenv("B200C_UMMA_RING"); return e ? std::atoi(e) : kU32MaxRing; }();
-    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa), one = (size_t)a.PL * DC * 2;
+    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa, TS), one = (size_t)a.PL * DC * 2;
     a.R = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, std::min(ring, kU32MaxRing)), (216 * 1024 - fixed) / one));
     // one CTA per SM: its two accumulator stages take all (complex) or half (real) of tensor memory
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);
     const int grid = (int)std::min<long long>(a.ntiles, (long long)sm_count);
     static const bool dbg = std::getenv("B200C_UMMA_DBG") != nullptr;
+    unsigned long long *watch = nullptr;
     if (dbg) {
         B200C_CUDA_TRY(cudaMalloc(&a.dbg, (size_t)grid * 10 * sizeof(long long)));
         B200C_CUDA_TRY(cudaMemset(a.dbg, 0, (size_t)grid * 10 * sizeof(long long)));
+        // watchdog records in host-mapped memory: readable after the kernel trapped
+        B200C_CUDA_TRY(cudaHostAlloc(&watch, ((size_t)grid * 32 + 8) * sizeof(unsigned long long), cudaHostAllocMapped));
+        std::memset(watch, 0, ((size_t)grid * 32 + 8) * sizeof(unsigned long long));
+        unsigned long long *dwatch = nullptr;
+        B200C_CUDA_TRY(cudaHostGetDevicePointer(&dwatch, watch, 0));
+        B200C_CUDA_TRY(cudaMemcpyToSymbol(g_umma_watch, &dwatch, sizeof(dwatch)));
     }
-    kern<<<grid, kU32Threads, smem, stream>>>(a);
+    kern<<<grid, TS ? kU32tThreads : kU32Threads, smem, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
     if (dbg) {
         std::vector<long long> h((size_t)grid * 10);
-        B200C_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (cudaStreamSynchronize(stream) != cudaSuccess) {
+            const unsigned long long *names = watch + (size_t)grid * 32;
+            static const char *const what[6] = {"raw_full", "raw_empty", "planes_full", "planes_empty", "acc_full", "acc_empty"};
+            int shown = 0;
+            for (int g = 0; g < grid && shown < 40; g++)
+                for (int w = 0; w < 32 && shown < 40; w++) {
+                    const unsigned long long r = watch[(size_t)g * 32 + w];
+                    if (!(r & 1)) continue;
+                    const unsigned long long addr = r >> 8;
+                    int which = -1;
+                    for (int k = 0; k < 6; k++) if (addr >= names[k] && (which < 0 || names[k] > names[which])) which = k;
+                    std::fprintf(stderr, "umma32 watchdog: block %d warp %d stuck on %s[%llu] parity %llu\n", g, w, which >= 0 ? what[which] : "?",
+                                 which >= 0 ? (addr - names[which]) / 8 : 0ull, (r >> 1) & 1);
+                    shown++;
+                }
+            return B200C_ERR_CUDA;
+        }
         B200C_CUDA_TRY(cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.dbg);
         double s8[8] = {0};
@@ -413,11 +630,13 @@ int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems,
 {
     if (n_out == 0) return B200C_OK;
     FirUmma32Args a;
-    a.in = d_in; a.out = d_out; a.bmat = p.d_bmat;
+    const int tile = p.swapped ? kU32tTile : kU32Tile;
+    a.in = d_in; a.out = d_out; a.bmat = p.swapped ? p.d_amat : p.d_bmat;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out;
-    a.ntiles = ((long long)n_out + kU32Tile - 1) / kU32Tile;
-    a.K = p.K; a.NB = p.NB; a.PL = kU32Tile + 32 * p.NB; a.PLa = (a.PL + 255) / 256 * 256; a.R = 2; a.dbg = nullptr;
-    return p.dc == 1 ? launch_u32<1>(a, sm_count, stream) : launch_u32<2>(a, sm_count, stream);
+    a.ntiles = ((long long)n_out + tile - 1) / tile;
+    a.K = p.K; a.NB = p.NB; a.PL = tile + 32 * p.NB; a.PLa = (a.PL + 255) / 256 * 256; a.R = 2; a.dbg = nullptr;
+    if (p.swapped) return launch_u32<2, true>(a, sm_count, stream);
+    return p.dc == 1 ? launch_u32<1, false>(a, sm_count, stream) : launch_u32<2, false>(a, sm_count, stream);
 }
 
 } // namespace b200c

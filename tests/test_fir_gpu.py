@@ -507,7 +507,7 @@ def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, s
     _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
 
 
-@pytest.mark.parametrize("kernel", ["fir_imma_kernel", "fir_umma_kernel", "fir_umma32_kernel"])
+@pytest.mark.parametrize("kernel", ["fir_imma_kernel", "fir_umma_kernel", "fir_umma32_kernel", "fir_umma32t_kernel"])
 @pytest.mark.parametrize("dt", ["CI16", "I16"])
 def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     """A ring-buffer window starts at any element: the kernel's 16-byte loads and 8-byte stores
@@ -517,7 +517,10 @@ def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     code = getattr(oracle, dt)
     rng = np.random.default_rng(99)
     taps = rng.standard_normal(64) * 0.05
-    with _with_algo({"fir_imma_kernel": "imma", "fir_umma_kernel": "umma", "fir_umma32_kernel": "umma32"}[kernel]):
+    if kernel == "fir_umma32t_kernel" and dt == "I16":
+        pytest.skip("the operand-swapped kernel is the complex-data formulation (M = 128 rows)")
+    with _with_algo({"fir_imma_kernel": "imma", "fir_umma_kernel": "umma", "fir_umma32_kernel": "umma32",
+                     "fir_umma32t_kernel": "umma32t"}[kernel]):
         f = FirFilter(code, "REAL")
         f.set_taps(taps)
     assert f.kernel == kernel
@@ -580,6 +583,77 @@ def test_umma32_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
             assert f.kernel == "fir_umma32_kernel"
         assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
         _compare(oracle, code, y, y_ref, f"umma32 K={ntaps} n={n_new} zt={zero_tail}")
+
+
+@pytest.mark.parametrize("ntaps", [2, 33, 34, 65, 66, 128, 129, 193, 194, 225])
+@pytest.mark.parametrize("taps_type", ["COMPLEX", "REAL"])
+def test_umma32t_path_is_bit_exact(oracle, cuda_device, taps_type, ntaps):
+    """The operand-swapped formulation (fir_umma32t_kernel): the tap-digit tiles are the A operand and sit in
+    tensor memory, the swizzled data planes are the B operand (96 windows of 32 outputs per tile), the epilogue
+    combines digits and components across TMEM lanes with warp shuffles.  Tap counts either side of the k-block
+    boundaries up to the tensor-memory limit (8 k-blocks), tiles of 3072 outputs ending mid-window, zero tail,
+    full-scale input."""
+    code = oracle.CI16
+    cx = taps_type == "COMPLEX"
+    rng = np.random.default_rng(ntaps * 17 + 3)
+    taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    if cx:
+        taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    for n_new, zero_tail in ((1, False), (31, False), (32, False), (33, False), (3071, False), (3072, False), (3073, False),
+                             (5 * 3072 + 1001, False), (148 * 3072 + 17, False), (700001, False), (1000, True), (1, True)):
+        x = _rand_input(oracle, code, ntaps - 1 + n_new, rng, full_scale=True)
+        y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x, zero_tail=zero_tail)
+        with _with_algo("umma32t"):
+            y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
+            assert f.kernel == "fir_umma32t_kernel"
+        assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
+        _compare(oracle, code, y, y_ref, f"umma32t K={ntaps} n={n_new} zt={zero_tail}")
+
+
+@pytest.mark.parametrize("algo,kernel", [("umma32", "fir_umma32_kernel"), ("umma32t", "fir_umma32t_kernel")])
+def test_umma32_kernels_over_many_tiles_per_cta(oracle, cuda_device, algo, kernel):
+    """Twenty-odd tiles per persistent CTA: both accumulator stages and every slot of the bulk-copy landing ring are
+    reused several times (the short cases above give a CTA two tiles at most, which never waits on a released stage).
+    Oracle windows at the start, inside late tiles and at the ragged end; the whole output against the other variant."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    code = oracle.CI16
+    rng = np.random.default_rng(2024)
+    ntaps = 128
+    taps = (rng.standard_normal(ntaps) + 1j * rng.standard_normal(ntaps)) * 0.3 / np.sqrt(ntaps)
+    n = 21 * 148 * 3072 + 777
+    x = torch.randint(-32768, 32767, (ntaps - 1 + n, 2), dtype=torch.int16, device=cuda_device)
+    outs = {}
+    for a in ("umma32", "umma32t"):
+        with _with_algo(a):
+            f = FirFilter(code, "COMPLEX")
+            f.set_taps(taps)
+        y, cons, prod = f.run(x)
+        torch.cuda.synchronize()
+        assert (cons, prod) == (n, n)
+        outs[a] = (f.kernel, y[:prod].clone())
+    assert outs[algo][0] == kernel
+    y = outs[algo][1]
+    wlen = 20_000
+    for w0 in (0, 3 * 148 * 3072 - 5000, 10 * 148 * 4096 + 123, n // 2, n - wlen):
+        seg = x[w0: w0 + ntaps - 1 + wlen].cpu().numpy()
+        y_ref, _, p_ref = oracle.fir(code, True, taps, 1, 1, seg)
+        _compare(oracle, code, y[w0: w0 + p_ref].cpu().numpy(), y_ref, f"{algo} window at {w0}")
+    assert torch.equal(outs["umma32"][1], outs["umma32t"][1])
+
+
+def test_umma32t_falls_back_beyond_its_tensor_memory_budget(oracle, cuda_device):
+    """More than 8 k-blocks of tap tiles do not fit beside the accumulators: the original formulation runs."""
+    from pothoscomms_b200 import FirFilter
+    taps = np.random.default_rng(5).standard_normal(300) * 0.01
+    with _with_algo("umma32t"):
+        f = FirFilter(oracle.CI16, "REAL")
+        f.set_taps(taps)
+    assert f.kernel == "fir_umma32_kernel"
+    with _with_algo("umma32t"):
+        f = FirFilter(oracle.I16, "REAL")
+        f.set_taps(taps[:100])
+    assert f.kernel == "fir_umma32_kernel"
 
 
 @pytest.mark.parametrize("M,L", [(2, 1), (1, 2), (3, 1), (1, 3), (2, 3), (3, 2), (4, 3), (3, 4), (4, 4), (2, 2), (1, 4), (4, 1)])
