@@ -47,12 +47,15 @@ constexpr int kU32EpiWarps = 8, kU32StageWarps = 8, kU32MaxRing = 8;
 constexpr int kU32Batch = 5;      // stager loads in flight per thread: their latency under the MMA's operand traffic is long
 constexpr int kU32Threads = 32 * (kU32EpiWarps + kU32StageWarps + 2);
 // the swapped kernel is bound by instruction issue (ncu r02ad: 1.3 warp instructions per sample, 47 % of them the
-// stagers' -- mostly per-tile overhead of eight warps converting three items each): four stager warps with
-// compile-time sizes
-constexpr int kU32tStageWarps = 4;
+// stagers' -- mostly per-tile overhead of eight warps converting three items each): compile-time sizes, and six
+// stager warps.  Measured at C2 (profiles/r02ah): 4 / 6 / 8 stager warps and loading all of a tile's accumulators at once
+// instead of in three chunks all land within 0.70-0.71 of the HBM roofline: the tile time (~1270 cycles) is the 960 cycles
+// of the 20 MMAs (8192 MAC / clk, tools/probe_umma_rate.cu) plus the barrier hand-offs around them
+constexpr int kU32tStageWarps = 6;
+constexpr int kU32tPlaneStages = 3;   // the stagers run one tile further ahead of the MMAs than the two accumulator stages allow
 constexpr int kU32tThreads = 32 * (kU32EpiWarps + kU32tStageWarps + 2);
 
-template <int DC, bool TS, int NBT>   // NBT: the k-block count at compile time (0: a.NB)
+template <int DC, bool TS, int NBT, int SWT = kU32StageWarps>   // NBT: the k-block count at compile time (0: a.NB)
 __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
 {
     extern __shared__ __align__(1024) unsigned char smem_v[];
@@ -63,15 +66,17 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     constexpr int COLS = TS ? 2 * NW : 2 * N;      // lo and hi regions
     constexpr int ALLOC = TS ? 512 : 2 * COLS;     // two stages: 512 (complex) / 256 (real) columns
     constexpr int ACOL = 2 * COLS;                 // TS: first column of the tap tiles
-    constexpr int SW = TS ? kU32tStageWarps : kU32StageWarps, NTHR = TS ? kU32tThreads : kU32Threads;
+    constexpr int SW = SWT, NTHR = 32 * (kU32EpiWarps + SW + 2);
+    constexpr int PS = TS ? kU32tPlaneStages : 2;  // plane stages (the accumulators have two)
     static_assert(!TS || DC == 2, "the swapped formulation needs M = 128 = 32 outputs x 2 components x 2 digits");
     constexpr int NPL = DC * 2, ESZ = DC * 2;
     constexpr int CH = 16 / NQ;                    // outputs per 16-column epilogue chunk
     const int NB = NBT ? NBT : a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
     unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024); TS: none
     unsigned char *planes = bmat + (TS ? 0 : (size_t)DC * NB * N * 32);   // [2][NPL][PLa], 256-byte aligned, swizzled
-    unsigned char *raw = planes + 2 * (size_t)NPL * PLa;             // [R][PL * ESZ]
-    __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[2], planes_empty[2], acc_full[2], acc_empty[2];
+    unsigned char *raw = planes + PS * (size_t)NPL * PLa;            // [R][PL * ESZ]
+    __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[4], planes_empty[4], acc_full[2], acc_empty[2];
+    static_assert(PS <= 4, "planes_full / planes_empty hold four stages");
     __shared__ unsigned tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -84,10 +89,8 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
         // every stager / epilogue thread waits and arrives itself: one lane per warp followed by a warp barrier measured
         // 2x slower (profiles/r02ab: the stagers' proxy fence + arrival went from ~80 to ~1800 cycles per tile)
         for (int r = 0; r < R; r++) { mbar_init(&raw_full[r], 1); mbar_init(&raw_empty[r], 32 * SW); }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&planes_full[s], 32 * SW); mbar_init(&planes_empty[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * kU32EpiWarps);
-        }
+        for (int s = 0; s < PS; s++) { mbar_init(&planes_full[s], 32 * SW); mbar_init(&planes_empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * kU32EpiWarps); }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ALLOC) : "memory");
@@ -131,7 +134,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
         if (lane == 0)
             for (int i = 0, r = 0, ph = 0; i < ntl; i++) {
                 const long long tile = first + (long long)i * step;
-                watched_wait(&raw_empty[r], (unsigned)ph ^ 1, w0);
+                watched_wait(a.dbg != nullptr, &raw_empty[r], (unsigned)ph ^ 1, w0);
                 if (bulk_ok(tile))
                     bulk_load(raw + (size_t)r * PL * ESZ, static_cast<const unsigned char *>(a.in) + (size_t)tile * TILE * ESZ,
                               (unsigned)(PL * ESZ), &raw_full[r]);
@@ -157,10 +160,11 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             constexpr unsigned long long kAStep = 32 >> 4, kBStep = (N * 32) >> 4;   // start-address field is in 16-byte units
             // the tile loop is unrolled over the two stages so that every index below is a compile-time
             // constant (dynamically indexed descriptor arrays would live in local memory)
-            auto issue_tile = [&](auto stage_c, const unsigned ph) {
+            // ps / pph: plane stage and its phase (== S, ph with two plane stages)
+            auto issue_tile = [&](auto stage_c, const unsigned ph, const int ps, const unsigned pph) {
                 constexpr int S = decltype(stage_c)::value;
-                watched_wait(&planes_full[S], ph, w0);
-                watched_wait(&acc_empty[S], ph ^ 1, w1);
+                watched_wait(a.dbg != nullptr, &planes_full[ps], pph, w0);
+                watched_wait(a.dbg != nullptr, &acc_empty[S], ph ^ 1, w1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if constexpr (TS) {
                     // D'[m' = (output j, component, digit)][n' = window] += taps[m'][k] . plane[32 (n' + b) + k]:
@@ -172,7 +176,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                         constexpr unsigned idesc_lo = umma_idesc_i8_ab(true, false, NW), idesc_hi = umma_idesc_i8_ab(true, true, NW);
 #pragma unroll
                         for (int dc = 0; dc < DC; dc++) {
-                            unsigned long long bd = a_base[S][2 * dc + dl];
+                            unsigned long long bd = a_base[0][2 * dc + dl] + (unsigned long long)ps * (unsigned long long)((NPL * PLa) >> 4);
                             unsigned at = tmem_base + (unsigned)(ACOL + 8 * dc * NB);
                             if (dc == 0) { umma_i8_ts_first(d, at, bd, dl ? idesc_hi : idesc_lo); bd += kAStep; at += 8; }
                             if constexpr (NBT > 0) {
@@ -208,13 +212,17 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                         }
                     }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[S])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&planes_empty[ps])) : "memory");
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[S])) : "memory");
             };
+            int ps = 0;
+            unsigned pph = 0;
+            auto next_planes = [&] { if (++ps == PS) { ps = 0; pph ^= 1; } };
             for (int i = 0; i < ntl; i += 2) {
                 const unsigned ph = (unsigned)(i >> 1) & 1;
-                issue_tile(std::integral_constant<int, 0>{}, ph);
-                if (i + 1 < ntl) issue_tile(std::integral_constant<int, 1>{}, ph);
+                issue_tile(std::integral_constant<int, 0>{}, ph, ps, pph);
+                next_planes();
+                if (i + 1 < ntl) { issue_tile(std::integral_constant<int, 1>{}, ph, ps, pph); next_planes(); }
             }
         }
     } else if (warp >= kU32EpiWarps) {
@@ -224,16 +232,15 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
         const int st = tid - 32 * kU32EpiWarps;
         constexpr int NST = 32 * SW;
         const int nq = PL / 4;
-        for (int i = 0, r = 0, rph = 0; i < ntl; i++) {
-            const int s = i & 1;
-            const unsigned ph = (unsigned)(i >> 1) & 1;
+        for (int i = 0, r = 0, rph = 0, s = 0, ph = 0; i < ntl; i++) {      // s / ph: plane stage and its phase
             const long long tile = first + (long long)i * step, o0 = tile * TILE;
             const bool landed = bulk_ok(tile);
-            watched_wait(&raw_full[r], (unsigned)rph, w0);
-            watched_wait(&planes_empty[s], ph ^ 1, w1);
+            watched_wait(a.dbg != nullptr, &raw_full[r], (unsigned)rph, w0);
+            watched_wait(a.dbg != nullptr, &planes_empty[s], (unsigned)ph ^ 1, w1);
             unsigned *pl = reinterpret_cast<unsigned *>(planes + (size_t)s * NPL * PLa);
             const unsigned char *rw = raw + (size_t)r * PL * ESZ;
-            const long long t_c0 = clock64();
+            const bool timed = a.dbg != nullptr;
+            const long long t_c0 = timed ? clock64() : 0;
             if (TS && landed) {
                 // every size is a compile-time constant here: item q = st + 128 u of this thread (four samples: 16 raw
                 // bytes -> one word of each plane) sits 2048 bytes further in the landing slot and 512 bytes further
@@ -320,13 +327,13 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                     }
                 }
             }
-            const long long t_c1 = clock64();
+            const long long t_c1 = timed ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&planes_full[s]);
             mbar_arrive(&raw_empty[r]);
-            const long long t_c2 = clock64();
-            t_conv += t_c1 - t_c0; t_fence += t_c2 - t_c1;
+            if (timed) { const long long t_c2 = clock64(); t_conv += t_c1 - t_c0; t_fence += t_c2 - t_c1; }
             if (++r == R) { r = 0; rph ^= 1; }
+            if (++s == PS) { s = 0; ph ^= 1; }
         }
     } else if constexpr (TS) {
         // ============================================================= epilogue (swapped operands)
@@ -350,7 +357,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             const bool whole = (tile + 1) * TILE <= a.n_out;
             const unsigned tcol = lane_addr + (unsigned)(s * COLS + (NW / 2) * half);
             unsigned *const ot = out32 + o00;
-            watched_wait(&acc_full[s], ph, w0);
+            watched_wait(a.dbg != nullptr, &acc_full[s], ph, w0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c = 0; c < NW / 32; c++) {
@@ -393,7 +400,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             const int s = i & 1;
             const unsigned ph = (unsigned)(i >> 1) & 1;
             const long long tile = first + (long long)i * step, orow = tile * TILE + 32LL * m + 16 * half;
-            watched_wait(&acc_full[s], ph, w0);
+            watched_wait(a.dbg != nullptr, &acc_full[s], ph, w0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < 16 / CH; c++) {
@@ -456,7 +463,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
 template <int DC>
 __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmma32Args a) { fir_umma32_body<DC, false, 0>(a); }
 template <int NBT>
-__global__ void __launch_bounds__(kU32tThreads, 1) fir_umma32t_kernel(const FirUmma32Args a) { fir_umma32_body<2, true, NBT>(a); }
+__global__ void __launch_bounds__(kU32tThreads, 1) fir_umma32t_kernel(const FirUmma32Args a) { fir_umma32_body<2, true, NBT, kU32tStageWarps>(a); }
 
 // ------------------------------------------------------------------------------- host ---
 // balanced byte digits (d0, d1) of q = d0 + 256 d1, both in [-128, 127]; false if q does not fit
@@ -470,7 +477,7 @@ static bool two_digits(long long q, int8_t &d0, int8_t &d1)
 
 static size_t u32_fixed_smem(int dc, int NB, int PLa, bool swapped = false)
 {
-    return (swapped ? 0 : (size_t)dc * NB * (32 * dc * 2) * 32) + 2 * ((size_t)dc * 2 * PLa) + 1024;
+    return (swapped ? 0 : (size_t)dc * NB * (32 * dc * 2) * 32) + (swapped ? kU32tPlaneStages : 2) * ((size_t)dc * 2 * PLa) + 1024;
 }
 
 // swap: 1 forces the operand-swapped kernel where it applies, 0 forbids it, -1 follows B200C_UMMA32T
@@ -481,7 +488,7 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
     if (!base.ready || !(enabled || force) || base.nlt != 2) return B200C_OK;
     const int K = base.K, dc = base.dc, tc = base.tc, NQ = dc * 2, N = 32 * NQ;
     const int NB = (K + 31 + 31) / 32;
-    static const bool swap_default = [] { const char *e = std::getenv("B200C_UMMA32T"); return e && std::atoi(e) != 0; }();
+    static const bool swap_default = [] { const char *e = std::getenv("B200C_UMMA32T"); return !e || std::atoi(e) != 0; }();   // =0: the original formulation
     const bool swapped = dc == 2 && NB <= kU32tMaxNB && (swap < 0 ? swap_default : swap != 0);
     const int PL = (swapped ? kU32tTile : kU32Tile) + 32 * NB, PLa = (PL + 255) / 256 * 256;
     // B tiles, two plane stages and at least a 3-deep landing ring must fit
@@ -565,10 +572,10 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         default: kern = fir_umma32t_kernel<8>; break;
         }
     }
-    static thread_local bool configured[16][9] = {{false}};
+    const int threads = TS ? kU32tThreads : kU32Threads, slot = TS ? a.NB : 0;
+    static thread_local bool configured[16][16] = {{false}};
     int dev = 0;
     B200C_CUDA_TRY(cudaGetDevice(&dev));
-    const int slot = TS ? a.NB : 0;
     if (dev < 16 && !configured[dev][slot]) {
         B200C_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured[dev][slot] = true;
@@ -591,7 +598,7 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         B200C_CUDA_TRY(cudaHostGetDevicePointer(&dwatch, watch, 0));
         B200C_CUDA_TRY(cudaMemcpyToSymbol(g_umma_watch, &dwatch, sizeof(dwatch)));
     }
-    kern<<<grid, TS ? kU32tThreads : kU32Threads, smem, stream>>>(a);
+    kern<<<grid, threads, smem, stream>>>(a);
     B200C_CUDA_TRY(cudaGetLastError());
     if (dbg) {
         std::vector<long long> h((size_t)grid * 10);

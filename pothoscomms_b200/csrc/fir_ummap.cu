@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kUPThreads, 1) fir_ummap_kernel(const FirUmmaP
             }
     } else if (warp == kUPEpiWarps + kUPStageWarps) {
         // ====================================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             const unsigned idesc_lo = umma_idesc_i8(false, Nh), idesc_hi = umma_idesc_i8(true, Nh);
             // A: plane (e, dc, dl): row m = plane[16 m + 32 b ..] (SBO 128, LBO 16), start address = stage + table offset
             const unsigned long long a_stage0 = umma_smem_desc(smem_u32(planes), 16, 128, 0);

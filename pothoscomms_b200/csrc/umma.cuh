@@ -165,15 +165,19 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
     return ok != 0;
 }
 
+
 __device__ __forceinline__ void timed_wait(unsigned long long *bar, unsigned parity, long long &acc)
 {
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    while (!mbar_try_wait(bar, parity)) {}
     acc += clock64() - t0;
 }
 
-__device__ __forceinline__ void watched_wait(unsigned long long *bar, unsigned parity, long long &acc)
+__device__ __forceinline__ void watched_wait(bool timed, unsigned long long *bar, unsigned parity, long long &acc)
 {
+    // the phase is usually complete, or completes within the first suspended try: no clock reads on that path unless
+    // the role timers are on
+    if (!timed && mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     bool noted = false;
     while (!mbar_try_wait(bar, parity)) {

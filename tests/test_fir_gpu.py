@@ -502,7 +502,9 @@ def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, s
     x = _rand_input(oracle, code, 9000, rng, full_scale=True)
     y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x)
     y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x)
-    assert f.kernel == ("fir_umma32_kernel" if limbs == 2 else "fir_imma_kernel")   # tcgen05 path: 2-limb taps
+    # tcgen05 paths take 2-limb taps: the operand-swapped kernel for complex data, the original one for real data
+    two_limb = "fir_umma32t_kernel" if dt == "CI16" else "fir_umma32_kernel"
+    assert f.kernel == (two_limb if limbs == 2 else "fir_imma_kernel")
     assert (cons, prod) == (c_ref, p_ref)
     _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
 
