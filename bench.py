@@ -528,8 +528,12 @@ def bench_stream(ctx: Ctx, name: str, steps: int, warmup: int, e2e: bool, cpu: b
         peak_i8 = 2 * ctx.peaks.get("bf16_tflops", 1590.0)
         roofline["tensor"] = {"bound": "tensor", "achieved": 2 * macs / (kernel_ms * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s",
                               "frac": 2 * macs / (kernel_ms * 1e-3) / 1e12 / peak_i8,
-                              "note": "int8 MAC x 2 of the limb GEMMs (2 data limbs x 2 tap digits), dense int8 peak taken as 2 x "
-                                      "the measured bf16 rate; the kernel is bound by shared-memory operand fetch (ncu l1tex), see DESIGN 4.6"}
+                              "note": "useful int8 MAC x 2 of the limb GEMMs (2 data limbs x 2 tap digits; Toeplitz padding not counted), "
+                                      "dense int8 peak taken as 2 x the measured bf16 rate. " +
+                                      ("fir_umma32t_kernel: tap tiles in tensor memory; ncu (profiles/r02ai_prof_umma32t_c2.txt) has the "
+                                       "imma sub-pipe active 75 % of cycles at 1.72 GHz: tensor-pipe bound, see DESIGN 4.6"
+                                       if kernel == "fir_umma32t_kernel" else
+                                       "bound by shared-memory operand fetch (ncu l1tex), see DESIGN 4.6")}
     flops = {"c1": 512, "c1_real": 256, "headline": 2048, "c3": 510, "c5": 8192}.get(name)
     if flops and not kernel.startswith("fir_os"):
         roofline["fp32_tflops"] = flops * n_seg / (kernel_ms * 1e-3) / 1e12

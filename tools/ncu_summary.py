@@ -18,7 +18,9 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__inst_executed.sum", "smsp__cycles_active.avg", "launch__registers_per_thread", "launch__grid_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum"]
+        "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+        "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg.per_second"]
 for k in want:
     if k in m: print(f"{k}: {m[k][0]} {m[k][1]}")
 for h in hdr:
