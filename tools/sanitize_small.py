@@ -35,9 +35,13 @@ def fir(dt, tt, ntaps, M, L, n, algo=None):
     print(dt, tt, ntaps, M, L, n, f.kernel, c, p)
 
 
-for algo in ("umma32", "umma", "imma", "direct"):
+for algo in ("umma32t", "umma32", "umma", "imma", "direct"):
     fir("complex_int16", "COMPLEX", 128, 1, 1, 20000, algo)
     fir("int16", "REAL", 64, 1, 1, 9001, algo)
+# several tiles per persistent CTA: the accumulator stages, plane stages and landing-ring slots of the tcgen05 kernels are reused
+fir("complex_int16", "COMPLEX", 128, 1, 1, 4 * 148 * 3072 + 11, "umma32t")
+fir("complex_int16", "REAL", 40, 1, 1, 3 * 148 * 3072 + 5, "umma32t")
+fir("int16", "REAL", 64, 1, 1, 3 * 148 * 4096 + 7, "umma32")
 fir("complex_int16", "COMPLEX", 255, 2, 3, 30001)
 fir("int16", "REAL", 100, 3, 2, 30001)
 fir("complex_int16", "REAL", 40, 1, 4, 5000)
