@@ -327,6 +327,7 @@ struct FirOs32Args {
     int nchan;
     int K;
     int spread;         // TABS form: warp-major task order (launches smaller than one wave of warps)
+    int pdl;            // TABS form: launched with programmatic stream serialization (prologue before griddepcontrol.wait)
 };
 
 // TABS: one persistent CTA per SM whose warps share ONE copy of the tap spectrum and the twiddles in (dynamic) shared
@@ -371,15 +372,29 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32_kernel(const FirOs3
     __syncwarp();
     const c2 *src = nullptr;
     bool pending = bulk_src(ch, blk, src);
-    if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
     unsigned parity = 0;
     if constexpr (TABS) {
-        // the tables are staged while the first block is in flight (a launch's fixed cost matters for small work() buffers)
+        // Programmatic dependent launch (the host sets the attribute on this form, B200C_PDL=0 turns it off): the NEXT launch
+        // in the stream may start its CTAs on the SMs this one has left, and this launch ran its own prologue -- barrier
+        // init, 16 KB of tables -- while its predecessor was still finishing; only here, before the first access to stream
+        // data, does it wait for the predecessor to complete and flush.  Back-to-back work() calls on small buffers pay the
+        // launch latency and the prologue once, not per call.  Both instructions are no-ops in a plain launch.
+        asm volatile("griddepcontrol.launch_dependents;");
         c2 *tab = os32_dyn + WARPS * kOs32SmemElems;
         const c2 *__restrict__ hf0 = static_cast<const c2 *>(a.hf);
-        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
+        if (a.pdl) {
+            for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
+        } else {
+            // plain launch: the tables are staged while the first block is in flight
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
+            for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) { tab[i] = hf0[i]; tab[1024 + i] = tw[i]; }
+        }
         __syncthreads();
         hf_tab = tab; tw = tab + 1024;
+    } else {
+        if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), bar);
     }
     while (ch < a.nchan) {
         const long long base = blk * hop;
@@ -1604,7 +1619,7 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
         a.in = d_in; a.out = d_out; a.hf = batch ? batch->d_hf : p.d_hf1k; a.tw = p.d_tw1k;
         a.n_in = (long long)in_elems; a.n_out = (long long)n_out; a.K = p.K;
         a.nchan = nchan; a.in_stride = batch ? batch->in_stride : 0; a.out_stride = batch ? batch->out_stride : 0;
-        a.spread = 0;
+        a.spread = 0; a.pdl = 0;
         if (nchan == 1) {
             // single stream: one persistent 12-warp CTA per SM, tap spectrum + twiddles in shared memory, a landing buffer per
             // warp (the next block is fetched a whole block ahead).  Round-1 steps, headline Gsamples/s: 12 one-warp CTAs 272,
@@ -1620,7 +1635,19 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
             // fewer blocks than one wave of warps: one CTA per SM anyway, blocks dealt warp-major
             a.spread = nblk < 12LL * sm_count ? 1 : 0;
             const int grid = (int)std::min<long long>(a.spread ? nblk : (nblk + 11) / 12, (long long)sm_count);
-            fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
+            static const bool pdl = [] { const char *e = std::getenv("B200C_PDL"); return !e || std::atoi(e) != 0; }();
+            a.pdl = pdl ? 1 : 0;
+            if (pdl) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * 12); cfg.dynamicSmemBytes = smem_early; cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                B200C_CUDA_TRY(cudaLaunchKernelEx(&cfg, fir_os32_kernel<12, 1, true, false, true>, a));
+            } else {
+                fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
+            }
             B200C_CUDA_TRY(cudaGetLastError());
             return B200C_OK;
         }

@@ -882,3 +882,41 @@ def test_baseline_configs_at_their_stated_sizes_sampled_windows(oracle, cuda_dev
         _compare(oracle, code, y[o0: o0 + p_ref].cpu().numpy(), y_ref, f"{cfg} 2^{log2n} window at {w0} [{f.kernel}]")
     del x, y
     torch.cuda.empty_cache()
+
+
+def test_back_to_back_launches_chain_through_device_buffers(oracle, cuda_device):
+    """Programmatic dependent launch (fir_os32_kernel's persistent form): a launch may start its prologue before its
+    predecessor in the stream has finished, and must not touch stream data before `griddepcontrol.wait`.  Two filters
+    chained through a device buffer (B reads what A just wrote), forty small buffers back to back with no host
+    synchronisation in between, A's output buffer reused every round: every round's result against the oracle."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    code = oracle.CF32
+    rng = np.random.default_rng(77)
+    ta = rng.standard_normal(64) / 8 + 1j * rng.standard_normal(64) / 8
+    tb = rng.standard_normal(256) / 16 + 1j * rng.standard_normal(256) / 16
+    fa, fb = FirFilter(code, "COMPLEX"), FirFilter(code, "COMPLEX")
+    fa.set_taps(ta)
+    fb.set_taps(tb)
+    assert fa.kernel == "fir_os32_kernel" and fb.kernel == "fir_os32_kernel"
+    n = 150_000
+    rounds = 40
+    xs = [torch.from_numpy(_rand_input(oracle, code, n, rng)).cuda() for _ in range(4)]
+    mid = torch.empty((n, 2), dtype=torch.float32, device=cuda_device)
+    outs = [torch.empty((n, 2), dtype=torch.float32, device=cuda_device) for _ in range(rounds)]
+    prods = []
+    torch.cuda.synchronize()
+    for r in range(rounds):
+        _, _, pa = fa.run(xs[r % 4], out=mid)
+        _, _, pb = fb.run(mid[:pa], out=outs[r])
+        prods.append((pa, pb))
+    torch.cuda.synchronize()
+    refs = {}
+    for k in range(4):
+        ya, _, pa = oracle.fir(code, True, ta, 1, 1, xs[k].cpu().numpy())
+        yb, _, pb = oracle.fir(code, True, tb, 1, 1, ya)
+        refs[k] = (yb, pa, pb)
+    for r in range(rounds):
+        yb, pa, pb = refs[r % 4]
+        assert prods[r] == (pa, pb)
+        _compare(oracle, code, outs[r][:pb].cpu().numpy(), yb, f"round {r}")
