@@ -537,6 +537,7 @@ struct FirOsX32Args {
     long long n_in, n_out;
     long long p0;       // input element at which block 0's window starts (<= 0: zeros in front)
     int m0;             // first alias-free output of a block
+    int pdl;            // launched with programmatic stream serialization (see fir_os32_kernel)
 };
 constexpr int kX32Rows = 48, kX32SmemElems = kX32Rows * kOs32Stride;
 
@@ -579,16 +580,30 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) fir_os32x_kernel(const FirOs
     const long long bstep = (long long)gridDim.x * WARPS;
     const c2 *src = nullptr;
     bool pending = bulk_src(blk, src);
-    if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
     unsigned parity = 0;
     if constexpr (WARPS > 1) {
-        // tables staged while the first block is in flight
+        // dependent launch as in fir_os32_kernel: with a.pdl the 44 KB of tables are staged while the predecessor in the stream
+        // is still running and stream data is touched only after griddepcontrol.wait; a plain launch stages them while its
+        // first block is in flight
+        asm volatile("griddepcontrol.launch_dependents;");
         c2 *tab = x32_smem + WARPS * kX32SmemElems;
-        for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
-        for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
-        for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
+        auto stage = [&] {
+            for (int i = threadIdx.x; i < 3072; i += 32 * WARPS) tab[i] = hx[i];
+            for (int i = threadIdx.x; i < 1536; i += 32 * WARPS) tab[3072 + i] = tw3[i];
+            for (int i = threadIdx.x; i < 1024; i += 32 * WARPS) tab[3072 + 1536 + i] = tw[i];
+        };
+        if (a.pdl) {
+            stage();
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
+        } else {
+            if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
+            stage();
+        }
         __syncthreads();
         hx = tab; tw3 = tab + 3072; tw = tab + 3072 + 1536;
+    } else {
+        if (pending && t == 0) bulk_load(Lb, src, kBulk * (unsigned)sizeof(c2), &bar);
     }
     for (; blk < nblk; blk += bstep) {
         const long long P = a.p0 + blk * hop_in;
@@ -1528,6 +1543,25 @@ static void launch_ospg(const FirOs32GArgs &a, int M, size_t smem, long long nbl
     kern<<<grid, 32 * NW * G, smem, stream>>>(a, M);
 }
 
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still running;
+// it must execute griddepcontrol.wait before touching stream data (fir_os32_kernel, fir_os32x_kernel persistent forms).
+static bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("B200C_PDL"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+template <typename Kernel, typename Args>
+static cudaError_t launch_dependent(Kernel kern, int grid, int block, size_t smem, cudaStream_t stream, const Args &a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d_out, size_t nq, int sm_count,
                   cudaStream_t stream, const FirOsBatch *batch)
 {
@@ -1554,7 +1588,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
             configured[dev] = true;
         }
         const int grid = (int)std::min<long long>((nblk + 11) / 12, (long long)sm_count);
-        fir_os32x_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
+        a.pdl = pdl_enabled() ? 1 : 0;
+        if (a.pdl) B200C_CUDA_TRY(launch_dependent(fir_os32x_kernel<12, 1, true, true>, grid, 32 * 12, smem, stream, a));
+        else fir_os32x_kernel<12, 1, true, true><<<grid, 32 * 12, smem, stream>>>(a);
         B200C_CUDA_TRY(cudaGetLastError());
         return B200C_OK;
     }
@@ -1635,19 +1671,9 @@ int fir_os_launch(const FirOsPlan &p, const void *d_in, size_t in_elems, void *d
             // fewer blocks than one wave of warps: one CTA per SM anyway, blocks dealt warp-major
             a.spread = nblk < 12LL * sm_count ? 1 : 0;
             const int grid = (int)std::min<long long>(a.spread ? nblk : (nblk + 11) / 12, (long long)sm_count);
-            static const bool pdl = [] { const char *e = std::getenv("B200C_PDL"); return !e || std::atoi(e) != 0; }();
-            a.pdl = pdl ? 1 : 0;
-            if (pdl) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * 12); cfg.dynamicSmemBytes = smem_early; cfg.stream = stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                B200C_CUDA_TRY(cudaLaunchKernelEx(&cfg, fir_os32_kernel<12, 1, true, false, true>, a));
-            } else {
-                fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
-            }
+            a.pdl = pdl_enabled() ? 1 : 0;
+            if (a.pdl) B200C_CUDA_TRY(launch_dependent(fir_os32_kernel<12, 1, true, false, true>, grid, 32 * 12, smem_early, stream, a));
+            else fir_os32_kernel<12, 1, true, false, true><<<grid, 32 * 12, smem_early, stream>>>(a);
             B200C_CUDA_TRY(cudaGetLastError());
             return B200C_OK;
         }

@@ -920,3 +920,40 @@ def test_back_to_back_launches_chain_through_device_buffers(oracle, cuda_device)
         yb, pa, pb = refs[r % 4]
         assert prods[r] == (pa, pb)
         _compare(oracle, code, outs[r][:pb].cpu().numpy(), yb, f"round {r}")
+
+
+def test_back_to_back_launches_resampler_then_filter(oracle, cuda_device):
+    """The same chain with the spectral resampler (fir_os32x_kernel, also a programmatic dependent) feeding the filter."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    from pothoscomms_b200 import workloads as wl
+    code = oracle.CF32
+    rng = np.random.default_rng(78)
+    ta, tta = wl.config_taps("c3")
+    tb = rng.standard_normal(256) / 16 + 1j * rng.standard_normal(256) / 16
+    fa, fb = FirFilter(code, tta), FirFilter(code, "COMPLEX")
+    fa.set_taps(ta)
+    fa.set_rates(2, 3)
+    fb.set_taps(tb)
+    assert fa.kernel == "fir_os32x_kernel" and fb.kernel == "fir_os32_kernel"
+    n = 100_000
+    rounds = 24
+    xs = [torch.from_numpy(_rand_input(oracle, code, n, rng)).cuda() for _ in range(3)]
+    mid = torch.empty((n * 3 // 2 + 8, 2), dtype=torch.float32, device=cuda_device)
+    outs = [torch.empty((n * 3 // 2 + 8, 2), dtype=torch.float32, device=cuda_device) for _ in range(rounds)]
+    prods = []
+    torch.cuda.synchronize()
+    for r in range(rounds):
+        _, _, pa = fa.run(xs[r % 3], out=mid)
+        _, _, pb = fb.run(mid[:pa], out=outs[r])
+        prods.append((pa, pb))
+    torch.cuda.synchronize()
+    refs = {}
+    for k in range(3):
+        ya, _, pa = oracle.fir(code, tta == "COMPLEX", ta, 2, 3, xs[k].cpu().numpy())
+        yb, _, pb = oracle.fir(code, True, tb, 1, 1, ya)
+        refs[k] = (yb, pa, pb)
+    for r in range(rounds):
+        yb, pa, pb = refs[r % 3]
+        assert prods[r] == (pa, pb)
+        _compare(oracle, code, outs[r][:pb].cpu().numpy(), yb, f"round {r}")
