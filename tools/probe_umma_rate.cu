@@ -53,7 +53,8 @@ __global__ void probe(Mode m, int iters, long long *out)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {
         const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(m.N >> 3) << 17) | ((128u >> 4) << 24);
-        const unsigned long long ad0 = m.a_sw32 ? desc(smem_u32(sm), 16, 256, 6) : desc(smem_u32(sm), 128, 256, 0);
+        // a_sw32 == 2: the 16-byte-pitch rows of fir_umma_kernel / fir_ummap_kernel (no swizzle, LBO 16, SBO 128: row m = plane[16 m ..])
+        const unsigned long long ad0 = m.a_sw32 == 2 ? desc(smem_u32(sm), 16, 128, 0) : m.a_sw32 ? desc(smem_u32(sm), 16, 256, 6) : desc(smem_u32(sm), 128, 256, 0);
         const unsigned long long bd0 = m.b_sw32 ? desc(smem_u32(sm + 24576), 16, 256, 6) : desc(smem_u32(sm + 24576), 128, 256, 0);
         // everything per MMA is a compile-time choice among registers set up here (the kernels do the same)
         unsigned dcol[NACC];
@@ -103,6 +104,7 @@ int main()
         {1, 0, 1, 96, 1, 0},  {1, 0, 1, 96, 2, 0},  {1, 0, 1, 96, 4, 0},  {1, 0, 1, 128, 1, 0}, {1, 0, 1, 128, 2, 0}, {1, 0, 1, 192, 1, 0},
         {1, 0, 1, 192, 2, 0}, {1, 0, 1, 240, 2, 0}, {1, 0, 1, 64, 1, 0},  {1, 0, 1, 64, 4, 0},  {1, 0, 1, 32, 1, 0},  {1, 0, 1, 32, 4, 0},
         {1, 0, 0, 96, 2, 0},  {1, 0, 0, 128, 2, 0}, {1, 0, 0, 240, 2, 0}, {1, 0, 0, 64, 4, 0},
+        {0, 2, 0, 64, 1, 0},  {0, 2, 0, 96, 2, 0},  {0, 2, 0, 128, 2, 0}, {0, 2, 0, 192, 2, 0},
     };
     std::printf("A operand        B operand        N  accumulators  cycles/MMA  MAC/cycle\n");
     for (const Mode &m : modes) {
@@ -123,7 +125,7 @@ int main()
         cudaDeviceSynchronize();
         cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
         const double c = (double)h / iters;
-        std::printf("%-16s %-16s %3d  %5d  %10.1f  %9.0f\n", m.a_tmem ? "tensor memory" : m.a_sw32 ? "smem 32B-swizzle" : "smem canonical",
+        std::printf("%-16s %-16s %3d  %5d  %10.1f  %9.0f\n", m.a_tmem ? "tensor memory" : m.a_sw32 == 2 ? "smem 16B-pitch" : m.a_sw32 ? "smem 32B-swizzle" : "smem canonical",
                     m.b_sw32 ? "smem 32B-swizzle" : "smem canonical", m.N, m.nacc, c, 128.0 * m.N * 32 / c);
     }
     return 0;
