@@ -43,6 +43,10 @@ constexpr int kU32Tile = 4096;
 // TENSOR MEMORY, the data planes are the B operand with N = NW windows per tile.  Columns: two stages x
 // two data limbs x NW accumulators + 8 per (data component, k-block) tap tile <= 512.
 constexpr int kU32tNW = 96, kU32tTile = 32 * kU32tNW, kU32tMaxNB = (512 - 4 * kU32tNW) / 16;
+// The same for REAL int16 data: one component leaves half of the 128 rows free, so a window is 64 outputs (rows = 64 outputs
+// x 2 tap digits) and the plane rows are 64 bytes (SWIZZLE_64B), read 32 bytes -- one k-block -- at a time; a tile is
+// 96 x 64 = 6144 outputs, still 3072 32-bit words of output.
+constexpr int kU32trTile = 64 * kU32tNW;
 constexpr int kU32EpiWarps = 8, kU32StageWarps = 8, kU32MaxRing = 8;
 constexpr int kU32Batch = 5;      // stager loads in flight per thread: their latency under the MMA's operand traffic is long
 constexpr int kU32Threads = 32 * (kU32EpiWarps + kU32StageWarps + 2);
@@ -62,13 +66,13 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     constexpr int NQ = DC * 2;                     // (output component, tap digit) per output
     constexpr int N = 32 * NQ;                     // MMA N = columns of one data-limb region
     constexpr int NW = kU32tNW;                    // TS: windows per tile = MMA N
-    constexpr int TILE = TS ? kU32tTile : kU32Tile;
+    constexpr bool TR = TS && DC == 1;             // swapped formulation on real data
+    constexpr int TILE = TR ? kU32trTile : TS ? kU32tTile : kU32Tile;
     constexpr int COLS = TS ? 2 * NW : 2 * N;      // lo and hi regions
     constexpr int ALLOC = TS ? 512 : 2 * COLS;     // two stages: 512 (complex) / 256 (real) columns
     constexpr int ACOL = 2 * COLS;                 // TS: first column of the tap tiles
     constexpr int SW = SWT, NTHR = 32 * (kU32EpiWarps + SW + 2);
     constexpr int PS = TS ? kU32tPlaneStages : 2;  // plane stages (the accumulators have two)
-    static_assert(!TS || DC == 2, "the swapped formulation needs M = 128 = 32 outputs x 2 components x 2 digits");
     constexpr int NPL = DC * 2, ESZ = DC * 2;
     constexpr int CH = 16 / NQ;                    // outputs per 16-column epilogue chunk
     const int NB = NBT ? NBT : a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
@@ -151,8 +155,9 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
 #pragma unroll
             for (int s = 0; s < 2; s++)
 #pragma unroll
-                for (int p = 0; p < NPL; p++)      // A: plane p of stage s, rows of 32-byte pitch (SWIZZLE_32B)
-                    a_base[s][p] = umma_smem_desc(smem_u32(planes + ((size_t)s * NPL + p) * PLa), 16, 256, 6);
+                for (int p = 0; p < NPL; p++)      // plane p of stage s, rows of 32-byte pitch (SWIZZLE_32B); TR: 64-byte pitch (SWIZZLE_64B)
+                    a_base[s][p] = TR ? umma_smem_desc(smem_u32(planes + ((size_t)s * NPL + p) * PLa), 16, 512, 4)
+                                      : umma_smem_desc(smem_u32(planes + ((size_t)s * NPL + p) * PLa), 16, 256, 6);
             if constexpr (!TS) {
 #pragma unroll
                 for (int dc = 0; dc < DC; dc++) b_base[dc] = umma_smem_desc(smem_u32(bmat + (size_t)dc * NB * N * 32), 128, 256, 0);
@@ -241,7 +246,48 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             const unsigned char *rw = raw + (size_t)r * PL * ESZ;
             const bool timed = a.dbg != nullptr;
             const long long t_c0 = timed ? clock64() : 0;
-            if (TS && landed) {
+            if constexpr (TR) {
+                // real int16: item q = eight samples = 16 raw bytes -> eight bytes (half a 16-byte chunk) of the lo and of the hi
+                // plane, stored with the 64-byte swizzle: chunk c lives at c ^ (c >> 3 & 3).  q + NST is NST / 2 chunks on, a
+                // multiple of 32: the swizzle bits do not change.
+                constexpr int PLc = kU32trTile + 32 * (NBT ? NBT : 1), PLac = (PLc + 511) / 512 * 512, NQc = PLc / 8;
+                constexpr int FULL = NQc / NST, REM = NQc % NST;
+                static_assert(NST % 64 == 0, "q + NST must keep the swizzle bits");
+                const int c0 = st >> 1;
+                unsigned *dst = pl + (((c0 ^ ((c0 >> 3) & 3)) << 2) | ((st & 1) << 1));
+                auto split = [&](const uint4 v, unsigned *p) {
+                    *reinterpret_cast<uint2 *>(p) = make_uint2(prmt_u(v.x, v.y, 0x6420), prmt_u(v.z, v.w, 0x6420));
+                    *reinterpret_cast<uint2 *>(p + PLac / 4) = make_uint2(prmt_u(v.x, v.y, 0x7531), prmt_u(v.z, v.w, 0x7531));
+                };
+                if (landed) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(rw) + st;
+                    uint4 v[FULL];
+#pragma unroll
+                    for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                    uint4 vt = make_uint4(0, 0, 0, 0);
+                    if (REM && st < REM) vt = src[FULL * NST];
+#pragma unroll
+                    for (int u = 0; u < FULL; u++) split(v[u], dst + u * (NST * 2));
+                    if (REM && st < REM) split(vt, dst + FULL * (NST * 2));
+                } else {
+                    // edge tiles and unaligned streams: guarded element loads
+                    const unsigned short *__restrict__ in16 = static_cast<const unsigned short *>(a.in);
+#pragma unroll 1
+                    for (int u = 0; u <= FULL; u++) {
+                        const int q = st + u * NST;
+                        if (q >= NQc) break;
+                        const long long sm = o0 + 8LL * q;
+                        unsigned w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const unsigned x0 = sm + 2 * k < a.n_in ? __ldg(in16 + sm + 2 * k) : 0u;
+                            const unsigned x1 = sm + 2 * k + 1 < a.n_in ? __ldg(in16 + sm + 2 * k + 1) : 0u;
+                            w[k] = x0 | (x1 << 16);
+                        }
+                        split(make_uint4(w[0], w[1], w[2], w[3]), dst + u * (NST * 2));
+                    }
+                }
+            } else if (TS && landed) {
                 // every size is a compile-time constant here: item q = st + 128 u of this thread (four samples: 16 raw
                 // bytes -> one word of each plane) sits 2048 bytes further in the landing slot and 512 bytes further
                 // in the planes (q + 128 is 32 chunks on: the swizzle bit (c >> 3) & 1 does not change)
@@ -353,8 +399,10 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             const unsigned ph = (unsigned)(i >> 1) & 1;
             const long long tile = first + (long long)i * step;
             // output of (window n0 + 2 q, j); the thread's others are whole windows (32 outputs) further on
-            const long long o00 = tile * TILE + 32LL * ((NW / 2) * half + 2 * q) + 8 * quad + (lane >> 2);
-            const bool whole = (tile + 1) * TILE <= a.n_out;
+            // (32-bit words: a complex sample, or -- TR -- two consecutive real outputs: rows ordered so that the second 16-lane
+            // load holds the odd outputs of the same window, see fir_umma32_configure)
+            const long long o00 = tile * kU32tTile + 32LL * ((NW / 2) * half + 2 * q) + 8 * quad + (lane >> 2);
+            const bool whole = (tile + 1) * TILE <= a.n_out && (!TR || (reinterpret_cast<unsigned long long>(a.out) & 3) == 0);
             const unsigned tcol = lane_addr + (unsigned)(s * COLS + (NW / 2) * half);
             unsigned *const ot = out32 + o00;
             watched_wait(a.dbg != nullptr, &acc_full[s], ph, w0);
@@ -384,10 +432,18 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                         res[2 * g + e] = prmt_u(yr, yi, 0x7632);
                         if (whole) __stcg(o + w, res[2 * g + e]);
                     }
-                if (!whole)       // the stream's last tile
+                if (!whole)       // the stream's last tile (TR: or an output pointer that is not word-aligned)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (o00 + 32 * 16 * c + 32 * (8 * (k >> 1) + (k & 1)) < a.n_out) o[32 * (8 * (k >> 1) + (k & 1))] = res[k];
+                    for (int k = 0; k < 4; k++) {
+                        const long long wi = o00 + 32 * 16 * c + 32 * (8 * (k >> 1) + (k & 1));
+                        if constexpr (TR) {
+                            unsigned short *o16 = static_cast<unsigned short *>(a.out);
+                            if (2 * wi < a.n_out) o16[2 * wi] = (unsigned short)res[k];
+                            if (2 * wi + 1 < a.n_out) o16[2 * wi + 1] = (unsigned short)(res[k] >> 16);
+                        } else {
+                            if (wi < a.n_out) o[32 * (8 * (k >> 1) + (k & 1))] = res[k];
+                        }
+                    }
             }
         }
     } else {
@@ -464,6 +520,8 @@ template <int DC>
 __global__ void __launch_bounds__(kU32Threads, 1) fir_umma32_kernel(const FirUmma32Args a) { fir_umma32_body<DC, false, 0>(a); }
 template <int NBT>
 __global__ void __launch_bounds__(kU32tThreads, 1) fir_umma32t_kernel(const FirUmma32Args a) { fir_umma32_body<2, true, NBT, kU32tStageWarps>(a); }
+template <int NBT>   // real int16 data
+__global__ void __launch_bounds__(kU32tThreads, 1) fir_umma32tr_kernel(const FirUmma32Args a) { fir_umma32_body<1, true, NBT, kU32tStageWarps>(a); }
 
 // ------------------------------------------------------------------------------- host ---
 // balanced byte digits (d0, d1) of q = d0 + 256 d1, both in [-128, 127]; false if q does not fit
@@ -487,13 +545,17 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
     const bool enabled = [] { const char *e = std::getenv("B200C_UMMA32"); return !e || std::atoi(e) != 0; }();   // B200C_UMMA32=0: stay on fir_umma_kernel
     if (!base.ready || !(enabled || force) || base.nlt != 2) return B200C_OK;
     const int K = base.K, dc = base.dc, tc = base.tc, NQ = dc * 2, N = 32 * NQ;
-    const int NB = (K + 31 + 31) / 32;
     static const bool swap_default = [] { const char *e = std::getenv("B200C_UMMA32T"); return !e || std::atoi(e) != 0; }();   // =0: the original formulation
-    const bool swapped = dc == 2 && NB <= kU32tMaxNB && (swap < 0 ? swap_default : swap != 0);
-    const int PL = (swapped ? kU32tTile : kU32Tile) + 32 * NB, PLa = (PL + 255) / 256 * 256;
+    // k-blocks per window: 32 outputs + K - 1 positions (the swapped kernel on real data: 64 outputs)
+    const int NBo = (K + 31 + 31) / 32, NBr = (K + 63 + 31) / 32;
+    const bool swapped = (dc == 2 ? NBo : NBr) <= kU32tMaxNB && (swap < 0 ? swap_default : swap != 0);
+    const bool swapped_real = swapped && dc == 1;
+    const int NB = swapped_real ? NBr : NBo;
+    const int PL = (swapped_real ? kU32trTile : swapped ? kU32tTile : kU32Tile) + 32 * NB;
+    const int PLa = swapped_real ? (PL + 511) / 512 * 512 : (PL + 255) / 256 * 256;
     // B tiles, two plane stages and at least a 3-deep landing ring must fit
     if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * (size_t)PL * dc * 2 > 200 * 1024) return B200C_OK;
-    std::vector<uint8_t> bm((size_t)dc * NB * N * 32, 0), am(swapped ? (size_t)dc * NB * N * 32 : 0, 0);
+    std::vector<uint8_t> bm(swapped_real ? 0 : (size_t)dc * NB * N * 32, 0), am(swapped ? (size_t)dc * NB * 128 * 32 : 0, 0);
     for (int d = 0; d < K; d++)
         for (int c = 0; c < tc; c++) {
             const long long q = (long long)(int32_t)(long long)std::ldexp(taps[(size_t)d * tc + c], 16);
@@ -508,6 +570,18 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
             if (dc == 1) { uses[nuse++] = {0, 0, false}; }
             else if (c == 0) { uses[nuse++] = {0, 0, false}; uses[nuse++] = {1, 1, false}; }
             else { uses[nuse++] = {0, 1, false}; uses[nuse++] = {1, 0, true}; }
+            if (swapped_real) {
+                // 64 outputs per window; TMEM lane of (output n, digit l): 32 quad + 16 (n & 1) + 8 l + (n >> 1 & 7) with
+                // quad = n >> 4 -- the epilogue's two 16-lane loads then hold the even and the odd outputs of the same pair
+                for (int n = 0; n < 64; n++) {
+                    const int j = n + K - 1 - d, b = j / 32, jj = j % 32;
+                    for (int l = 0; l < 2; l++) {
+                        const int row = 32 * (n >> 4) + 16 * (n & 1) + 8 * l + ((n >> 1) & 7);
+                        am[((size_t)b * 128 + row) * 32 + jj] = (uint8_t)pos[l];
+                    }
+                }
+                continue;
+            }
             for (int u = 0; u < nuse; u++)
                 for (int n = 0; n < 32; n++) {
                     const int j = n + K - 1 - d;                         // window position of tap d for output n
@@ -527,13 +601,13 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
                     }
                 }
         }
-    if (bm.size() > p.capacity) {
+    if (!bm.empty() && bm.size() > p.capacity) {
         if (p.d_bmat) cudaFree(p.d_bmat);
         p.d_bmat = nullptr; p.capacity = 0;
         B200C_CUDA_TRY(cudaMalloc(&p.d_bmat, bm.size()));
         p.capacity = bm.size();
     }
-    B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+    if (!bm.empty()) B200C_CUDA_TRY(cudaMemcpy(p.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
     if (swapped) {
         if (am.size() > p.a_capacity) {
             if (p.d_amat) cudaFree(p.d_amat);
@@ -560,7 +634,17 @@ template <int DC, bool TS>
 static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
 {
     void (*kern)(FirUmma32Args) = fir_umma32_kernel<DC>;
-    if (TS) {
+    if (TS && DC == 1) {
+        switch (a.NB) {      // 64 outputs + K - 1 positions: at least two k-blocks
+        case 2: kern = fir_umma32tr_kernel<2>; break;
+        case 3: kern = fir_umma32tr_kernel<3>; break;
+        case 4: kern = fir_umma32tr_kernel<4>; break;
+        case 5: kern = fir_umma32tr_kernel<5>; break;
+        case 6: kern = fir_umma32tr_kernel<6>; break;
+        case 7: kern = fir_umma32tr_kernel<7>; break;
+        default: kern = fir_umma32tr_kernel<8>; break;
+        }
+    } else if (TS) {
         switch (a.NB) {
         case 1: kern = fir_umma32t_kernel<1>; break;
         case 2: kern = fir_umma32t_kernel<2>; break;
@@ -637,12 +721,13 @@ int fir_umma32_launch(const FirUmma32Plan &p, const void *d_in, size_t in_elems,
 {
     if (n_out == 0) return B200C_OK;
     FirUmma32Args a;
-    const int tile = p.swapped ? kU32tTile : kU32Tile;
+    const int tile = p.swapped ? (p.dc == 1 ? kU32trTile : kU32tTile) : kU32Tile;
     a.in = d_in; a.out = d_out; a.bmat = p.swapped ? p.d_amat : p.d_bmat;
     a.n_in = (long long)in_elems; a.n_out = (long long)n_out;
     a.ntiles = ((long long)n_out + tile - 1) / tile;
-    a.K = p.K; a.NB = p.NB; a.PL = tile + 32 * p.NB; a.PLa = (a.PL + 255) / 256 * 256; a.R = 2; a.dbg = nullptr;
-    if (p.swapped) return launch_u32<2, true>(a, sm_count, stream);
+    a.K = p.K; a.NB = p.NB; a.PL = tile + 32 * p.NB; a.R = 2; a.dbg = nullptr;
+    a.PLa = p.swapped && p.dc == 1 ? (a.PL + 511) / 512 * 512 : (a.PL + 255) / 256 * 256;
+    if (p.swapped) return p.dc == 1 ? launch_u32<1, true>(a, sm_count, stream) : launch_u32<2, true>(a, sm_count, stream);
     return p.dc == 1 ? launch_u32<1, false>(a, sm_count, stream) : launch_u32<2, false>(a, sm_count, stream);
 }
 

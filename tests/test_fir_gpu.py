@@ -502,9 +502,8 @@ def test_imma_tap_limb_counts_and_wrapping(oracle, cuda_device, dt, taps_type, s
     x = _rand_input(oracle, code, 9000, rng, full_scale=True)
     y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x)
     y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x)
-    # tcgen05 paths take 2-limb taps: the operand-swapped kernel for complex data, the original one for real data
-    two_limb = "fir_umma32t_kernel" if dt == "CI16" else "fir_umma32_kernel"
-    assert f.kernel == (two_limb if limbs == 2 else "fir_imma_kernel")
+    # tcgen05 paths take 2-limb taps (the operand-swapped kernel at this tap count)
+    assert f.kernel == ("fir_umma32t_kernel" if limbs == 2 else "fir_imma_kernel")
     assert (cons, prod) == (c_ref, p_ref)
     _compare(oracle, code, y, y_ref, f"scale={scale} ({limbs} limbs)")
 
@@ -519,8 +518,6 @@ def test_imma_unaligned_device_pointers(oracle, cuda_device, dt, kernel):
     code = getattr(oracle, dt)
     rng = np.random.default_rng(99)
     taps = rng.standard_normal(64) * 0.05
-    if kernel == "fir_umma32t_kernel" and dt == "I16":
-        pytest.skip("the operand-swapped kernel is the complex-data formulation (M = 128 rows)")
     with _with_algo({"fir_imma_kernel": "imma", "fir_umma_kernel": "umma", "fir_umma32_kernel": "umma32",
                      "fir_umma32t_kernel": "umma32t"}[kernel]):
         f = FirFilter(code, "REAL")
@@ -588,28 +585,34 @@ def test_umma32_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
 
 
 @pytest.mark.parametrize("ntaps", [2, 33, 34, 65, 66, 128, 129, 193, 194, 225])
-@pytest.mark.parametrize("taps_type", ["COMPLEX", "REAL"])
-def test_umma32t_path_is_bit_exact(oracle, cuda_device, taps_type, ntaps):
+@pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
+def test_umma32t_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
     """The operand-swapped formulation (fir_umma32t_kernel): the tap-digit tiles are the A operand and sit in
-    tensor memory, the swizzled data planes are the B operand (96 windows of 32 outputs per tile), the epilogue
-    combines digits and components across TMEM lanes with warp shuffles.  Tap counts either side of the k-block
-    boundaries up to the tensor-memory limit (8 k-blocks), tiles of 3072 outputs ending mid-window, zero tail,
-    full-scale input."""
-    code = oracle.CI16
+    tensor memory, the swizzled data planes are the B operand (96 windows per tile), the epilogue reads both digits
+    of an output with the 16-lane tensor-memory load shape.  Complex data: windows of 32 outputs, 32-byte-swizzled
+    rows; real data: windows of 64 outputs, 64-byte-swizzled rows read 32 bytes at a time.  Tap counts either side
+    of the k-block boundaries up to the tensor-memory limit (8 k-blocks: 225 complex / 193 real), tiles of 3072 /
+    6144 outputs ending mid-window, odd output counts (real: the last 32-bit word half used), zero tail, full-scale
+    input."""
+    code = getattr(oracle, dt)
+    if dt == "I16" and ntaps > 193:
+        pytest.skip("real data: 64 outputs + K - 1 positions must fit 8 k-blocks")
     cx = taps_type == "COMPLEX"
-    rng = np.random.default_rng(ntaps * 17 + 3)
+    rng = np.random.default_rng(ntaps * 17 + 3 + code)
     taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
     if cx:
         taps = taps + 1j * rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
-    for n_new, zero_tail in ((1, False), (31, False), (32, False), (33, False), (3071, False), (3072, False), (3073, False),
-                             (5 * 3072 + 1001, False), (148 * 3072 + 17, False), (700001, False), (1000, True), (1, True)):
+    tile = 3072 if dt == "CI16" else 6144
+    for n_new, zero_tail in ((1, False), (31, False), (32, False), (33, False), (63, False), (64, False), (65, False),
+                             (tile - 1, False), (tile, False), (tile + 1, False), (5 * tile + 1001, False), (148 * tile + 17, False),
+                             (700001, False), (1000, True), (1, True)):
         x = _rand_input(oracle, code, ntaps - 1 + n_new, rng, full_scale=True)
         y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, 1, 1, x, zero_tail=zero_tail)
         with _with_algo("umma32t"):
             y, cons, prod, f = _run_gpu(code, taps_type, taps, 1, 1, x, zero_tail=zero_tail)
             assert f.kernel == "fir_umma32t_kernel"
         assert (cons, prod) == (c_ref, p_ref), (n_new, zero_tail)
-        _compare(oracle, code, y, y_ref, f"umma32t K={ntaps} n={n_new} zt={zero_tail}")
+        _compare(oracle, code, y, y_ref, f"umma32t {dt} K={ntaps} n={n_new} zt={zero_tail}")
 
 
 @pytest.mark.parametrize("algo,kernel", [("umma32", "fir_umma32_kernel"), ("umma32t", "fir_umma32t_kernel")])
@@ -654,7 +657,7 @@ def test_umma32t_falls_back_beyond_its_tensor_memory_budget(oracle, cuda_device)
     assert f.kernel == "fir_umma32_kernel"
     with _with_algo("umma32t"):
         f = FirFilter(oracle.I16, "REAL")
-        f.set_taps(taps[:100])
+        f.set_taps(taps[:200])                # real data: 64 + 199 positions are nine k-blocks
     assert f.kernel == "fir_umma32_kernel"
 
 
@@ -957,3 +960,33 @@ def test_back_to_back_launches_resampler_then_filter(oracle, cuda_device):
         yb, pa, pb = refs[r % 3]
         assert prods[r] == (pa, pb)
         _compare(oracle, code, outs[r][:pb].cpu().numpy(), yb, f"round {r}")
+
+
+def test_umma32t_real_data_over_many_tiles_per_cta(oracle, cuda_device):
+    """The operand-swapped kernel on REAL int16 (64-output windows, 64-byte-swizzled planes): eleven tiles per persistent
+    CTA, oracle windows at the start, deep inside and at the ragged (odd) end, the whole output against the original kernel."""
+    import torch
+    from pothoscomms_b200 import FirFilter
+    code = oracle.I16
+    rng = np.random.default_rng(2025)
+    ntaps = 64
+    taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
+    n = 11 * 148 * 6144 + 333
+    x = torch.randint(-32768, 32767, (ntaps - 1 + n, 1), dtype=torch.int16, device=cuda_device)
+    outs = {}
+    for a in ("umma32", "umma32t"):
+        with _with_algo(a):
+            f = FirFilter(code, "REAL")
+            f.set_taps(taps)
+        y, cons, prod = f.run(x)
+        torch.cuda.synchronize()
+        assert (cons, prod) == (n, n)
+        outs[a] = (f.kernel, y[:prod].clone())
+    assert outs["umma32"][0] == "fir_umma32_kernel" and outs["umma32t"][0] == "fir_umma32t_kernel"
+    y = outs["umma32t"][1]
+    wlen = 30_000
+    for w0 in (0, 3 * 148 * 6144 - 7000, 7 * 148 * 6144 + 123, n // 2, n - wlen):
+        seg = x[w0: w0 + ntaps - 1 + wlen].cpu().numpy()
+        y_ref, _, p_ref = oracle.fir(code, False, taps, 1, 1, seg)
+        _compare(oracle, code, y[w0: w0 + p_ref].cpu().numpy(), y_ref, f"window at {w0}")
+    assert torch.equal(outs["umma32"][1], outs["umma32t"][1])

@@ -42,6 +42,7 @@ for algo in ("umma32t", "umma32", "umma", "imma", "direct"):
 fir("complex_int16", "COMPLEX", 128, 1, 1, 4 * 148 * 3072 + 11, "umma32t")
 fir("complex_int16", "REAL", 40, 1, 1, 3 * 148 * 3072 + 5, "umma32t")
 fir("int16", "REAL", 64, 1, 1, 3 * 148 * 4096 + 7, "umma32")
+fir("int16", "REAL", 64, 1, 1, 3 * 148 * 6144 + 7, "umma32t")      # real data on 64-output windows
 fir("complex_int16", "COMPLEX", 255, 2, 3, 30001)
 fir("int16", "REAL", 100, 3, 2, 30001)
 fir("complex_int16", "REAL", 40, 1, 4, 5000)
