@@ -47,6 +47,7 @@ constexpr int kU32tNW = 96, kU32tTile = 32 * kU32tNW, kU32tMaxNB = (512 - 4 * kU
 // x 2 tap digits) and the plane rows are 64 bytes (SWIZZLE_64B), read 32 bytes -- one k-block -- at a time; a tile is
 // 96 x 64 = 6144 outputs, still 3072 32-bit words of output.
 constexpr int kU32trTile = 64 * kU32tNW;
+constexpr int kU32trMaxNB = 16;    // one data component: 8 columns of tap tiles per k-block, 128 columns beside the accumulators
 constexpr int kU32EpiWarps = 8, kU32StageWarps = 8, kU32MaxRing = 8;
 constexpr int kU32Batch = 5;      // stager loads in flight per thread: their latency under the MMA's operand traffic is long
 constexpr int kU32Threads = 32 * (kU32EpiWarps + kU32StageWarps + 2);
@@ -548,7 +549,7 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
     static const bool swap_default = [] { const char *e = std::getenv("B200C_UMMA32T"); return !e || std::atoi(e) != 0; }();   // =0: the original formulation
     // k-blocks per window: 32 outputs + K - 1 positions (the swapped kernel on real data: 64 outputs)
     const int NBo = (K + 31 + 31) / 32, NBr = (K + 63 + 31) / 32;
-    const bool swapped = (dc == 2 ? NBo : NBr) <= kU32tMaxNB && (swap < 0 ? swap_default : swap != 0);
+    const bool swapped = (dc == 2 ? NBo <= kU32tMaxNB : NBr <= kU32trMaxNB) && (swap < 0 ? swap_default : swap != 0);
     const bool swapped_real = swapped && dc == 1;
     const int NB = swapped_real ? NBr : NBo;
     const int PL = (swapped_real ? kU32trTile : swapped ? kU32tTile : kU32Tile) + 32 * NB;
@@ -642,7 +643,15 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         case 5: kern = fir_umma32tr_kernel<5>; break;
         case 6: kern = fir_umma32tr_kernel<6>; break;
         case 7: kern = fir_umma32tr_kernel<7>; break;
-        default: kern = fir_umma32tr_kernel<8>; break;
+        case 8: kern = fir_umma32tr_kernel<8>; break;
+        case 9: kern = fir_umma32tr_kernel<9>; break;
+        case 10: kern = fir_umma32tr_kernel<10>; break;
+        case 11: kern = fir_umma32tr_kernel<11>; break;
+        case 12: kern = fir_umma32tr_kernel<12>; break;
+        case 13: kern = fir_umma32tr_kernel<13>; break;
+        case 14: kern = fir_umma32tr_kernel<14>; break;
+        case 15: kern = fir_umma32tr_kernel<15>; break;
+        default: kern = fir_umma32tr_kernel<16>; break;
         }
     } else if (TS) {
         switch (a.NB) {
@@ -657,7 +666,8 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         }
     }
     const int threads = TS ? kU32tThreads : kU32Threads, slot = TS ? a.NB : 0;
-    static thread_local bool configured[16][16] = {{false}};
+    static_assert(kU32trMaxNB == 16, "launch_u32 instantiates fir_umma32tr_kernel for 2..16 k-blocks");
+    static thread_local bool configured[16][17] = {{false}};
     int dev = 0;
     B200C_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 16 && !configured[dev][slot]) {

@@ -584,19 +584,19 @@ def test_umma32_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
         _compare(oracle, code, y, y_ref, f"umma32 K={ntaps} n={n_new} zt={zero_tail}")
 
 
-@pytest.mark.parametrize("ntaps", [2, 33, 34, 65, 66, 128, 129, 193, 194, 225])
+@pytest.mark.parametrize("ntaps", [2, 33, 34, 65, 66, 128, 129, 193, 194, 225, 321, 449])
 @pytest.mark.parametrize("dt,taps_type", [("CI16", "COMPLEX"), ("CI16", "REAL"), ("I16", "REAL")])
 def test_umma32t_path_is_bit_exact(oracle, cuda_device, dt, taps_type, ntaps):
     """The operand-swapped formulation (fir_umma32t_kernel): the tap-digit tiles are the A operand and sit in
     tensor memory, the swizzled data planes are the B operand (96 windows per tile), the epilogue reads both digits
     of an output with the 16-lane tensor-memory load shape.  Complex data: windows of 32 outputs, 32-byte-swizzled
     rows; real data: windows of 64 outputs, 64-byte-swizzled rows read 32 bytes at a time.  Tap counts either side
-    of the k-block boundaries up to the tensor-memory limit (8 k-blocks: 225 complex / 193 real), tiles of 3072 /
+    of the k-block boundaries up to the tensor-memory limit (complex: 8 k-blocks = 225 taps; real: 16 = 449), tiles of 3072 /
     6144 outputs ending mid-window, odd output counts (real: the last 32-bit word half used), zero tail, full-scale
     input."""
     code = getattr(oracle, dt)
-    if dt == "I16" and ntaps > 193:
-        pytest.skip("real data: 64 outputs + K - 1 positions must fit 8 k-blocks")
+    if dt == "CI16" and ntaps > 225:
+        pytest.skip("complex data: 32 outputs + K - 1 positions must fit 8 k-blocks")
     cx = taps_type == "COMPLEX"
     rng = np.random.default_rng(ntaps * 17 + 3 + code)
     taps = rng.standard_normal(ntaps) * 0.3 / np.sqrt(ntaps)
@@ -657,7 +657,7 @@ def test_umma32t_falls_back_beyond_its_tensor_memory_budget(oracle, cuda_device)
     assert f.kernel == "fir_umma32_kernel"
     with _with_algo("umma32t"):
         f = FirFilter(oracle.I16, "REAL")
-        f.set_taps(taps[:200])                # real data: 64 + 199 positions are nine k-blocks
+        f.set_taps(np.random.default_rng(6).standard_normal(460) * 0.01)   # real data: 64 + 459 positions are seventeen k-blocks
     assert f.kernel == "fir_umma32_kernel"
 
 
