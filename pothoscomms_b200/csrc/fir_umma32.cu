@@ -15,7 +15,15 @@
 //    2^0 and 2^8) needs separate regions: N = 32 outputs x 2 components x 2 tap digits = 128 columns,
 //    2 regions, 8 accumulators per output instead of 16; two stages fill the 512 TMEM columns.
 //  * NB = ceil((K + 31) / 32) k-blocks; a tile is 128 rows x 32 = 4096 outputs.
-// Warp-specialised like fir_umma_ws_kernel: bulk-copy issuer -> stagers -> MMA issuer -> epilogue.
+// Warp-specialised: bulk-copy issuer -> stagers -> MMA issuer -> epilogue, connected by mbarrier rings.
+//
+// Three kernels share the body below:
+//   fir_umma32_kernel<DC>      the formulation above (data planes = A operand, tap tiles = B operand in shared memory):
+//                              shared-memory-bandwidth bound (8 KB of operands per MMA); what stays on it: filters beyond
+//                              the tap counts of the next two
+//   fir_umma32t_kernel<NB>     operands swapped, complex data: tap tiles = A operand resident in TENSOR MEMORY, data planes =
+//                              B operand, N = 96 windows of 32 outputs; tensor-pipe bound
+//   fir_umma32tr_kernel<NB>    the same on real data: windows of 64 outputs over 64-byte-swizzled planes; HBM bound
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -31,7 +39,7 @@ namespace b200c {
 struct FirUmma32Args {
     const void *in;
     void *out;
-    const void *bmat;    // [DC][NB][N x 32 B] canonical K-major no-swizzle B tiles
+    const void *bmat;    // [DC][NB][N x 32 B] canonical K-major no-swizzle B tiles; swapped kernels: [DC][NB][128 rows x 32 B] A tiles
     long long n_in, n_out, ntiles;
     int K, NB, PL, PLa;  // PL: bytes per plane in use = 4096 + 32 NB; PLa: allocated (multiple of 256)
     int R;               // depth of the bulk-copy landing ring
@@ -39,7 +47,7 @@ struct FirUmma32Args {
 };
 
 constexpr int kU32Tile = 4096;
-// operand-swapped variant (TS = true, complex int16 only): the tap tiles are the A operand and live in
+// operand-swapped variant (TS = true), complex int16: the tap tiles are the A operand and live in
 // TENSOR MEMORY, the data planes are the B operand with N = NW windows per tile.  Columns: two stages x
 // two data limbs x NW accumulators + 8 per (data component, k-block) tap tile <= 512.
 constexpr int kU32tNW = 96, kU32tTile = 32 * kU32tNW, kU32tMaxNB = (512 - 4 * kU32tNW) / 16;
