@@ -87,7 +87,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     const int NB = NBT ? NBT : a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
     unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024); TS: none
     unsigned char *planes = bmat + (TS ? 0 : (size_t)DC * NB * N * 32);   // [2][NPL][PLa], 256-byte aligned, swizzled
-    unsigned char *raw = planes + PS * (size_t)NPL * PLa;            // [R][PL * ESZ]
+    unsigned char *raw = planes + PS * (size_t)NPL * PLa;            // [R][PL * ESZ (+ 16: swapped kernels, misaligned streams)]
     __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[4], planes_empty[4], acc_full[2], acc_empty[2];
     static_assert(PS <= 4, "planes_full / planes_empty hold four stages");
     __shared__ unsigned tmem_base_s;
@@ -132,8 +132,17 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     }
     const long long first = blockIdx.x, step = gridDim.x;
     const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;
-    const bool al = (reinterpret_cast<unsigned long long>(a.in) & 15) == 0;
-    auto bulk_ok = [&](long long tile) { return al && tile * TILE + PL <= a.n_in; };
+    // A stream that does not start on a 16-byte boundary (the block layer's read pointer after any work() call: it has
+    // advanced by n - (K - 1) elements) is still fetched by bulk copies in the swapped kernels: from the aligned address below,
+    // `mis` bytes early and one 16-byte unit longer, and the stagers shift the bytes back (every tile starts a multiple of
+    // 16 bytes after the first, so `mis` is one number per launch).  The original kernel takes guarded element loads.
+    const int mis = (int)(reinterpret_cast<unsigned long long>(a.in) & 15);
+    const bool al = mis == 0;
+    const int slot_bytes = PL * ESZ + (TS ? 16 : 0);
+    auto bulk_ok = [&](long long tile) {
+        if (TS) return (tile * TILE + PL) * ESZ + (mis ? 16 - mis : 0) <= a.n_in * ESZ;
+        return al && tile * TILE + PL <= a.n_in;
+    };
     long long w0 = 0, w1 = 0, t_conv = 0, t_fence = 0;
     const long long t_begin = clock64();
     if (g_umma_watch && blockIdx.x == 0 && tid == 0) {     // barrier addresses, to decode the watchdog's records
@@ -149,8 +158,8 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                 const long long tile = first + (long long)i * step;
                 watched_wait(a.dbg != nullptr, &raw_empty[r], (unsigned)ph ^ 1, w0);
                 if (bulk_ok(tile))
-                    bulk_load(raw + (size_t)r * PL * ESZ, static_cast<const unsigned char *>(a.in) + (size_t)tile * TILE * ESZ,
-                              (unsigned)(PL * ESZ), &raw_full[r]);
+                    bulk_load(raw + (size_t)r * slot_bytes, static_cast<const unsigned char *>(a.in) + (size_t)tile * TILE * ESZ - mis,
+                              (unsigned)(PL * ESZ + (mis ? 16 : 0)), &raw_full[r]);
                 else
                     mbar_arrive(&raw_full[r]);
                 if (++r == R) { r = 0; ph ^= 1; }
@@ -252,9 +261,23 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             watched_wait(a.dbg != nullptr, &raw_full[r], (unsigned)rph, w0);
             watched_wait(a.dbg != nullptr, &planes_empty[s], (unsigned)ph ^ 1, w1);
             unsigned *pl = reinterpret_cast<unsigned *>(planes + (size_t)s * NPL * PLa);
-            const unsigned char *rw = raw + (size_t)r * PL * ESZ;
+            const unsigned char *rw = raw + (size_t)r * slot_bytes;
             const bool timed = a.dbg != nullptr;
             const long long t_c0 = timed ? clock64() : 0;
+            // item q of a landed tile: 16 bytes starting `mis` bytes into unit q of the slot
+            auto fetch = [&](const uint4 *src) {
+                const uint4 lo = src[0];
+                if (mis == 0) return lo;
+                const uint4 hi = src[1];
+                const unsigned bs = (unsigned)(mis & 3) * 8;     // complex samples are 4 bytes: bs == 0 there
+                auto sh = [&](unsigned x, unsigned y) { return DC == 2 ? x : __funnelshift_r(x, y, bs); };
+                switch (mis >> 2) {
+                case 0: return make_uint4(sh(lo.x, lo.y), sh(lo.y, lo.z), sh(lo.z, lo.w), sh(lo.w, hi.x));
+                case 1: return make_uint4(sh(lo.y, lo.z), sh(lo.z, lo.w), sh(lo.w, hi.x), sh(hi.x, hi.y));
+                case 2: return make_uint4(sh(lo.z, lo.w), sh(lo.w, hi.x), sh(hi.x, hi.y), sh(hi.y, hi.z));
+                default: return make_uint4(sh(lo.w, hi.x), sh(hi.x, hi.y), sh(hi.y, hi.z), sh(hi.z, hi.w));
+                }
+            };
             if constexpr (TR) {
                 // real int16: item q = eight samples = 16 raw bytes -> eight bytes (half a 16-byte chunk) of the lo and of the hi
                 // plane, stored with the 64-byte swizzle: chunk c lives at c ^ (c >> 3 & 3).  q + NST is NST / 2 chunks on, a
@@ -272,9 +295,9 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                     const uint4 *src = reinterpret_cast<const uint4 *>(rw) + st;
                     uint4 v[FULL];
 #pragma unroll
-                    for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                    for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
                     uint4 vt = make_uint4(0, 0, 0, 0);
-                    if (REM && st < REM) vt = src[FULL * NST];
+                    if (REM && st < REM) vt = fetch(src + FULL * NST);
 #pragma unroll
                     for (int u = 0; u < FULL; u++) split(v[u], dst + u * (NST * 2));
                     if (REM && st < REM) split(vt, dst + FULL * (NST * 2));
@@ -316,9 +339,9 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                 };
                 uint4 v[FULL];
 #pragma unroll
-                for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
                 uint4 vt = make_uint4(0, 0, 0, 0);
-                if (REM && st < REM) vt = src[FULL * NST];
+                if (REM && st < REM) vt = fetch(src + FULL * NST);
 #pragma unroll
                 for (int u = 0; u < FULL; u++) split(v[u], dst + u * NST);
                 if (REM && st < REM) split(vt, dst + FULL * NST);
@@ -563,7 +586,7 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
     const int PL = (swapped_real ? kU32trTile : swapped ? kU32tTile : kU32Tile) + 32 * NB;
     const int PLa = swapped_real ? (PL + 511) / 512 * 512 : (PL + 255) / 256 * 256;
     // B tiles, two plane stages and at least a 3-deep landing ring must fit
-    if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * (size_t)PL * dc * 2 > 200 * 1024) return B200C_OK;
+    if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * ((size_t)PL * dc * 2 + 16) > 200 * 1024) return B200C_OK;
     std::vector<uint8_t> bm(swapped_real ? 0 : (size_t)dc * NB * N * 32, 0), am(swapped ? (size_t)dc * NB * 128 * 32 : 0, 0);
     for (int d = 0; d < K; d++)
         for (int c = 0; c < tc; c++) {
@@ -683,7 +706,7 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         configured[dev][slot] = true;
     }
     static const int ring = [] { const char *e = std::getenv("B200C_UMMA_RING"); return e ? std::atoi(e) : kU32MaxRing; }();
-    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa, TS), one = (size_t)a.PL * DC * 2;
+    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa, TS), one = (size_t)a.PL * DC * 2 + (TS ? 16 : 0);
     a.R = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, std::min(ring, kU32MaxRing)), (216 * 1024 - fixed) / one));
     // one CTA per SM: its two accumulator stages take all (complex) or half (real) of tensor memory
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);
