@@ -87,7 +87,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     const int NB = NBT ? NBT : a.NB, PL = a.PL, PLa = a.PLa, R = a.R;
     unsigned char *bmat = smem_v;                                    // DC * NB * N * 32 bytes (multiple of 1024); TS: none
     unsigned char *planes = bmat + (TS ? 0 : (size_t)DC * NB * N * 32);   // [2][NPL][PLa], 256-byte aligned, swizzled
-    unsigned char *raw = planes + PS * (size_t)NPL * PLa;            // [R][PL * ESZ (+ 16: swapped kernels, misaligned streams)]
+    unsigned char *raw = planes + PS * (size_t)NPL * PLa;            // [R][PL * ESZ (+ 128: swapped kernels, misaligned streams)]
     __shared__ __align__(8) unsigned long long raw_full[kU32MaxRing], raw_empty[kU32MaxRing], planes_full[4], planes_empty[4], acc_full[2], acc_empty[2];
     static_assert(PS <= 4, "planes_full / planes_empty hold four stages");
     __shared__ unsigned tmem_base_s;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
     // 16 bytes after the first, so `mis` is one number per launch).  The original kernel takes guarded element loads.
     const int mis = (int)(reinterpret_cast<unsigned long long>(a.in) & 15);
     const bool al = mis == 0;
-    const int slot_bytes = PL * ESZ + (TS ? 16 : 0);
+    const int slot_bytes = PL * ESZ + (TS ? 128 : 0);      // one more 16-byte unit, kept on the 128-byte grid of the slots
     auto bulk_ok = [&](long long tile) {
         if (TS) return (tile * TILE + PL) * ESZ + (mis ? 16 - mis : 0) <= a.n_in * ESZ;
         return al && tile * TILE + PL <= a.n_in;
@@ -267,7 +267,6 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
             // item q of a landed tile: 16 bytes starting `mis` bytes into unit q of the slot
             auto fetch = [&](const uint4 *src) {
                 const uint4 lo = src[0];
-                if (mis == 0) return lo;
                 const uint4 hi = src[1];
                 const unsigned bs = (unsigned)(mis & 3) * 8;     // complex samples are 4 bytes: bs == 0 there
                 auto sh = [&](unsigned x, unsigned y) { return DC == 2 ? x : __funnelshift_r(x, y, bs); };
@@ -294,10 +293,16 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                 if (landed) {
                     const uint4 *src = reinterpret_cast<const uint4 *>(rw) + st;
                     uint4 v[FULL];
-#pragma unroll
-                    for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
                     uint4 vt = make_uint4(0, 0, 0, 0);
-                    if (REM && st < REM) vt = fetch(src + FULL * NST);
+                    if (mis == 0) {          // one uniform branch per tile, not per item
+#pragma unroll
+                        for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                        if (REM && st < REM) vt = src[FULL * NST];
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
+                        if (REM && st < REM) vt = fetch(src + FULL * NST);
+                    }
 #pragma unroll
                     for (int u = 0; u < FULL; u++) split(v[u], dst + u * (NST * 2));
                     if (REM && st < REM) split(vt, dst + FULL * (NST * 2));
@@ -338,10 +343,16 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                     p[3 * (PLac / 4)] = prmt_u(u01, u23, 0x7632);
                 };
                 uint4 v[FULL];
-#pragma unroll
-                for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
                 uint4 vt = make_uint4(0, 0, 0, 0);
-                if (REM && st < REM) vt = fetch(src + FULL * NST);
+                if (mis == 0) {              // one uniform branch per tile, not per item
+#pragma unroll
+                    for (int u = 0; u < FULL; u++) v[u] = src[u * NST];
+                    if (REM && st < REM) vt = src[FULL * NST];
+                } else {
+#pragma unroll
+                    for (int u = 0; u < FULL; u++) v[u] = fetch(src + u * NST);
+                    if (REM && st < REM) vt = fetch(src + FULL * NST);
+                }
 #pragma unroll
                 for (int u = 0; u < FULL; u++) split(v[u], dst + u * NST);
                 if (REM && st < REM) split(vt, dst + FULL * NST);
@@ -586,7 +597,7 @@ int fir_umma32_configure(FirUmma32Plan &p, const FirImmaPlan &base, const double
     const int PL = (swapped_real ? kU32trTile : swapped ? kU32tTile : kU32Tile) + 32 * NB;
     const int PLa = swapped_real ? (PL + 511) / 512 * 512 : (PL + 255) / 256 * 256;
     // B tiles, two plane stages and at least a 3-deep landing ring must fit
-    if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * ((size_t)PL * dc * 2 + 16) > 200 * 1024) return B200C_OK;
+    if (u32_fixed_smem(dc, NB, PLa, swapped) + 3 * ((size_t)PL * dc * 2 + 128) > 200 * 1024) return B200C_OK;
     std::vector<uint8_t> bm(swapped_real ? 0 : (size_t)dc * NB * N * 32, 0), am(swapped ? (size_t)dc * NB * 128 * 32 : 0, 0);
     for (int d = 0; d < K; d++)
         for (int c = 0; c < tc; c++) {
@@ -706,7 +717,7 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         configured[dev][slot] = true;
     }
     static const int ring = [] { const char *e = std::getenv("B200C_UMMA_RING"); return e ? std::atoi(e) : kU32MaxRing; }();
-    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa, TS), one = (size_t)a.PL * DC * 2 + (TS ? 16 : 0);
+    const size_t fixed = u32_fixed_smem(DC, a.NB, a.PLa, TS), one = (size_t)a.PL * DC * 2 + (TS ? 128 : 0);
     a.R = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, std::min(ring, kU32MaxRing)), (216 * 1024 - fixed) / one));
     // one CTA per SM: its two accumulator stages take all (complex) or half (real) of tensor memory
     const size_t smem = std::max<size_t>(fixed + a.R * one, 116 * 1024);
