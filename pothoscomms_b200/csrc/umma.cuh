@@ -145,7 +145,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Watchdog of the warp-specialised kernels: a barrier wait longer than ~2 s is a deadlock, and the kernel traps
+// Watchdog of the warp-specialised kernels: a barrier wait longer than ~25 s (a time-sliced GPU can park a kernel for a
+// while; no pipeline hand-off takes milliseconds) is a deadlock, and the kernel traps
 // (the launch fails loudly) instead of hanging the stream.  With B200C_UMMA_DBG the stuck waits are first
 // recorded in host-mapped memory: entry [block * 32 + warp] = shared address of the barrier << 8 | parity << 1 | 1.
 static __device__ unsigned long long *g_umma_watch = nullptr;
@@ -182,14 +183,14 @@ __device__ __forceinline__ void watched_wait(bool timed, unsigned long long *bar
     bool noted = false;
     while (!mbar_try_wait(bar, parity)) {
         const long long waited = clock64() - t0;
-        if (waited > (1ll << 32) && !noted) {
+        if (waited > (1ll << 35) && !noted) {
             noted = true;
             if (g_umma_watch) {
                 g_umma_watch[blockIdx.x * 32 + (threadIdx.x >> 5)] = ((unsigned long long)smem_u32(bar) << 8) | (parity << 1) | 1ull;
                 __threadfence_system();
             }
         }
-        if (waited > (3ll << 31)) __trap();
+        if (waited > (3ll << 34)) __trap();
     }
     acc += clock64() - t0;
 }
