@@ -757,6 +757,11 @@ static int launch_u32(FirUmma32Args a, int sm_count, cudaStream_t stream)
         }
         B200C_CUDA_TRY(cudaMemcpy(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.dbg);
+        {   // the next (untimed) launch must not write through a freed pointer
+            unsigned long long *none = nullptr;
+            B200C_CUDA_TRY(cudaMemcpyToSymbol(g_umma_watch, &none, sizeof(none)));
+        }
+        cudaFreeHost(watch);
         double s8[8] = {0};
         for (int g = 0; g < grid; g++) for (int k = 0; k < 8; k++) s8[k] += (double)h[(size_t)g * 8 + k] / grid;
         double tc = 0, tf = 0;
