@@ -24,6 +24,7 @@ template <typename T> struct FloatTraits {
     using E = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
     using Sc = T;
     using S = E;   // storage type (global / shared memory) == register type
+    using TwS = S; // storage type of the fast kernel's twiddle tables
     static constexpr bool kFixed = false;
     __device__ static E ld(S s) { return s; }
     __device__ static E ldtw(S s) { return s; }
@@ -41,6 +42,7 @@ template <typename T> struct FloatTraits {
 struct Q15Traits {   // fft/_kiss_fft_guts.h:44-124 with FIXED_POINT=16
     using E = short2;
     using S = short2;
+    using TwS = S;
     using Sc = int;  // int16 values carried in 32-bit registers, wrapped at every assignment
     static constexpr bool kFixed = true;
     __device__ static E ld(S s) { return s; }
@@ -82,7 +84,8 @@ struct Q15Lazy {
     static constexpr bool kFixed = true;
     __device__ static int sx(int a) { return (int)(short)a; }
     __device__ static E ld(S u) { return make_int2((int)u, (int)u >> 16); }          // re keeps garbage high bits (lazy)
-    __device__ static E ldtw(S u) { return make_int2(sx((int)u), (int)u >> 16); }    // twiddles multiply: exact
+    using TwS = int2;      // twiddles of the 4096-point kernel are stored unpacked (two ALU-pipe instructions less per load)
+    __device__ static E ldtw(TwS u) { return u; }                                    // twiddles multiply: exact values
     __device__ static S st(E e) { return __byte_perm((unsigned)e.x, (unsigned)e.y, 0x5410); }
     __device__ static int wrap(int a) { return a; }
     __device__ static E mk(int r, int i) { return make_int2(r, i); }
@@ -343,12 +346,12 @@ struct Fft4096Args {
 // The three passes on one transform.  In: v[4*k4 + k5] = x[t + 256*(k4 + 4*k5)] (thread t of
 // 256).  Out: v[A] = X[256*A + t].  F is the CTA's 4096+16 element exchange buffer.
 template <typename Tr, bool CONJ, typename E>
-__device__ __forceinline__ void fft4096_core(E (&v)[16], typename Tr::S *F, const typename Tr::S *__restrict__ tw1_s,
-                                             const typename Tr::S *__restrict__ tw2_s, const typename Tr::S *__restrict__ tw3_s,
+__device__ __forceinline__ void fft4096_core(E (&v)[16], typename Tr::S *F, const typename Tr::TwS *__restrict__ tw1_s,
+                                             const typename Tr::TwS *__restrict__ tw2_s, const typename Tr::TwS *__restrict__ tw3_s,
                                              const int t, const int inverse)
 {
     // twiddle tables and the exchange buffer hold the storage type; registers hold Tr::E
-    struct Tw { const typename Tr::S *__restrict__ p; __device__ __forceinline__ E operator[](int i) const { return Tr::ldtw(p[i]); } };
+    struct Tw { const typename Tr::TwS *__restrict__ p; __device__ __forceinline__ E operator[](int i) const { return Tr::ldtw(p[i]); } };
     const Tw tw1{tw1_s}, tw2{tw2_s}, tw3{tw3_s};
     // pass-1 slot base: t = k0 + 4k1 + 16k2 + 64k3  ->  A = 4k0 + k1, B = 4k2 + k3
     const int A1 = ((t & 3) << 2) | ((t >> 2) & 3), B1 = (((t >> 4) & 3) << 2) | ((t >> 6) & 3);
@@ -410,9 +413,10 @@ __global__ void __launch_bounds__(256, 3) fft4096_kernel(const Fft4096Args a)
     using S = typename Tr::S;
     __shared__ S F[4096 + 16];
     const int t = threadIdx.x;
-    const S *__restrict__ tw1 = static_cast<const S *>(a.tw1);
-    const S *__restrict__ tw2 = static_cast<const S *>(a.tw2);
-    const S *__restrict__ tw3 = static_cast<const S *>(a.tw3);
+    using TwS = typename Tr::TwS;
+    const TwS *__restrict__ tw1 = static_cast<const TwS *>(a.tw1);
+    const TwS *__restrict__ tw2 = static_cast<const TwS *>(a.tw2);
+    const TwS *__restrict__ tw3 = static_cast<const TwS *>(a.tw3);
     for (long long xf = blockIdx.x; xf < a.batch; xf += gridDim.x) {
         const S *in = static_cast<const S *>(a.in) + xf * 4096;
         S *out = static_cast<S *>(a.out) + xf * 4096;
@@ -525,6 +529,18 @@ int fft_plan_create(FftPlan &p, int dtype, size_t nbins, int inverse, size_t sme
         B200C_CUDA_TRY(cudaMemcpy(p.d_fast[0], t1.data(), t1.size(), cudaMemcpyHostToDevice));
         B200C_CUDA_TRY(cudaMemcpy(p.d_fast[1], t2.data(), t2.size(), cudaMemcpyHostToDevice));
         B200C_CUDA_TRY(cudaMemcpy(p.d_fast[2], t3.data(), t3.size(), cudaMemcpyHostToDevice));
+        if (dtype == B200C_CI16) {
+            // the lazy-wrap kernel reads them unpacked: (re, im) as two int32
+            const std::vector<uint8_t> *src[3] = {&t1, &t2, &t3};
+            for (int k = 0; k < 3; k++) {
+                const size_t cnt = src[k]->size() / 4;
+                std::vector<int32_t> w(2 * cnt);
+                const int16_t *s16 = reinterpret_cast<const int16_t *>(src[k]->data());
+                for (size_t i = 0; i < 2 * cnt; i++) w[i] = s16[i];
+                B200C_CUDA_TRY(cudaMalloc(&p.d_fastw[k], w.size() * sizeof(int32_t)));
+                B200C_CUDA_TRY(cudaMemcpy(p.d_fastw[k], w.data(), w.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
+        }
         p.fast = 4096;
     }
 
@@ -545,6 +561,7 @@ void fft_plan_destroy(FftPlan &p)
     if (p.d_scatter) cudaFree(p.d_scatter);
     if (p.d_scratch) cudaFree(p.d_scratch);
     for (auto &f : p.d_fast) { if (f) cudaFree(f); f = nullptr; }
+    for (auto &f : p.d_fastw) { if (f) cudaFree(f); f = nullptr; }
     p.d_tw = nullptr; p.d_scatter = nullptr; p.d_scratch = nullptr;
 }
 
@@ -576,6 +593,7 @@ int fft_launch(FftPlan &p, const void *d_in, void *d_out, size_t batch, int sm_c
         else {
             // lazy-wrap Q15 (bit-identical; B200C_FFT_Q15=packed keeps the per-assignment wrap of round 1 for A/B runs)
             static const bool packed = [] { const char *e = std::getenv("B200C_FFT_Q15"); return e && std::strcmp(e, "packed") == 0; }();
+            if (!packed) { f.tw1 = p.d_fastw[0]; f.tw2 = p.d_fastw[1]; f.tw3 = p.d_fastw[2]; }
             if (packed) fft4096_kernel<Q15Traits><<<grid, 256, 0, stream>>>(f);
             else if (f.inverse) fft4096_kernel<Q15Lazy, 1><<<grid, 256, 0, stream>>>(f);
             else fft4096_kernel<Q15Lazy, 0><<<grid, 256, 0, stream>>>(f);

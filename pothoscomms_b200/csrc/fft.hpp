@@ -31,6 +31,7 @@ struct FftPlan {
     size_t scratch_bytes = 0;
     int fast = 0;               // 0 = generic staged kernel, 4096 = three-pass register kernel
     void *d_fast[3] = {nullptr, nullptr, nullptr};   // per-pass twiddle tables of the fast kernel
+    void *d_fastw[3] = {nullptr, nullptr, nullptr};  // the same unpacked to (int32 re, int32 im): complex int16, lazy-wrap kernel
     bool force_staged = false;  // tests: run the generic staged kernel even when a fast path exists
 };
 
