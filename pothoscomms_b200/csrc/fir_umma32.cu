@@ -325,9 +325,9 @@ __device__ __forceinline__ void fir_umma32_body(const FirUmma32Args &a)
                     }
                 }
             } else if (TS && landed) {
-                // every size is a compile-time constant here: item q = st + 128 u of this thread (four samples: 16 raw
-                // bytes -> one word of each plane) sits 2048 bytes further in the landing slot and 512 bytes further
-                // in the planes (q + 128 is 32 chunks on: the swizzle bit (c >> 3) & 1 does not change)
+                // every size is a compile-time constant here: item q = st + NST u of this thread (four samples: 16 raw
+                // bytes -> one word of each plane) sits 16 NST bytes further in the landing slot and 4 NST bytes further
+                // in the planes (q + NST is NST / 4 chunks on, a multiple of 16: the swizzle bit (c >> 3) & 1 does not change)
                 constexpr int PLc = kU32tTile + 32 * (NBT ? NBT : 1), PLac = (PLc + 255) / 256 * 256, NQc = PLc / 4;
                 constexpr int FULL = NQc / NST, REM = NQc % NST;
                 static_assert(NST % 64 == 0, "q + NST must keep the swizzle bit");
