@@ -992,3 +992,39 @@ def test_umma32t_real_data_over_many_tiles_per_cta(oracle, cuda_device):
         y_ref, _, p_ref = oracle.fir(code, False, taps, 1, 1, seg)
         _compare(oracle, code, y[w0: w0 + p_ref].cpu().numpy(), y_ref, f"window at {w0}")
     assert torch.equal(outs["umma32"][1], outs["umma32t"][1])
+
+
+def test_gpu_equals_oracle_fuzz(oracle, cuda_device):
+    """Property-based sweep through the C ABI: random row of the 18-row type table, rates, tap count and scale (two- to
+    four-digit Q16 taps), window length, zero tail and output capacity -- whatever kernel the dispatch picks must reproduce
+    the oracle: counts exactly, integers bit for bit, floats within the stated tolerance."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    rows = [("F32", "REAL"), ("CF32", "REAL"), ("CF32", "COMPLEX"), ("F64", "REAL"), ("CF64", "REAL"), ("CF64", "COMPLEX"),
+            ("I8", "REAL"), ("CI8", "REAL"), ("CI8", "COMPLEX"), ("I16", "REAL"), ("CI16", "REAL"), ("CI16", "COMPLEX"),
+            ("I32", "REAL"), ("CI32", "REAL"), ("CI32", "COMPLEX"), ("I64", "REAL"), ("CI64", "REAL"), ("CI64", "COMPLEX")]
+    seen = set()
+
+    @settings(max_examples=200, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(row=st.integers(0, len(rows) - 1), M=st.integers(1, 5), L=st.integers(1, 5), ntaps=st.integers(1, 300),
+           n=st.integers(1, 30000), scale=st.sampled_from([0.02, 0.3, 0.7, 150.0]), zero_tail=st.booleans(),
+           cap_frac=st.sampled_from([None, None, 1.0, 0.37]), seed=st.integers(0, 2 ** 31))
+    def check(row, M, L, ntaps, n, scale, zero_tail, cap_frac, seed):
+        dt, taps_type = rows[row]
+        code = getattr(oracle, dt)
+        cx = taps_type == "COMPLEX"
+        rng = np.random.default_rng(seed)
+        taps = rng.uniform(-scale, scale, ntaps) / np.sqrt(ntaps)
+        if cx:
+            taps = taps + 1j * rng.uniform(-scale, scale, ntaps) / np.sqrt(ntaps)
+        x = _rand_input(oracle, code, n, rng, full_scale=True)
+        cap = None if cap_frac is None else int(cap_frac * (n // M + 1) * L)
+        y_ref, c_ref, p_ref = oracle.fir(code, cx, taps, M, L, x, zero_tail=zero_tail, out_capacity=cap)
+        y, cons, prod, f = _run_gpu(code, taps_type, taps, M, L, x, zero_tail=zero_tail, out_capacity=cap)
+        seen.add(f.kernel)
+        what = f"{dt} {taps_type} M={M} L={L} ntaps={ntaps} n={n} scale={scale} zt={zero_tail} cap={cap} [{f.kernel}]"
+        assert (cons, prod) == (c_ref, p_ref), what
+        _compare(oracle, code, y[:prod], y_ref, what, rms_hint=float(np.sqrt(np.mean(np.abs(taps) ** 2) * ntaps)))
+
+    check()
+    assert len(seen) >= 5, seen        # the sweep crosses the dispatch table
